@@ -1,0 +1,18 @@
+"""driftdiffusionpoissonsystems.jl_b200 -- B200-native hot path of DriftDiffusionPoissonSystems.jl.
+
+Import as ``import ddps_b200`` (the root-level shim maps that name onto this directory, whose
+literal name is not a valid Python identifier).
+
+Public surface (mirrors the reference's exports, ``src:6-7``):
+    Mesh, read_mesh, construct_mesh4, construct_mesh8, construct_mesh, structured_mesh,
+    solve_ddpe, solve_semlin_poisson, aquire_boundary, SinhRHS, PolyRHS, Session
+"""
+from .mesh import Mesh, read_mesh, construct_mesh4, construct_mesh8, construct_mesh, structured_mesh
+from .functors import SinhRHS, PolyRHS
+from .api import (Session, DDPSError, solve_ddpe, solve_semlin_poisson, aquire_boundary, dirichlet_nodes,
+                  neumann_edges)
+from . import problems
+
+__all__ = ["Mesh", "read_mesh", "construct_mesh4", "construct_mesh8", "construct_mesh", "structured_mesh",
+           "solve_ddpe", "solve_semlin_poisson", "aquire_boundary", "SinhRHS", "PolyRHS", "Session", "DDPSError",
+           "problems", "dirichlet_nodes", "neumann_edges"]

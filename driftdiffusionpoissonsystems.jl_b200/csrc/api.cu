@@ -1,0 +1,943 @@
+// C ABI (include/ddps.h) + the device-resident Gummel / Newton drivers.
+//
+//   ddps_ddpe_begin/step  <->  solve_ddpe's loop + G + Vsolve + uvsolve (src:630-658, 596-601, 292-425, 433-589)
+//   ddps_solve_semlin     <->  solve_semlin_poisson (src:895-1097)
+//
+// Host code here only sequences kernels and reads back scalars (residual norms, iteration counts);
+// every array stays on the device between iterations.
+#include <chrono>
+#include <cstdio>
+#include <map>
+
+#include "ddps_internal.cuh"
+
+using namespace ddps;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+int dev_alloc(Context* ctx, T** p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  DDPS_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+
+template <typename T>
+void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+void free_mesh(Context* ctx) {
+  free_pattern(ctx);
+  dev_free(ctx->xy); dev_free(ctx->elem); dev_free(ctx->d_own_glob);
+  dev_free(ctx->isD);
+  for (int f = 0; f < 4; ++f) { dev_free(ctx->gD[f]); ctx->have_D[f] = false; }
+  for (int s = 0; s < 64; ++s) { dev_free(ctx->coeff[s]); ctx->coeff_len[s] = 0; }
+  dev_free(ctx->val_base); dev_free(ctx->val_op); dev_free(ctx->lift);
+  dev_free(ctx->V); dev_free(ctx->U); dev_free(ctx->W); dev_free(ctx->V0); dev_free(ctx->U0); dev_free(ctx->W0);
+  dev_free(ctx->Unew); dev_free(ctx->EH); dev_free(ctx->EHi); dev_free(ctx->E3); dev_free(ctx->gw);
+  dev_free(ctx->b); dev_free(ctx->resid); dev_free(ctx->dinv); dev_free(ctx->x); dev_free(ctx->r); dev_free(ctx->q);
+  dev_free(ctx->p); dev_free(ctx->partials);
+  if (ctx->halo.send_idx) { cudaFree(ctx->halo.send_idx); ctx->halo.send_idx = nullptr; }
+  if (ctx->halo.send_buf) { cudaFree(ctx->halo.send_buf); ctx->halo.send_buf = nullptr; }
+  ctx->halo.nneigh = 0; ctx->halo.peer.clear(); ctx->halo.send_off.clear(); ctx->halo.recv_off.clear(); ctx->halo.nsend = 0;
+  ctx->loc2glob.clear(); ctx->elem_glob.clear(); ctx->Dset.clear();
+  ctx->have_mesh = false; ctx->base_ready = false; ctx->ddpe_active = false;
+}
+
+__global__ void k_count_negative(const int4* __restrict__ elem, const double2* __restrict__ xy, int nme, int* out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nme) return;
+  int4 el = elem[e];
+  double2 q1 = xy[el.x], q2 = xy[el.y], q3 = xy[el.z];
+  double ar = ((q2.x - q3.x) * (q3.y - q1.y) - (q2.y - q3.y) * (q3.x - q1.x)) / 2.0;
+  if (ar < 0.0) atomicAdd(out, 1);
+}
+
+__global__ void k_scatter_global(int n, const long long* __restrict__ glob, const double* __restrict__ src,
+                                 double* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[glob[i]] = src[i];
+}
+
+// upload a host array through the stream (pageable source: the copy is staged by the driver)
+template <typename T>
+int upload(Context* ctx, T* dst, const T* src, size_t n) {
+  if (!n) return 0;
+  DDPS_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int require_mesh(Context* ctx) {
+  if (!ctx->have_mesh) { ctx->fail(DDPS_ERR_STATE, "no mesh: call ddps_mesh_set first"); return DDPS_ERR_STATE; }
+  return 0;
+}
+
+// Fill a local [n_loc] array from a global [nq] host array.
+int upload_nodal(Context* ctx, double* dst, const double* src_global) {
+  if (ctx->loc2glob.empty()) return upload(ctx, dst, src_global, (size_t)ctx->n_loc);
+  std::vector<double> tmp(ctx->n_loc);
+  for (int i = 0; i < ctx->n_loc; ++i) tmp[i] = src_global[ctx->loc2glob[i]];
+  int rc = upload(ctx, dst, tmp.data(), tmp.size());
+  if (rc) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Copy the owned part of a local field into a global [nq] host array (all ranks get the full field).
+int download_nodal(Context* ctx, const double* src_local, double* dst_global) {
+  if (ctx->nranks == 1) {
+    DDPS_CUDA(cudaMemcpyAsync(dst_global, src_local, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  double* g = nullptr;
+  DDPS_CUDA(cudaMalloc(&g, (size_t)ctx->nq_global * sizeof(double)));
+  cudaMemsetAsync(g, 0, (size_t)ctx->nq_global * sizeof(double), ctx->stream);
+  if (ctx->n_own) k_scatter_global<<<(ctx->n_own + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_own, ctx->d_own_glob, src_local, g);
+  int rc = 0;
+  const int64_t chunk = 1 << 28;
+  for (int64_t o = 0; o < ctx->nq_global && !rc; o += chunk)
+    rc = allreduce_sum(ctx, g + o, (int)std::min<int64_t>(chunk, ctx->nq_global - o));
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(dst_global, g, (size_t)ctx->nq_global * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->fail(DDPS_ERR_CUDA, cudaGetErrorString(e)); rc = DDPS_ERR_CUDA; }
+  }
+  cudaFree(g);
+  return rc;
+}
+
+AsmArgs base_args(Context* ctx) {
+  AsmArgs a;
+  memset(&a, 0, sizeof(a));
+  const Pattern& P = ctx->pat;
+  a.nrows = P.nrows; a.nslices = P.nslices; a.slice_ptr = P.slice_ptr; a.col = P.col;
+  a.inc_slice_ptr = P.inc_slice_ptr; a.inc = P.inc; a.xy = ctx->xy; a.elem = ctx->elem; a.isD = ctx->isD;
+  a.partial_max = ctx->partials; a.scal = ctx->scal;
+  return a;
+}
+
+int need_coeff(Context* ctx, int slot, const char* name) {
+  if (!ctx->coeff[slot]) { ctx->fail(DDPS_ERR_STATE, std::string("coefficient not set: ") + name); return DDPS_ERR_STATE; }
+  return 0;
+}
+
+// MV_assemble (src:229-287) / the constant semlin stiffness (src:924-1028)
+int assemble_base(Context* ctx, bool semlin) {
+  int rc;
+  AsmArgs a = base_args(ctx);
+  int field = semlin ? DDPS_FIELD_SCALAR : DDPS_FIELD_V;
+  if (!ctx->have_D[field]) { ctx->fail(DDPS_ERR_STATE, "Dirichlet data not set"); return DDPS_ERR_STATE; }
+  if (semlin) {
+    if ((rc = need_coeff(ctx, DDPS_COEFF_A11, "A11")) || (rc = need_coeff(ctx, DDPS_COEFF_A22, "A22"))) return rc;
+    a.phx = ctx->coeff[DDPS_COEFF_A22];   // x components pair with A[4], src:926
+    a.phy = ctx->coeff[DDPS_COEFF_A11];
+  } else {
+    if ((rc = need_coeff(ctx, DDPS_COEFF_LAMBDA2, "LAMBDA2"))) return rc;
+    a.phx = a.phy = ctx->coeff[DDPS_COEFF_LAMBDA2];
+  }
+  a.gD = ctx->gD[field];
+  a.out_val = ctx->val_base;
+  a.lift_out = ctx->lift;
+  if ((rc = launch_assemble_base(ctx, a))) return rc;
+  ctx->base_ready = true;
+  ctx->base_is_semlin = semlin;
+  return 0;
+}
+
+// One Newton-system assembly at the iterate Vit: A = base - J0(V), b(V), F = base*V - b, ||F||_inf.
+int assemble_newton(Context* ctx, bool semlin, double delta, const double* Vit, const double* u, const double* v) {
+  int rc;
+  AsmArgs a = base_args(ctx);
+  a.base_val = ctx->val_base; a.lift_in = ctx->lift; a.gw = ctx->gw; a.xvec = Vit;
+  a.out_val = ctx->val_op; a.dinv = ctx->dinv; a.b = ctx->b; a.resid = ctx->resid;
+  if (!semlin) {
+    if ((rc = need_coeff(ctx, DDPS_COEFF_C_MID, "C_MID"))) return rc;
+    if ((rc = launch_prep_poisson(ctx, Vit, u, v, delta * delta))) return rc;
+    a.gD = ctx->gD[DDPS_FIELD_V];
+    a.fu = u; a.fv = v; a.EH = ctx->EH; a.EHi = ctx->EHi; a.mid = ctx->coeff[DDPS_COEFF_C_MID];
+    a.par0 = delta * delta;
+    return launch_assemble_newton(ctx, a, RHS_DDP);
+  }
+  if ((rc = launch_prep_semlin(ctx, Vit))) return rc;
+  a.gD = ctx->gD[DDPS_FIELD_SCALAR];
+  a.EH = Vit;
+  a.nodal_const = ctx->coeff[DDPS_COEFF_NEUMANN];
+  if (ctx->functor_kind == DDPS_FUNCTOR_SINH) {
+    if ((rc = need_coeff(ctx, DDPS_COEFF_H_MID, "H_MID"))) return rc;
+    a.mid = ctx->coeff[DDPS_COEFF_H_MID];
+    a.par0 = ctx->functor_par[0]; a.par1 = ctx->functor_par[1];
+    return launch_assemble_newton(ctx, a, RHS_SINH);
+  } else if (ctx->functor_kind == DDPS_FUNCTOR_POLY) {
+    int deg = (int)ctx->functor_par[0];
+    for (int k = 0; k <= deg; ++k) {
+      if ((rc = need_coeff(ctx, DDPS_COEFF_POLY_MID0 + k, "POLY_MID")) || (rc = need_coeff(ctx, DDPS_COEFF_POLY_NODE0 + k, "POLY_NODE")))
+        return rc;
+      a.mid_poly[k] = ctx->coeff[DDPS_COEFF_POLY_MID0 + k];
+    }
+    a.par0 = (double)deg;
+    return launch_assemble_newton(ctx, a, RHS_POLY);
+  }
+  ctx->fail(DDPS_ERR_STATE, "no functor registered for f,g (arbitrary closures cannot run on the device; no CPU fallback)");
+  return DDPS_ERR_STATE;
+}
+
+// uvsolve's system (src:433-588).  which = FIELD_U: (V, tau_p, tau_n, mu_p, u0, v0);
+// which = FIELD_W: (-V, tau_n, tau_p, mu_n, v0, u0) exactly as G passes them (src:598-599).
+int assemble_uv(Context* ctx, int which, int rec_mode, double tau_p, double tau_n, const double* V, const double* u0,
+                const double* v0) {
+  int rc;
+  const bool isU = (which == DDPS_FIELD_U);
+  int mu_slot = isU ? DDPS_COEFF_MU_P : DDPS_COEFF_MU_N;
+  if ((rc = need_coeff(ctx, mu_slot, isU ? "MU_P" : "MU_N"))) return rc;
+  if (!ctx->have_D[which]) { ctx->fail(DDPS_ERR_STATE, "Dirichlet data for u/v not set"); return DDPS_ERR_STATE; }
+  if ((rc = launch_prep_uv(ctx, isU ? 1.0 : -1.0, V, nullptr, u0, v0, tau_p, tau_n, rec_mode))) return rc;
+  AsmArgs a = base_args(ctx);
+  a.gD = ctx->gD[which];
+  a.phx = ctx->coeff[mu_slot]; a.E3 = ctx->E3; a.gw = ctx->gw;
+  a.fu = isU ? u0 : v0; a.fv = isU ? v0 : u0;   // callee's (u0, v0)
+  a.EH = ctx->EH; a.EHi = ctx->EHi;
+  a.par0 = isU ? tau_p : tau_n; a.par1 = isU ? tau_n : tau_p;   // callee's (tau_p, tau_n)
+  a.out_val = ctx->val_op; a.dinv = ctx->dinv; a.b = ctx->b;
+  if (rec_mode == DDPS_REC_SHOCKLEY) return launch_assemble_uv(ctx, a, RHS_SRH, true);
+  return launch_assemble_uv(ctx, a, RHS_ZERO, false);
+}
+
+struct EventTimer {
+  Context* ctx;
+  cudaEvent_t a, b;
+  EventTimer(Context* c, cudaEvent_t a_, cudaEvent_t b_) : ctx(c), a(a_), b(b_) { cudaEventRecord(a, c->stream); }
+  void stop() { cudaEventRecord(b, ctx->stream); }
+  double ms() { float t = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&t, a, b); return t; }
+};
+
+// Vsolve (src:292-425): Newton from V=0 on MV*V = b(V) at frozen (u0,v0).
+int vsolve(Context* ctx) {
+  int rc;
+  const int n = ctx->n_own;
+  DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:311
+  int newton = 0;
+  const int cap = ctx->opts.max_newton > 0 ? ctx->opts.max_newton : 1000;
+  while (true) {
+    EventTimer ta(ctx, ctx->ev0, ctx->ev1);
+    if ((rc = assemble_newton(ctx, false, ctx->delta, ctx->V, ctx->U0, ctx->W0))) return rc;
+    ta.stop();
+    double res;
+    if ((rc = fetch_resid_norm(ctx, &res))) return rc;
+    ctx->stats.t_asm_ms += ta.ms();
+    if (!(res > ctx->tol)) break;                                                            // src:368
+    if (newton >= cap) { ctx->fail(DDPS_ERR_NOCONV, "Vsolve: Newton iteration cap reached"); return DDPS_ERR_NOCONV; }
+    EventTimer tp(ctx, ctx->ev2, ctx->ev3);
+    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, ctx->opts.lin_max_it,
+                   nullptr, nullptr);
+    tp.stop();
+    ctx->stats.t_pcg_ms += tp.ms();
+    if (rc) return rc;
+    if ((rc = launch_axpy(ctx, -1.0, ctx->x, ctx->V, n))) return rc;                         // src:394-395
+    if ((rc = halo_exchange(ctx, ctx->V))) return rc;
+    ++newton;
+  }
+  ctx->stats.newton_total += newton;
+  ctx->hist_newton.push_back((double)newton);
+  return 0;
+}
+
+int uvsolve(Context* ctx, int which) {
+  int rc;
+  EventTimer ta(ctx, ctx->ev0, ctx->ev1);
+  if ((rc = assemble_uv(ctx, which, ctx->rec_mode, ctx->tau_p, ctx->tau_n, ctx->V, ctx->U0, ctx->W0))) return rc;
+  ta.stop();
+  double* field = (which == DDPS_FIELD_U) ? ctx->U : ctx->W;
+  EventTimer tp(ctx, ctx->ev2, ctx->ev3);
+  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, field, ctx->opts.warm_start != 0, ctx->opts.lin_rtol,
+                 ctx->opts.lin_max_it, nullptr, nullptr);                                     // src:588
+  tp.stop();
+  ctx->stats.t_pcg_ms += tp.ms();
+  ctx->stats.t_asm_ms += ta.ms();
+  if (rc) return rc;
+  return halo_exchange(ctx, field);
+}
+
+// One application of the Gummel map G (src:596-601) + the update norm (src:653).
+int gummel_step(Context* ctx, double* control) {
+  int rc;
+  const size_t bytes = (size_t)ctx->n_loc * sizeof(double);
+  DDPS_CUDA(cudaMemcpyAsync(ctx->U0, ctx->U, bytes, cudaMemcpyDeviceToDevice, ctx->stream));   // src:650
+  DDPS_CUDA(cudaMemcpyAsync(ctx->W0, ctx->W, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  DDPS_CUDA(cudaMemcpyAsync(ctx->V0, ctx->V, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  if ((rc = vsolve(ctx))) return rc;                   // src:597
+  if ((rc = uvsolve(ctx, DDPS_FIELD_U))) return rc;    // src:598
+  if ((rc = uvsolve(ctx, DDPS_FIELD_W))) return rc;    // src:599 (uses the OLD u0)
+  return launch_max_abs_diff3(ctx, ctx->U, ctx->U0, ctx->W, ctx->W0, ctx->V, ctx->V0, ctx->n_own, control);
+}
+
+void reset_stats(Context* ctx) {
+  int neg = ctx->stats.n_negative_area;
+  double ts = ctx->stats.t_setup_ms;
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.n_negative_area = neg;
+  ctx->stats.t_setup_ms = ts;
+  ctx->hist_outer.clear(); ctx->hist_newton.clear(); ctx->hist_pcg.clear();
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int ddps_version(void) { return DDPS_VERSION; }
+
+const char* ddps_last_error(const ddps_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+void ddps_default_opts(ddps_solver_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->lin_rtol = 1e-13;
+  o->newton_eta = 1e-10;
+  o->lin_max_it = 200000;
+  o->max_newton = 0;
+  o->max_gummel = 0;
+  o->check_every = 32;
+  o->warm_start = 1;
+  o->verbose = 0;
+}
+
+int ddps_ctx_create(ddps_ctx** out, int device) {
+  if (!out) return DDPS_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device available (this library has no CPU fallback): ") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return DDPS_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return DDPS_ERR_ARG; }
+  ddps_ctx* ctx = new ddps_ctx();
+  ctx->device = device;
+  ddps_default_opts(&ctx->opts);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_err = std::string(what) + ": " + cudaGetErrorString(err);
+    delete ctx;
+    return DDPS_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  ctx->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
+  if ((e = cudaMalloc(&ctx->scal, sizeof(PcgScalars))) != cudaSuccess) return bail("cudaMalloc", e);
+  cudaMemset(ctx->scal, 0, sizeof(PcgScalars));
+  if ((e = cudaMallocHost(&ctx->scal_host, sizeof(PcgScalars))) != cudaSuccess) return bail("cudaMallocHost", e);
+  memset(ctx->scal_host, 0, sizeof(PcgScalars));
+  *out = ctx;
+  return DDPS_OK;
+}
+
+int ddps_ctx_destroy(ddps_ctx* ctx) {
+  if (!ctx) return DDPS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_mesh(ctx);
+  comm_destroy(ctx);
+  cudaFree(ctx->scal);
+  cudaFreeHost(ctx->scal_host);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return DDPS_OK;
+}
+
+int ddps_set_opts(ddps_ctx* ctx, const ddps_solver_opts* o) {
+  if (!ctx || !o) return DDPS_ERR_ARG;
+  if (!(o->lin_rtol >= 0) || !(o->newton_eta >= 0)) { ctx->fail(DDPS_ERR_ARG, "negative tolerance"); return DDPS_ERR_ARG; }
+  ctx->opts = *o;
+  if (ctx->opts.lin_max_it <= 0) ctx->opts.lin_max_it = 200000;
+  if (ctx->opts.check_every <= 0) ctx->opts.check_every = 32;
+  return DDPS_OK;
+}
+
+int ddps_comm_unique_id(char id128[128]) { return comm_unique_id(id128); }
+
+int ddps_comm_init(ddps_ctx* ctx, const char id128[128], int rank, int nranks) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->have_mesh) { ctx->fail(DDPS_ERR_STATE, "ddps_comm_init must precede ddps_mesh_set"); return DDPS_ERR_STATE; }
+  return comm_init(ctx, id128, rank, nranks);
+}
+
+int ddps_partition_nodes(const double* nodes, int64_t nq, int nparts, int32_t* owner) {
+  if (!nodes || !owner || nq < 0 || nparts < 1) return DDPS_ERR_ARG;
+  partition_nodes_rcb(nodes, nq, nparts, owner);
+  return DDPS_OK;
+}
+
+int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t* elements, int64_t nme) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (!nodes || !elements || nq <= 0 || nme <= 0) { ctx->fail(DDPS_ERR_ARG, "empty mesh"); return DDPS_ERR_ARG; }
+  if (nq >= (1LL << 31) - 64) { ctx->fail(DDPS_ERR_ARG, "too many nodes"); return DDPS_ERR_ARG; }
+  double t0 = now_ms();
+  free_mesh(ctx);
+  ctx->nq_global = nq; ctx->nme_global = nme;
+  int rc;
+  std::vector<int4> hel;
+  if (ctx->nranks == 1) {
+    ctx->n_own = ctx->n_loc = (int)nq;
+    if (nme >= (1LL << 29)) { ctx->fail(DDPS_ERR_ARG, "too many triangles for one GPU"); return DDPS_ERR_ARG; }
+    ctx->nme = (int)nme;
+    hel.resize(nme);
+    for (int64_t e = 0; e < nme; ++e) {
+      const int64_t* c = elements + 5 * e;
+      int64_t a = c[0] - 1, b = c[1] - 1, d = c[2] - 1;
+      if (a < 0 || b < 0 || d < 0 || a >= nq || b >= nq || d >= nq) {
+        ctx->fail(DDPS_ERR_ARG, "element " + std::to_string(e + 1) + " references a node outside 1..nq");
+        return DDPS_ERR_ARG;
+      }
+      hel[e] = make_int4((int)a, (int)b, (int)d, (int)c[4]);
+    }
+    if ((rc = dev_alloc(ctx, &ctx->xy, (size_t)nq))) return rc;
+    if ((rc = upload(ctx, (double*)ctx->xy, nodes, (size_t)2 * nq))) return rc;
+  } else {
+    // ---- node partition by recursive coordinate bisection; every rank computes the same owner[] ----
+    std::vector<int32_t> owner(nq);
+    partition_nodes_rcb(nodes, nq, ctx->nranks, owner.data());
+    const int me = ctx->rank;
+    std::vector<int32_t> g2l(nq, -1);
+    std::vector<std::pair<int, int64_t>> ghosts, sends;   // (peer, global id)
+    std::vector<int64_t> eg;
+    for (int64_t e = 0; e < nme; ++e) {
+      const int64_t* c = elements + 5 * e;
+      int64_t g[3] = {c[0] - 1, c[1] - 1, c[2] - 1};
+      for (int k = 0; k < 3; ++k)
+        if (g[k] < 0 || g[k] >= nq) {
+          ctx->fail(DDPS_ERR_ARG, "element " + std::to_string(e + 1) + " references a node outside 1..nq");
+          return DDPS_ERR_ARG;
+        }
+      int o[3] = {owner[g[0]], owner[g[1]], owner[g[2]]};
+      if (o[0] != me && o[1] != me && o[2] != me) continue;
+      eg.push_back(e);
+      for (int k = 0; k < 3; ++k) {
+        if (o[k] != me) ghosts.emplace_back(o[k], g[k]);
+        else
+          for (int j = 0; j < 3; ++j)
+            if (o[j] != me) sends.emplace_back(o[j], g[k]);
+      }
+    }
+    auto uniq = [](std::vector<std::pair<int, int64_t>>& v) {
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+    };
+    uniq(ghosts); uniq(sends);
+    int n_own = 0;
+    for (int64_t i = 0; i < nq; ++i) if (owner[i] == me) ++n_own;
+    ctx->n_own = n_own;
+    ctx->n_loc = n_own + (int)ghosts.size();
+    ctx->loc2glob.resize(ctx->n_loc);
+    int k = 0;
+    for (int64_t i = 0; i < nq; ++i) if (owner[i] == me) { g2l[i] = k; ctx->loc2glob[k] = i; ++k; }
+    for (auto& pr : ghosts) { g2l[pr.second] = k; ctx->loc2glob[k] = pr.second; ++k; }
+    // halo plan: neighbours = union of peers in ghosts and sends
+    std::vector<int> peers;
+    for (auto& pr : ghosts) peers.push_back(pr.first);
+    for (auto& pr : sends) peers.push_back(pr.first);
+    std::sort(peers.begin(), peers.end());
+    peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+    HaloPlan& H = ctx->halo;
+    H.nneigh = (int)peers.size(); H.peer = peers;
+    H.send_off.assign(H.nneigh + 1, 0); H.recv_off.assign(H.nneigh + 1, 0);
+    std::vector<int> sidx;
+    for (int j = 0; j < H.nneigh; ++j) {
+      for (auto& pr : sends) if (pr.first == peers[j]) sidx.push_back(g2l[pr.second]);
+      H.send_off[j + 1] = (int)sidx.size();
+      int cnt = 0;
+      for (auto& pr : ghosts) if (pr.first == peers[j]) ++cnt;
+      H.recv_off[j + 1] = H.recv_off[j] + cnt;   // ghosts are sorted by (peer, gid) = local ghost order
+    }
+    H.nsend = (int)sidx.size();
+    if ((rc = dev_alloc(ctx, &H.send_idx, sidx.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &H.send_buf, sidx.size()))) return rc;
+    if ((rc = upload(ctx, H.send_idx, sidx.data(), sidx.size()))) return rc;
+    // local mesh
+    ctx->nme = (int)eg.size();
+    ctx->elem_glob = eg;
+    hel.resize(eg.size());
+    for (size_t i = 0; i < eg.size(); ++i) {
+      const int64_t* c = elements + 5 * eg[i];
+      hel[i] = make_int4(g2l[c[0] - 1], g2l[c[1] - 1], g2l[c[2] - 1], (int)c[4]);
+    }
+    std::vector<double> hxy((size_t)2 * ctx->n_loc);
+    for (int i = 0; i < ctx->n_loc; ++i) { hxy[2 * i] = nodes[2 * ctx->loc2glob[i]]; hxy[2 * i + 1] = nodes[2 * ctx->loc2glob[i] + 1]; }
+    if ((rc = dev_alloc(ctx, &ctx->xy, (size_t)ctx->n_loc))) return rc;
+    if ((rc = upload(ctx, (double*)ctx->xy, hxy.data(), hxy.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_own_glob, (size_t)ctx->n_own))) return rc;
+    std::vector<long long> og(ctx->loc2glob.begin(), ctx->loc2glob.begin() + ctx->n_own);
+    if ((rc = upload(ctx, ctx->d_own_glob, og.data(), og.size()))) return rc;
+    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if ((rc = dev_alloc(ctx, &ctx->elem, (size_t)ctx->nme))) return rc;
+  if ((rc = upload(ctx, ctx->elem, hel.data(), hel.size()))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  hel.clear(); hel.shrink_to_fit();
+
+  // orientation report (Q2: the mass weights use the SIGNED area, src:375)
+  {
+    int* d_neg = nullptr;
+    DDPS_CUDA(cudaMalloc(&d_neg, sizeof(int)));
+    cudaMemsetAsync(d_neg, 0, sizeof(int), ctx->stream);
+    if (ctx->nme) k_count_negative<<<(ctx->nme + 255) / 256, 256, 0, ctx->stream>>>(ctx->elem, ctx->xy, ctx->nme, d_neg);
+    int neg = 0;
+    cudaMemcpyAsync(&neg, d_neg, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_neg);
+    ctx->stats.n_negative_area = neg;
+  }
+  if ((rc = build_pattern(ctx))) { free_mesh(ctx); return rc; }
+
+  const size_t nl = ctx->n_loc, no = ctx->n_own, ne = (size_t)ctx->pat.nentries;
+  if ((rc = dev_alloc(ctx, &ctx->isD, nl))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(ctx->isD, 0, nl, ctx->stream));
+  for (int f = 0; f < 4; ++f) {
+    if ((rc = dev_alloc(ctx, &ctx->gD[f], nl))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(ctx->gD[f], 0, nl * sizeof(double), ctx->stream));
+  }
+  double** nodal[] = {&ctx->V, &ctx->U, &ctx->W, &ctx->V0, &ctx->U0, &ctx->W0, &ctx->Unew, &ctx->EH, &ctx->EHi, &ctx->E3,
+                      &ctx->gw, &ctx->p};
+  for (double** pp : nodal) {
+    if ((rc = dev_alloc(ctx, pp, nl))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(*pp, 0, nl * sizeof(double), ctx->stream));
+  }
+  double** owned[] = {&ctx->b, &ctx->resid, &ctx->dinv, &ctx->x, &ctx->r, &ctx->q, &ctx->lift};
+  for (double** pp : owned) {
+    if ((rc = dev_alloc(ctx, pp, no))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(*pp, 0, no * sizeof(double), ctx->stream));
+  }
+  if ((rc = dev_alloc(ctx, &ctx->val_base, ne))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->val_op, ne))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(ctx->val_base, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
+  DDPS_CUDA(cudaMemsetAsync(ctx->val_op, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
+  int asm_blocks = (ctx->pat.nslices * 32 + kAsmBlock - 1) / kAsmBlock;
+  ctx->partial_cap = std::max(asm_blocks, 4 * ctx->num_sms * 16) + 64;
+  if ((rc = dev_alloc(ctx, &ctx->partials, (size_t)ctx->partial_cap))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_mesh = true;
+  ctx->stats.t_setup_ms = now_ms() - t0;
+  return DDPS_OK;
+}
+
+int ddps_dirichlet_set(ddps_ctx* ctx, int field, const int64_t* idx1, const double* val, int64_t nd) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (field < 0 || field > 3 || nd < 0 || (nd > 0 && (!idx1 || !val))) { ctx->fail(DDPS_ERR_ARG, "bad Dirichlet arguments"); return DDPS_ERR_ARG; }
+  std::vector<int64_t> ids(nd);
+  for (int64_t i = 0; i < nd; ++i) {
+    ids[i] = idx1[i] - 1;
+    if (ids[i] < 0 || ids[i] >= ctx->nq_global) { ctx->fail(DDPS_ERR_ARG, "Dirichlet node outside 1..nq"); return DDPS_ERR_ARG; }
+  }
+  std::vector<int64_t> sorted = ids;
+  std::sort(sorted.begin(), sorted.end());
+  if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) {
+    // Q5: the reference would put 2 on the diagonal and double-subtract the lifting; not supported.
+    ctx->fail(DDPS_ERR_ARG, "a Dirichlet node is listed twice (conflicting boundary values at a shared node are not supported)");
+    return DDPS_ERR_ARG;
+  }
+  // solve_ddpe eliminates the node set of the V bddata for all three equations (src:640 -> 598-599);
+  // the u/v value lists must cover exactly that set (the reference throws DimensionMismatch at src:563).
+  if (field == DDPS_FIELD_SCALAR) {
+    ctx->have_D[0] = ctx->have_D[1] = ctx->have_D[2] = false;   // isD is shared: a new scalar set invalidates the DDP sets
+  } else {
+    ctx->have_D[DDPS_FIELD_SCALAR] = false;
+    bool any = false;
+    for (int f = 0; f < 3; ++f) any = any || (f != field && ctx->have_D[f]);
+    if (any && sorted != ctx->Dset) {
+      ctx->fail(DDPS_ERR_ARG, "Dirichlet node sets of V, u and v differ (reference: DimensionMismatch at src:563)");
+      return DDPS_ERR_ARG;
+    }
+  }
+  ctx->Dset = sorted;
+  std::vector<double> gl(ctx->nq_global, 0.0);
+  std::vector<unsigned char> fl(ctx->nq_global, 0);
+  for (int64_t i = 0; i < nd; ++i) { gl[ids[i]] = val[i]; fl[ids[i]] = 1; }
+  std::vector<unsigned char> lfl(ctx->n_loc);
+  std::vector<double> lg(ctx->n_loc);
+  for (int i = 0; i < ctx->n_loc; ++i) {
+    int64_t g = ctx->loc2glob.empty() ? i : ctx->loc2glob[i];
+    lfl[i] = fl[g]; lg[i] = gl[g];
+  }
+  if ((rc = upload(ctx, ctx->isD, lfl.data(), lfl.size()))) return rc;
+  if ((rc = upload(ctx, ctx->gD[field], lg.data(), lg.size()))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_D[field] = true;
+  ctx->base_ready = false;
+  return DDPS_OK;
+}
+
+int ddps_coeff_set(ddps_ctx* ctx, int slot, const double* data, int64_t len) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (slot < 0 || slot >= 64 || !data) { ctx->fail(DDPS_ERR_ARG, "bad coefficient slot"); return DDPS_ERR_ARG; }
+  int kind;  // 0: [nme], 1: [3,nme], 2: [nq]
+  if (slot == DDPS_COEFF_C_MID || slot == DDPS_COEFF_H_MID || (slot >= DDPS_COEFF_POLY_MID0 && slot < DDPS_COEFF_POLY_MID0 + kMaxPoly)) kind = 1;
+  else if (slot == DDPS_COEFF_NEUMANN || (slot >= DDPS_COEFF_POLY_NODE0 && slot < DDPS_COEFF_POLY_NODE0 + kMaxPoly)) kind = 2;
+  else if (slot <= DDPS_COEFF_A22) kind = 0;
+  else { ctx->fail(DDPS_ERR_ARG, "unknown coefficient slot"); return DDPS_ERR_ARG; }
+  int64_t want = kind == 0 ? ctx->nme_global : kind == 1 ? 3 * ctx->nme_global : ctx->nq_global;
+  if (len != want) { ctx->fail(DDPS_ERR_ARG, "coefficient array has the wrong length"); return DDPS_ERR_ARG; }
+  for (int64_t i = 0; i < len; ++i)
+    if (!std::isfinite(data[i])) { ctx->fail(DDPS_ERR_ARG, "coefficient array contains a non-finite value"); return DDPS_ERR_ARG; }
+  size_t nloc = kind == 0 ? (size_t)ctx->nme : kind == 1 ? (size_t)3 * ctx->nme : (size_t)ctx->n_loc;
+  if ((rc = dev_alloc(ctx, &ctx->coeff[slot], nloc))) return rc;
+  ctx->coeff_len[slot] = (int64_t)nloc;
+  if (ctx->nranks == 1) {
+    if ((rc = upload(ctx, ctx->coeff[slot], data, nloc))) return rc;
+  } else {
+    std::vector<double> tmp(nloc);
+    if (kind == 0) for (int e = 0; e < ctx->nme; ++e) tmp[e] = data[ctx->elem_glob[e]];
+    else if (kind == 1) for (int e = 0; e < ctx->nme; ++e) for (int k = 0; k < 3; ++k) tmp[3 * (size_t)e + k] = data[3 * ctx->elem_glob[e] + k];
+    else for (int i = 0; i < ctx->n_loc; ++i) tmp[i] = data[ctx->loc2glob[i]];
+    if ((rc = upload(ctx, ctx->coeff[slot], tmp.data(), nloc))) return rc;
+    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (slot == DDPS_COEFF_LAMBDA2 || slot == DDPS_COEFF_A11 || slot == DDPS_COEFF_A22) ctx->base_ready = false;
+  return DDPS_OK;
+}
+
+int ddps_functor_set(ddps_ctx* ctx, int kind, const double* params, int nparams) {
+  if (!ctx) return DDPS_ERR_ARG;
+  if (kind == DDPS_FUNCTOR_SINH) {
+    if (nparams != 2 || !params) { ctx->fail(DDPS_ERR_ARG, "SINH functor takes {alpha,beta}"); return DDPS_ERR_ARG; }
+  } else if (kind == DDPS_FUNCTOR_POLY) {
+    if (nparams != 1 || !params || params[0] < 0 || params[0] >= kMaxPoly || params[0] != floor(params[0])) {
+      ctx->fail(DDPS_ERR_ARG, "POLY functor takes {degree}, degree in 0..4");
+      return DDPS_ERR_ARG;
+    }
+  } else {
+    ctx->fail(DDPS_ERR_ARG, "unknown functor kind (arbitrary closures cannot run on the device; no CPU fallback)");
+    return DDPS_ERR_ARG;
+  }
+  ctx->functor_kind = kind;
+  for (int i = 0; i < nparams && i < 8; ++i) ctx->functor_par[i] = params[i];
+  return DDPS_OK;
+}
+
+// ---- solve_ddpe ---------------------------------------------------------------------------------
+int ddps_ddpe_begin(ddps_ctx* ctx, int rec_mode, double delta, double tau_p, double tau_n, double tol) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (rec_mode != DDPS_REC_ZERO && rec_mode != DDPS_REC_SHOCKLEY) { ctx->fail(DDPS_ERR_ARG, "rec_mode must be :shockley or :zero"); return DDPS_ERR_ARG; }
+  for (int f = 0; f < 3; ++f)
+    if (!ctx->have_D[f]) { ctx->fail(DDPS_ERR_STATE, "Dirichlet data for V, u and v must be set"); return DDPS_ERR_STATE; }
+  if ((rc = need_coeff(ctx, DDPS_COEFF_MU_P, "MU_P")) || (rc = need_coeff(ctx, DDPS_COEFF_MU_N, "MU_N")) ||
+      (rc = need_coeff(ctx, DDPS_COEFF_C_MID, "C_MID")))
+    return rc;
+  ctx->rec_mode = rec_mode; ctx->delta = delta; ctx->tau_p = tau_p; ctx->tau_n = tau_n; ctx->tol = tol;
+  reset_stats(ctx);
+  if ((rc = assemble_base(ctx, false))) return rc;                              // src:643, once per solve
+  const size_t bytes = (size_t)ctx->n_loc * sizeof(double);
+  DDPS_CUDA(cudaMemsetAsync(ctx->U, 0, bytes, ctx->stream));                     // src:635-637
+  DDPS_CUDA(cudaMemsetAsync(ctx->W, 0, bytes, ctx->stream));
+  DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, bytes, ctx->stream));
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->ddpe_active = true;
+  return DDPS_OK;
+}
+
+int ddps_ddpe_step(ddps_ctx* ctx, int nsteps, int stop_at_tol, double* control, int* steps_done) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->ddpe_active) { ctx->fail(DDPS_ERR_STATE, "call ddps_ddpe_begin first"); return DDPS_ERR_STATE; }
+  int done = 0, rc = 0;
+  double t0 = now_ms();
+  for (int k = 0; k < nsteps; ++k) {
+    double c = 0;
+    if ((rc = gummel_step(ctx, &c))) break;
+    ++done;
+    ctx->stats.outer_iters++;
+    ctx->stats.control = c;
+    ctx->hist_outer.push_back(c);
+    if (control) control[k] = c;
+    if (ctx->opts.verbose) printf("iteration %d, tolerance: %.17g\n", ctx->stats.outer_iters, c);   // src:655
+    if (stop_at_tol && !(c > ctx->tol)) break;                                                     // src:649
+  }
+  ctx->stats.t_solve_ms += now_ms() - t0;
+  if (steps_done) *steps_done = done;
+  ctx->stats.status = rc;
+  return rc;
+}
+
+int ddps_ddpe_fetch(ddps_ctx* ctx, double* V, double* u, double* v) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (V && (rc = download_nodal(ctx, ctx->V, V))) return rc;
+  if (u && (rc = download_nodal(ctx, ctx->U, u))) return rc;
+  if (v && (rc = download_nodal(ctx, ctx->W, v))) return rc;
+  return DDPS_OK;
+}
+
+int ddps_solve_ddpe(ddps_ctx* ctx, int rec_mode, double delta, double tau_p, double tau_n, double tol, double* V,
+                    double* u, double* v, ddps_stats* stats) {
+  if (!ctx) return DDPS_ERR_ARG;
+  int rc = ddps_ddpe_begin(ctx, rec_mode, delta, tau_p, tau_n, tol);
+  if (rc) return rc;
+  const int cap = ctx->opts.max_gummel > 0 ? ctx->opts.max_gummel : 1000;
+  double control = 1.0;   // src:645
+  int total = 0;
+  while (control > tol) {
+    if (total >= cap) { ctx->fail(DDPS_ERR_NOCONV, "Gummel iteration cap reached"); rc = DDPS_ERR_NOCONV; break; }
+    int done = 0;
+    rc = ddps_ddpe_step(ctx, 1, 1, &control, &done);
+    if (rc) break;
+    ++total;
+  }
+  ctx->stats.status = rc;
+  int rc2 = ddps_ddpe_fetch(ctx, V, u, v);
+  if (stats) *stats = ctx->stats;
+  return rc ? rc : rc2;
+}
+
+// ---- solve_semlin_poisson ---------------------------------------------------------------------
+int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  reset_stats(ctx);
+  ctx->ddpe_active = false;
+  double t0 = now_ms();
+  if ((rc = assemble_base(ctx, true))) return rc;                                            // src:924-1028
+  DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:948
+  const int cap = ctx->opts.max_newton > 0 ? ctx->opts.max_newton : 1000;
+  int count = 0;
+  while (true) {
+    EventTimer ta(ctx, ctx->ev0, ctx->ev1);
+    if ((rc = assemble_newton(ctx, true, 0.0, ctx->V, nullptr, nullptr))) break;
+    ta.stop();
+    double res;
+    if ((rc = fetch_resid_norm(ctx, &res))) break;
+    ctx->stats.t_asm_ms += ta.ms();
+    ctx->hist_outer.push_back(res);
+    ctx->stats.control = res;
+    if (count > 0 && ctx->opts.verbose) printf("iteration %d, tolerance: %.17g\n", count, res);   // src:1093
+    if (!(res > tol)) break;                                                                  // src:1040
+    if (count >= cap) { ctx->fail(DDPS_ERR_NOCONV, "semlin: Newton iteration cap reached"); rc = DDPS_ERR_NOCONV; break; }
+    EventTimer tp(ctx, ctx->ev2, ctx->ev3);
+    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, ctx->opts.lin_max_it,
+                   nullptr, nullptr);                                                         // src:1063
+    tp.stop();
+    ctx->stats.t_pcg_ms += tp.ms();
+    if (rc) break;
+    if ((rc = launch_axpy(ctx, -1.0, ctx->x, ctx->V, ctx->n_own))) break;                     // src:1064
+    if ((rc = halo_exchange(ctx, ctx->V))) break;
+    ++count;
+  }
+  ctx->stats.outer_iters = count;
+  ctx->stats.newton_total = count;
+  ctx->stats.status = rc;
+  ctx->stats.t_solve_ms = now_ms() - t0;
+  int rc2 = Vout ? download_nodal(ctx, ctx->V, Vout) : 0;
+  if (stats) *stats = ctx->stats;
+  return rc ? rc : rc2;
+}
+
+int ddps_get_history(ddps_ctx* ctx, int kind, double* out, int64_t cap, int64_t* n) {
+  if (!ctx || !n) return DDPS_ERR_ARG;
+  const std::vector<double>& h = kind == 0 ? ctx->hist_outer : kind == 1 ? ctx->hist_newton : ctx->hist_pcg;
+  *n = (int64_t)h.size();
+  if (out) for (int64_t i = 0; i < cap && i < (int64_t)h.size(); ++i) out[i] = h[i];
+  return DDPS_OK;
+}
+
+int ddps_get_stats(ddps_ctx* ctx, ddps_stats* stats) {
+  if (!ctx || !stats) return DDPS_ERR_ARG;
+  *stats = ctx->stats;
+  return DDPS_OK;
+}
+
+// ---- parity / debug exports -------------------------------------------------------------------
+int ddps_get_csr_size(ddps_ctx* ctx, int64_t* nrows, int64_t* nnz) {
+  if (!ctx) return DDPS_ERR_ARG;
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (nrows) *nrows = ctx->pat.nrows;
+  if (nnz) *nnz = ctx->pat.nnz;
+  return DDPS_OK;
+}
+
+int ddps_get_csr(ddps_ctx* ctx, int which, int64_t* rowptr, int64_t* col, double* val) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  const Pattern& P = ctx->pat;
+  std::vector<int> rp(P.nrows + 1), cc(P.nnz), sp(P.nslices + 1);
+  DDPS_CUDA(cudaMemcpy(rp.data(), P.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(cc.data(), P.csrcol, cc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(sp.data(), P.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  if (rowptr) for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
+  if (col) for (size_t i = 0; i < cc.size(); ++i) col[i] = ctx->loc2glob.empty() ? cc[i] : ctx->loc2glob[cc[i]];
+  if (val) {
+    const double* src = which == DDPS_MAT_BASE ? ctx->val_base : ctx->val_op;
+    std::vector<double> sv(P.nentries);
+    DDPS_CUDA(cudaMemcpy(sv.data(), src, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < P.nrows; ++r) {
+      int base = sp[r >> 5], lane = r & 31;
+      for (int k = 0; k < rp[r + 1] - rp[r]; ++k) val[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
+    }
+  }
+  return DDPS_OK;
+}
+
+int ddps_get_vector(ddps_ctx* ctx, int which, double* out, int64_t len) {
+  if (!ctx || !out) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  const double* src = nullptr;
+  switch (which) {
+    case DDPS_VEC_RHS: src = ctx->b; break;
+    case DDPS_VEC_RESID: src = ctx->resid; break;
+    case DDPS_VEC_V: src = ctx->V; break;
+    case DDPS_VEC_U: src = ctx->U; break;
+    case DDPS_VEC_W: src = ctx->W; break;
+    case DDPS_VEC_LIFT: src = ctx->lift; break;
+    default: ctx->fail(DDPS_ERR_ARG, "unknown vector"); return DDPS_ERR_ARG;
+  }
+  if (len != ctx->n_own) { ctx->fail(DDPS_ERR_ARG, "vector length must equal the number of owned rows"); return DDPS_ERR_ARG; }
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  DDPS_CUDA(cudaMemcpy(out, src, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost));
+  return DDPS_OK;
+}
+
+int ddps_debug_assemble_base(ddps_ctx* ctx, int use_semlin) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if ((rc = assemble_base(ctx, use_semlin != 0))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DDPS_OK;
+}
+
+int ddps_debug_assemble_newton(ddps_ctx* ctx, int use_semlin, double delta, const double* V, const double* u,
+                               const double* v, double* resid_inf) {
+  if (!ctx || !V) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (!ctx->base_ready || ctx->base_is_semlin != (use_semlin != 0)) { ctx->fail(DDPS_ERR_STATE, "assemble the matching base matrix first"); return DDPS_ERR_STATE; }
+  if ((rc = upload_nodal(ctx, ctx->V, V))) return rc;
+  if (!use_semlin) {
+    if (!u || !v) return DDPS_ERR_ARG;
+    if ((rc = upload_nodal(ctx, ctx->U0, u)) || (rc = upload_nodal(ctx, ctx->W0, v))) return rc;
+  }
+  if ((rc = assemble_newton(ctx, use_semlin != 0, delta, ctx->V, ctx->U0, ctx->W0))) return rc;
+  double res;
+  if ((rc = fetch_resid_norm(ctx, &res))) return rc;
+  if (resid_inf) *resid_inf = res;
+  return DDPS_OK;
+}
+
+int ddps_debug_assemble_uv(ddps_ctx* ctx, int which, int rec_mode, double tau_p, double tau_n, const double* V,
+                           const double* u0, const double* v0) {
+  if (!ctx || !V || !u0 || !v0) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (which != DDPS_FIELD_U && which != DDPS_FIELD_W) { ctx->fail(DDPS_ERR_ARG, "which must be U or W"); return DDPS_ERR_ARG; }
+  if ((rc = upload_nodal(ctx, ctx->V, V)) || (rc = upload_nodal(ctx, ctx->U0, u0)) || (rc = upload_nodal(ctx, ctx->W0, v0))) return rc;
+  if ((rc = assemble_uv(ctx, which, rec_mode, tau_p, tau_n, ctx->V, ctx->U0, ctx->W0))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DDPS_OK;
+}
+
+int ddps_debug_spmv(ddps_ctx* ctx, int which, const double* x, double* y) {
+  if (!ctx || !x || !y) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if ((rc = upload_nodal(ctx, ctx->p, x))) return rc;
+  if ((rc = launch_spmv(ctx, which == DDPS_MAT_BASE ? ctx->val_base : ctx->val_op, ctx->p, ctx->q))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  DDPS_CUDA(cudaMemcpy(y, ctx->q, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost));
+  return DDPS_OK;
+}
+
+int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int64_t max_it, int64_t* iters, double* relres) {
+  if (!ctx || !rhs || !x) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (ctx->nranks != 1) { ctx->fail(DDPS_ERR_STATE, "debug exports are single-GPU"); return DDPS_ERR_STATE; }
+  if ((rc = upload(ctx, ctx->b, rhs, (size_t)ctx->n_own)) || (rc = upload(ctx, ctx->x, x, (size_t)ctx->n_own))) return rc;
+  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, true, rtol, max_it, iters, relres);
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  DDPS_CUDA(cudaMemcpy(x, ctx->x, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost));
+  return rc;
+}
+
+// ---- kernel timing on the library stream --------------------------------------------------------
+int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_per_launch, double* algo_bytes) {
+  if (!ctx || reps <= 0) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  const Pattern& P = ctx->pat;
+  const double nnz = (double)P.nnz, nq = (double)ctx->n_own, nme = (double)ctx->nme;
+  double bytes = 0;
+  auto run = [&](int it) -> int {
+    switch (kernel) {
+      case 0: return launch_spmv(ctx, ctx->val_op, ctx->p, ctx->q);
+      case 1: return assemble_uv(ctx, DDPS_FIELD_U, ctx->rec_mode, ctx->tau_p, ctx->tau_n, ctx->V, ctx->U0, ctx->W0);
+      case 2: return pcg_iteration_launch(ctx, ctx->val_op, ctx->dinv, ctx->x, it, 1 << 30);
+      case 3: return assemble_newton(ctx, false, ctx->delta, ctx->V, ctx->U0, ctx->W0);
+      case 4: return assemble_base(ctx, ctx->base_is_semlin);
+    }
+    ctx->fail(DDPS_ERR_ARG, "unknown kernel id");
+    return DDPS_ERR_ARG;
+  };
+  // algorithmic bytes per launch: every input read once, every output written once,
+  // FP64 values, int32 indices
+  switch (kernel) {
+    case 0: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq; break;                     // 14.86 B/nnz
+    case 1: bytes = 12.0 * nme + 16.0 * nq + 8.0 * nme + 6 * 8.0 * nq + 8.0 * nnz + 16.0 * nq; break;
+    case 2: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq + 10 * 8.0 * nq; break;     // SURVEY 8d PCG iteration
+    case 3: bytes = 12.0 * nme + 16.0 * nq + 24.0 * nme + 6 * 8.0 * nq + 12.0 * nnz + 8.0 * nnz + 24.0 * nq; break;
+    case 4: bytes = 12.0 * nme + 16.0 * nq + 8.0 * nme + 8.0 * nnz + 8.0 * nq; break;
+  }
+  if (kernel == 2) {
+    // fresh PCG state on the last assembled system; rtol 0 keeps the done flag down
+    if ((rc = halo_exchange(ctx, ctx->p))) return rc;
+    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, false, 0.0, 1, nullptr, nullptr);
+    if (rc != DDPS_ERR_NOCONV && rc != 0) return rc;
+    DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
+  }
+  int it = 1;
+  for (int i = 0; i < warm; ++i, ++it) if ((rc = run(it))) return rc;
+  DDPS_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int i = 0; i < reps; ++i, ++it) if ((rc = run(it))) return rc;
+  DDPS_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  DDPS_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0;
+  DDPS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  if (ms_per_launch) *ms_per_launch = ms / reps;
+  if (algo_bytes) *algo_bytes = bytes;
+  return DDPS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+// Internal structures of libddps_b200.so (not part of the C ABI).
+//
+// Layout decisions:
+//  * node coordinates: double2 per node (x,y interleaved exactly like Mesh.nodes, src:11) -> one
+//    16-byte load per corner.
+//  * triangles: int4 {n1,n2,n3,_} with 0-based LOCAL node ids -> one 16-byte load per triangle.
+//  * sparsity pattern: CSR with sorted columns, stored slice-interleaved ("SELL-32"): rows are
+//    grouped in slices of 32 (one warp), every slice is padded to its longest row and stored
+//    column-major inside the slice, so lane l of a warp reads entry k of row 32*s+l at
+//    slice_ptr[s] + 32*k + l  -> perfectly coalesced value/column streams for both the row-major
+//    assembly (writes) and the SpMV (reads).  Padding entries carry value 0 and column = own row.
+//  * row -> incident triangle lists ("incidence"), also slice-interleaved; each record packs the
+//    triangle id, the row's local corner (0..2) and the three pre-computed slots of that
+//    triangle's row entries, so the scatter needs no search and no atomics.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ddps.h"
+
+#ifdef DDPS_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace ddps {
+
+constexpr int kSlice = 32;        // rows per slice = warp size
+constexpr int kAsmBlock = 128;    // threads per block of the row-major assembly kernels
+constexpr int kMaxRowLen = 40;    // shared-memory accumulator columns available per row
+constexpr int kVecBlock = 256;    // threads per block of SpMV / vector kernels
+constexpr int kMaxPoly = 5;       // polynomial functor: degree 0..4
+
+#define DDPS_CUDA(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ctx->fail(DDPS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+      return DDPS_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+struct Pattern {
+  int nrows = 0;        // owned rows
+  int ncols = 0;        // local nodes (owned + ghost)
+  int nslices = 0;
+  int64_t nnz = 0;      // true nonzeros of the owned rows
+  int64_t nentries = 0; // stored entries incl. padding (= slice_ptr[nslices])
+  int max_row_len = 0;
+  int* slice_ptr = nullptr;  // [nslices+1]
+  int* col = nullptr;        // [nentries] slice-interleaved
+  int* rowptr = nullptr;     // [nrows+1] plain CSR (export + slot search)
+  int* csrcol = nullptr;     // [nnz]
+  // incidence lists
+  int64_t inc_entries = 0;
+  int* inc_slice_ptr = nullptr;  // [nslices+1]
+  int2* inc = nullptr;           // [inc_entries] {tri*4+corner | -1, slot_self | slot_next<<8 | slot_prev<<16}
+};
+
+// device-side scalar block of one PCG solve (all control flow stays on the device)
+struct PcgScalars {
+  double rz[2];     // r.z, ping-pong by iteration parity
+  double pq;        // p.Ap
+  double rr;        // r.r
+  double bb;        // rhs.rhs
+  double thresh2;   // stop when rr <= thresh2
+  double sums[4];   // staging for allreduce: {pq} or {rz_new, rr}
+  int done;
+  int iters;
+  int breakdown;
+  int pad0;
+  unsigned cnt[4];  // last-block tickets
+  double norm_inf;  // generic max-norm result
+  double norm_aux;
+};
+
+struct HaloPlan {
+  int nneigh = 0;
+  std::vector<int> peer;        // neighbour ranks
+  std::vector<int> send_off;    // [nneigh+1] offsets into send_idx
+  std::vector<int> recv_off;    // [nneigh+1] offsets into the ghost block (relative to n_own)
+  int* send_idx = nullptr;      // device: local owned ids to pack, grouped by neighbour
+  double* send_buf = nullptr;   // device
+  int nsend = 0;
+};
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  int num_sms = 148;
+  std::string err;
+  int err_code = 0;
+  ddps_solver_opts opts;
+  ddps_stats stats;
+
+  // communicator
+  int rank = 0, nranks = 1;
+#ifdef DDPS_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  HaloPlan halo;
+
+  // mesh (local part)
+  bool have_mesh = false;
+  int64_t nq_global = 0, nme_global = 0;
+  int n_own = 0, n_loc = 0, nme = 0;
+  double2* xy = nullptr;
+  int4* elem = nullptr;
+  std::vector<int64_t> loc2glob;      // [n_loc] global 0-based node id of every local node
+  std::vector<int64_t> elem_glob;     // [nme] global element id of every local element
+  long long* d_own_glob = nullptr;    // device copy of loc2glob[0:n_own] (gather of results across ranks)
+  Pattern pat;
+
+  // boundary data
+  unsigned char* isD = nullptr;       // [n_loc]
+  double* gD[4] = {nullptr, nullptr, nullptr, nullptr};  // [n_loc] per ddps_field
+  bool have_D[4] = {false, false, false, false};
+  std::vector<int64_t> Dset;          // sorted global Dirichlet ids (from the first dirichlet_set)
+
+  // sampled coefficients: slot -> device array (element slots hold local elements only)
+  double* coeff[64] = {nullptr};
+  int64_t coeff_len[64] = {0};
+  int functor_kind = 0;
+  double functor_par[8] = {0};
+
+  // matrices (values in SELL order)
+  double* val_base = nullptr;  // MV / semlin M
+  double* val_op = nullptr;    // operator handed to the solver
+  double* lift = nullptr;      // [n_own] K[:,D]*gD of the base stiffness
+  bool base_ready = false;
+  bool base_is_semlin = false;
+
+  // nodal work arrays [n_loc]
+  double *V = nullptr, *U = nullptr, *W = nullptr;          // fields
+  double *V0 = nullptr, *U0 = nullptr, *W0 = nullptr;       // previous Gummel iterate
+  double *Unew = nullptr;                                   // scratch field
+  double *EH = nullptr, *EHi = nullptr, *E3 = nullptr, *gw = nullptr;
+  // solver vectors
+  double *b = nullptr, *resid = nullptr, *dinv = nullptr;   // [n_own]
+  double *x = nullptr, *r = nullptr, *q = nullptr;          // [n_own]
+  double *p = nullptr;                                      // [n_loc] (gathered by SpMV -> needs ghosts)
+  double* partials = nullptr;                               // block partial sums
+  int partial_cap = 0;
+  PcgScalars* scal = nullptr;                               // device
+  PcgScalars* scal_host = nullptr;                          // pinned
+
+  // ddpe state
+  bool ddpe_active = false;
+  int rec_mode = 0;
+  double delta = 1, tau_p = 1, tau_n = 1, tol = 1e-9;
+
+  std::vector<double> hist_outer, hist_newton, hist_pcg;
+
+  void fail(int code, const std::string& msg) {
+    err_code = code;
+    err = msg;
+  }
+};
+
+// ---- setup.cu ----
+int build_pattern(Context* ctx);
+void free_pattern(Context* ctx);
+// ---- partition.cpp-like host code (in setup.cu) ----
+void partition_nodes_rcb(const double* nodes, int64_t nq, int nparts, int32_t* owner);
+
+// ---- kernels.cu ----
+struct AsmArgs {
+  int nrows, nslices;
+  const int* slice_ptr;
+  const int* col;
+  const int* inc_slice_ptr;
+  const int2* inc;
+  const double2* xy;
+  const int4* elem;
+  const unsigned char* isD;
+  const double* gD;
+  const double* phx;      // per-element coefficient (x pairing) or mu
+  const double* phy;      // per-element coefficient (y pairing)
+  const double* E3;       // nodal exp(+-V/3)
+  const double* base_val; // base matrix values (STIFF==0)
+  const double* gw;       // nodal mass weight g_k
+  // rhs inputs
+  const double* fu;       // nodal u (or u0)
+  const double* fv;       // nodal v (or v0)
+  const double* EH;       // nodal exp(+V/2)   (semlin: the iterate itself)
+  const double* EHi;      // nodal exp(-V/2)
+  const double* mid;      // [nme*3] midpoint samples (C or H)
+  const double* mid_poly[kMaxPoly];
+  const double* nodal_const;  // neumann loads (may be null)
+  const double* lift_in;      // precomputed lifting of the base stiffness (STIFF==0)
+  double par0, par1, par2;    // delta^2 | tau_p,tau_n | alpha,beta | degree
+  const double* xvec;         // iterate for the residual
+  // outputs
+  double* out_val;
+  double* dinv;
+  double* b;
+  double* lift_out;
+  double* resid;
+  double* partial_max;
+  PcgScalars* scal;
+};
+
+enum { STIFF_BASE = 0, STIFF_COEF = 1, STIFF_EXPV = 2 };
+enum { RHS_NONE = 0, RHS_DDP = 1, RHS_SRH = 2, RHS_ZERO = 3, RHS_SINH = 4, RHS_POLY = 5 };
+
+int launch_assemble_base(Context* ctx, const AsmArgs& a);
+int launch_assemble_uv(Context* ctx, const AsmArgs& a, int rhs_kind, bool mass);
+int launch_assemble_newton(Context* ctx, const AsmArgs& a, int rhs_kind);
+
+int launch_prep_poisson(Context* ctx, const double* V, const double* u, const double* v, double delta2);
+int launch_prep_uv(Context* ctx, double sign, const double* V, const double* other, const double* u0, const double* v0,
+                   double tau_p, double tau_n, int rec_mode);
+int launch_prep_semlin(Context* ctx, const double* V);
+
+int launch_spmv(Context* ctx, const double* val, const double* x, double* y);
+int launch_axpy(Context* ctx, double a, const double* x, double* y, int n);          // y += a*x
+int launch_negate_copy(Context* ctx, const double* x, double* y, double s, int n);   // y = s*x
+int launch_max_abs_diff3(Context* ctx, const double* a0, const double* a1, const double* b0, const double* b1,
+                         const double* c0, const double* c1, int n, double* host_out);
+int launch_max_abs(Context* ctx, const double* a, int n, double* host_out);
+
+int fetch_resid_norm(Context* ctx, double* host_out);  // norm_inf written by the last RESID assembly
+int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it);
+// Jacobi-PCG: solve val*x = rhs; x holds the initial guess if x0_nonzero (else it is zeroed).
+int pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
+              double rtol, int64_t max_it, int64_t* iters_out, double* relres_out);
+
+// ---- comm.cu ----
+int halo_exchange(Context* ctx, double* vec);            // fill ghost part of a [n_loc] vector
+int allreduce_sum(Context* ctx, double* dev, int count); // in place on the library stream
+int allreduce_max(Context* ctx, double* dev, int count);
+int comm_init(Context* ctx, const char* id128, int rank, int nranks);
+int comm_unique_id(char* id128);
+void comm_destroy(Context* ctx);
+
+}  // namespace ddps
+
+struct ddps_ctx : public ddps::Context {};

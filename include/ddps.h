@@ -1,0 +1,192 @@
+/*
+ * ddps.h -- C ABI of libddps_b200.so, the B200-native (sm_100a, FP64) replacement for the hot path of
+ * DriftDiffusionPoissonSystems.jl: per-iteration P1-triangle FEM assembly + linear solve inside
+ * solve_ddpe (Gummel) and solve_semlin_poisson (Newton).
+ *
+ * The reference is a single Julia file with NO FFI/plugin interface; "src:N" below means
+ * /root/reference/src/DriftDiffusionPoissonSystems.jl line N and names the reference code each entry
+ * point replaces.  A Julia (ccall) or Python (ctypes) host shim evaluates the user's spatial
+ * closures once on the host, hands the sampled arrays to this library, and calls the solve entry
+ * points; all per-iteration work stays resident on the device.  See INTEGRATION.md for the
+ * reference-side binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; ddps_last_error(ctx) gives the message
+ *     (ctx may be NULL for errors of ddps_ctx_create).  No C++ exception crosses this boundary.
+ *   - the caller owns every host pointer; the library copies during the call and never retains it.
+ *   - index arrays are int64 and 1-BASED exactly like the reference's Mesh (src:9-18).
+ *   - there is NO CPU fallback: without a CUDA device ddps_ctx_create fails.
+ *   - calls are blocking; one ctx per host thread; one ctx (= one process) per GPU for multi-GPU.
+ */
+#ifndef DDPS_H
+#define DDPS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDPS_VERSION 100 /* 0.1.0 */
+
+typedef struct ddps_ctx ddps_ctx;
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define DDPS_OK 0
+#define DDPS_ERR_ARG (-1)       /* bad argument / inconsistent input (reference: error()/@assert) */
+#define DDPS_ERR_CUDA (-2)      /* CUDA runtime failure */
+#define DDPS_ERR_STATE (-3)     /* call sequence violated (e.g. solve before mesh_set) */
+#define DDPS_ERR_NOCONV (-4)    /* iteration cap reached (the reference would spin forever) */
+#define DDPS_ERR_BREAKDOWN (-5) /* PCG breakdown: operator not SPD (u or v went negative) */
+#define DDPS_ERR_COMM (-6)      /* NCCL failure */
+
+/* ---- which Dirichlet value set (src:640 V; src:532-544 u and v; src:1001-1013 semlin) ----- */
+enum ddps_field { DDPS_FIELD_V = 0, DDPS_FIELD_U = 1, DDPS_FIELD_W = 2 /* the reference's v */, DDPS_FIELD_SCALAR = 3 };
+
+/* ---- sampled coefficient slots (host evaluates the closures once) ------ */
+enum ddps_coeff {
+  DDPS_COEFF_LAMBDA2 = 0, /* [nme]    lambda(centroid)^2                     src:250-254 */
+  DDPS_COEFF_MU_P = 1,    /* [nme]    mu_p(centroid)                         src:463-467 */
+  DDPS_COEFF_MU_N = 2,    /* [nme]    mu_n(centroid)                         src:463-467 */
+  DDPS_COEFF_C_MID = 3,   /* [3,nme]  C at midpoints m12,m23,m31 (col-major) src:303-308,341-343 */
+  DDPS_COEFF_A11 = 4,     /* [nme]    A[1](geom tag)                         src:901 */
+  DDPS_COEFF_A22 = 5,     /* [nme]    A[4](geom tag)                         src:902 */
+  DDPS_COEFF_H_MID = 6,   /* [3,nme]  u-independent part of f at midpoints   src:940-957 */
+  DDPS_COEFF_NEUMANN = 7, /* [nq]     accumulated Neumann edge loads         src:986-996 */
+  DDPS_COEFF_POLY_MID0 = 16,  /* +k: [3,nme] polynomial coefficient c_k at midpoints, k=0..4 */
+  DDPS_COEFF_POLY_NODE0 = 32  /* +k: [nq]    polynomial coefficient c_k at nodes,     k=0..4 */
+};
+
+/* ---- registered u-dependent functors for solve_semlin_poisson's f,g (no CPU fallback) ----- */
+enum ddps_functor_kind {
+  DDPS_FUNCTOR_NONE = 0,
+  DDPS_FUNCTOR_SINH = 1, /* f = H_MID + alpha*sinh(beta*u), g = alpha*beta*cosh(beta*u); params {alpha,beta} */
+  DDPS_FUNCTOR_POLY = 2  /* f = sum_k c_k u^k, g = sum_k k c_k u^(k-1); params {degree} */
+};
+
+enum ddps_rec_mode { DDPS_REC_ZERO = 0 /* :zero src:520 */, DDPS_REC_SHOCKLEY = 1 /* :shockley src:516 */ };
+
+/* ---- matrices / vectors retrievable for parity tests -------------------------------------- */
+enum ddps_matrix {
+  DDPS_MAT_BASE = 0, /* eliminated constant stiffness: MV (src:284) or semlin M (src:1028) */
+  DDPS_MAT_OP = 1    /* last assembled operator M - J0 handed to the solver (src:394,588,1063) */
+};
+enum ddps_vector {
+  DDPS_VEC_RHS = 0,   /* last assembled right-hand side b (src:361-363, 562-564, 1031-1033) */
+  DDPS_VEC_RESID = 1, /* last Newton residual M*V - b (src:368,1040) */
+  DDPS_VEC_V = 2, DDPS_VEC_U = 3, DDPS_VEC_W = 4, /* current fields */
+  DDPS_VEC_LIFT = 5   /* K[:,D]*gD of the base stiffness (src:362, rows not in D) */
+};
+
+typedef struct ddps_solver_opts {
+  double lin_rtol;      /* PCG stop for the linear continuity solves: ||r||_2 <= lin_rtol*||b||_2   (default 1e-13) */
+  double newton_eta;    /* PCG stop for Newton corrections:          ||r||_2 <= newton_eta*||F||_2 (default 1e-10) */
+  int64_t lin_max_it;   /* PCG iteration cap per solve (default 200000) */
+  int32_t max_newton;   /* Newton cap per solve, 0 = 1000 (the reference has none, src:368,1040) */
+  int32_t max_gummel;   /* Gummel cap, 0 = 1000 (the reference has none, src:649) */
+  int32_t check_every;  /* PCG iterations between host polls of the device-side done flag (default 32) */
+  int32_t warm_start;   /* 1: continuity solves start PCG from the previous iterate (same solution) (default 1) */
+  int32_t verbose;      /* 1: print "iteration k, tolerance: c" lines like src:655,1093 */
+  int32_t reserved[7];
+} ddps_solver_opts;
+
+typedef struct ddps_stats {
+  int32_t outer_iters;     /* Gummel (ddpe) or Newton (semlin) iterations done */
+  int32_t newton_total;    /* Newton iterations summed over all Vsolve calls */
+  int64_t pcg_total;       /* PCG iterations summed over all solves */
+  int64_t spmv_total;      /* SpMV launches (PCG + residuals) */
+  int64_t kernel_launches; /* all kernel launches of this library during the call */
+  double control;          /* last Gummel update norm (src:653) or last Newton residual (src:1092) */
+  double t_setup_ms;       /* host wall: uploads + pattern build inside this call (0 when resident) */
+  double t_solve_ms;       /* device-resident loop, CUDA events on the library stream */
+  double t_asm_ms;         /* summed CUDA-event time of assembly kernels */
+  double t_pcg_ms;         /* summed CUDA-event time of PCG */
+  int32_t status;          /* DDPS_OK / DDPS_ERR_NOCONV / DDPS_ERR_BREAKDOWN */
+  int32_t n_negative_area; /* elements with signed area < 0 (Q2: mass uses signed ar, src:375) */
+  int32_t reserved[8];
+} ddps_stats;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+int ddps_version(void);
+const char* ddps_last_error(const ddps_ctx* ctx);
+int ddps_ctx_create(ddps_ctx** out, int device);
+int ddps_ctx_destroy(ddps_ctx* ctx);
+void ddps_default_opts(ddps_solver_opts* opts);
+int ddps_set_opts(ddps_ctx* ctx, const ddps_solver_opts* opts);
+
+/* ---- multi-GPU (one process per GPU; node-partitioned by coordinate bisection) ------------ */
+/* The reference has no communication at all; these are new.  id is an ncclUniqueId (128 bytes)
+ * produced on rank 0 and broadcast by the host's own plumbing (torch.distributed / MPI / files). */
+int ddps_comm_unique_id(char id128[128]);
+int ddps_comm_init(ddps_ctx* ctx, const char id128[128], int rank, int nranks);
+
+/* ---- mesh: replaces the per-call gathers of mesh.nodes/mesh.elements (src:235-247, 443-456, 909-921)
+ * nodes    f64 [2,nq]  column-major (x,y per node)        = Mesh.nodes    (src:11)
+ * elements i64 [5,nme] column-major, 1-based node ids     = Mesh.elements (src:17)
+ * Builds the fixed sparsity pattern + row->incident-triangle lists once (replaces every sparse()
+ * call, src:275,284,361,391,...).  With a communicator every rank passes the SAME global mesh. */
+int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t* elements, int64_t nme);
+
+/* Host-only partition query (runs without a GPU context's kernels; used by the CPU tests):
+ * owner[nq] <- rank owning each node under recursive coordinate bisection into nparts parts. */
+int ddps_partition_nodes(const double* nodes, int64_t nq, int nparts, int32_t* owner);
+
+/* ---- boundary + coefficient uploads (host shim output of aquire_boundary, src:162-218) ---- */
+int ddps_dirichlet_set(ddps_ctx* ctx, int field, const int64_t* idx1, const double* val, int64_t nd);
+int ddps_coeff_set(ddps_ctx* ctx, int slot, const double* data, int64_t len);
+int ddps_functor_set(ddps_ctx* ctx, int kind, const double* params, int nparams);
+
+/* ---- solve_ddpe (src:630-658) -------------------------------------------------------------
+ * begin: MV_assemble once (src:643), zero state (src:635-637).
+ * step : nsteps applications of the Gummel map G (src:596-601, 649-656); control[k] = update norm
+ *        of step k (src:653); stops early when control <= tol if stop_at_tol != 0.
+ * fetch: copy the current V,u,v (length nq each) to the host.
+ * solve: begin + step until control <= tol + fetch  == solve_ddpe(...) -> (V,u,v). */
+int ddps_ddpe_begin(ddps_ctx* ctx, int rec_mode, double delta, double tau_p, double tau_n, double tol);
+int ddps_ddpe_step(ddps_ctx* ctx, int nsteps, int stop_at_tol, double* control, int* steps_done);
+int ddps_ddpe_fetch(ddps_ctx* ctx, double* V, double* u, double* v);
+int ddps_solve_ddpe(ddps_ctx* ctx, int rec_mode, double delta, double tau_p, double tau_n, double tol,
+                    double* V, double* u, double* v, ddps_stats* stats);
+
+/* ---- solve_semlin_poisson (src:895-1097): Newton on M*u = b(u), Jacobian M - J0(g) -------- */
+int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* V, ddps_stats* stats);
+
+/* ---- iteration history of the last solve ---------------------------------------------------
+ * kind 0: Gummel control per outer iteration (src:653) / Newton residual per iteration (src:1092)
+ * kind 1: Newton iterations per Vsolve call; kind 2: PCG iterations per linear solve. */
+int ddps_get_history(ddps_ctx* ctx, int kind, double* out, int64_t cap, int64_t* n);
+int ddps_get_stats(ddps_ctx* ctx, ddps_stats* stats);
+
+/* ---- parity / debug exports (single-GPU contexts) ------------------------------------------ */
+int ddps_get_csr_size(ddps_ctx* ctx, int64_t* nrows, int64_t* nnz);
+/* CSR of the fixed pattern, 0-based, columns sorted within each row, explicit zeros kept (Q5). */
+int ddps_get_csr(ddps_ctx* ctx, int which, int64_t* rowptr, int64_t* col, double* val);
+int ddps_get_vector(ddps_ctx* ctx, int which, double* out, int64_t len);
+/* Assemble individual systems from host-supplied fields (each length nq), results retrievable with
+ * ddps_get_csr(DDPS_MAT_OP)/ddps_get_vector(DDPS_VEC_RHS):
+ *   base   : MV (src:229-287) from LAMBDA2, or semlin M (src:924-1028) from A11/A22 (use_semlin!=0)
+ *   newton : A = base - J0(V), b(V), F = base*V - b   (Vsolve src:368-420 / semlin src:1040-1089)
+ *   uv     : A,b of uvsolve (src:433-588); which = DDPS_FIELD_U (V,tau_p,tau_n,mu_p,u0,v0) or
+ *            DDPS_FIELD_W (-V,tau_n,tau_p,mu_n,v0,u0) exactly as G calls it (src:598-599). */
+int ddps_debug_assemble_base(ddps_ctx* ctx, int use_semlin);
+int ddps_debug_assemble_newton(ddps_ctx* ctx, int use_semlin, double delta, const double* V, const double* u,
+                               const double* v, double* resid_inf);
+int ddps_debug_assemble_uv(ddps_ctx* ctx, int which, int rec_mode, double tau_p, double tau_n, const double* V,
+                           const double* u0, const double* v0);
+/* y = A*x with the chosen matrix (K8). */
+int ddps_debug_spmv(ddps_ctx* ctx, int which, const double* x, double* y);
+/* Solve OP*x = rhs with Jacobi-PCG (K9); x holds the initial guess on entry. */
+int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int64_t max_it, int64_t* iters,
+                   double* relres);
+
+/* ---- in-library kernel timing (CUDA events on the library's own stream) --------------------
+ * kernel 0: SpMV on DDPS_MAT_OP; 1: continuity-system assembly (uvsolve A+b, src:433-588);
+ * 2: one full PCG iteration; 3: Newton-system assembly (Vsolve, src:368-420); 4: base stiffness.
+ * Runs `reps` launches after `warm` untimed ones and returns the mean milliseconds per launch and
+ * the algorithmic bytes of one launch (definition in DESIGN.md). */
+int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_per_launch, double* algo_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDPS_H */
