@@ -234,8 +234,10 @@ int vsolve(Context* ctx) {
     if (!(res > ctx->tol)) break;                                                            // src:368
     if (newton >= cap) { ctx->fail(DDPS_ERR_NOCONV, "Vsolve: Newton iteration cap reached"); return DDPS_ERR_NOCONV; }
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
-    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, ctx->opts.lin_max_it,
-                   nullptr, nullptr);
+    // Newton correction: the linear residual only has to be below the Newton tolerance (so that, like the
+    // reference's direct solve, a linear problem converges in one step); newton_eta is a relative floor.
+    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * ctx->tol,
+                   ctx->opts.lin_max_it, nullptr, nullptr);
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
     if (rc) return rc;
@@ -255,7 +257,7 @@ int uvsolve(Context* ctx, int which) {
   ta.stop();
   double* field = (which == DDPS_FIELD_U) ? ctx->U : ctx->W;
   EventTimer tp(ctx, ctx->ev2, ctx->ev3);
-  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, field, ctx->opts.warm_start != 0, ctx->opts.lin_rtol,
+  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, field, ctx->opts.warm_start != 0, ctx->opts.lin_rtol, 0.0,
                  ctx->opts.lin_max_it, nullptr, nullptr);                                     // src:588
   tp.stop();
   ctx->stats.t_pcg_ms += tp.ms();
@@ -298,7 +300,7 @@ const char* ddps_last_error(const ddps_ctx* ctx) { return ctx ? ctx->err.c_str()
 void ddps_default_opts(ddps_solver_opts* o) {
   memset(o, 0, sizeof(*o));
   o->lin_rtol = 1e-13;
-  o->newton_eta = 1e-10;
+  o->newton_eta = 1e-15;
   o->lin_max_it = 200000;
   o->max_newton = 0;
   o->max_gummel = 0;
@@ -737,8 +739,8 @@ int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats
     if (!(res > tol)) break;                                                                  // src:1040
     if (count >= cap) { ctx->fail(DDPS_ERR_NOCONV, "semlin: Newton iteration cap reached"); rc = DDPS_ERR_NOCONV; break; }
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
-    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, ctx->opts.lin_max_it,
-                   nullptr, nullptr);                                                         // src:1063
+    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
+                   ctx->opts.lin_max_it, nullptr, nullptr);                                   // src:1063
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
     if (rc) break;
@@ -885,7 +887,7 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
   if ((rc = require_mesh(ctx))) return rc;
   if (ctx->nranks != 1) { ctx->fail(DDPS_ERR_STATE, "debug exports are single-GPU"); return DDPS_ERR_STATE; }
   if ((rc = upload(ctx, ctx->b, rhs, (size_t)ctx->n_own)) || (rc = upload(ctx, ctx->x, x, (size_t)ctx->n_own))) return rc;
-  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, true, rtol, max_it, iters, relres);
+  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, true, rtol, 0.0, max_it, iters, relres);
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   DDPS_CUDA(cudaMemcpy(x, ctx->x, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost));
   return rc;
@@ -923,7 +925,7 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
   if (kernel == 2) {
     // fresh PCG state on the last assembled system; rtol 0 keeps the done flag down
     if ((rc = halo_exchange(ctx, ctx->p))) return rc;
-    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, false, 0.0, 1, nullptr, nullptr);
+    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, false, 0.0, -1.0, 1, nullptr, nullptr);
     if (rc != DDPS_ERR_NOCONV && rc != 0) return rc;
     DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
   }

@@ -77,7 +77,8 @@ struct PcgScalars {
   int pad0;
   unsigned cnt[4];  // last-block tickets
   double norm_inf;  // generic max-norm result
-  double norm_aux;
+  double rmax;      // ||r||_inf of the PCG residual
+  double thresh_inf;
 };
 
 struct HaloPlan {
@@ -230,7 +231,7 @@ int fetch_resid_norm(Context* ctx, double* host_out);  // norm_inf written by th
 int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it);
 // Jacobi-PCG: solve val*x = rhs; x holds the initial guess if x0_nonzero (else it is zeroed).
 int pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
-              double rtol, int64_t max_it, int64_t* iters_out, double* relres_out);
+              double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);
 
 // ---- comm.cu ----
 int halo_exchange(Context* ctx, double* vec);            // fill ghost part of a [n_loc] vector

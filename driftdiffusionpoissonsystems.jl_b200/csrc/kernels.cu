@@ -508,7 +508,7 @@ __global__ void k_pcg_init(int n, const double* __restrict__ rhs, const double* 
                            const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
                            double* partials, PcgScalars* scal) {
   __shared__ double sh_red[32];
-  double s_rz = 0.0, s_rr = 0.0, s_bb = 0.0;
+  double s_rz = 0.0, s_rr = 0.0, s_bb = 0.0, s_max = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double bi = rhs[i];
     const double ri = HAVE_Q ? bi - q[i] : bi;
@@ -516,21 +516,27 @@ __global__ void k_pcg_init(int n, const double* __restrict__ rhs, const double* 
     r[i] = ri;
     p[i] = zi;
     s_rz += ri * zi; s_rr += ri * ri; s_bb += bi * bi;
+    s_max = fmax(s_max, fabs(ri));
   }
   double v[3] = {s_rz, s_rr, s_bb}, tot[3];
-  if (grid_reduce<3, false>(v, partials, &scal->cnt[1], sh_red, tot)) {
-    if (threadIdx.x == 0) { scal->sums[0] = tot[0]; scal->sums[1] = tot[1]; scal->sums[2] = tot[2]; }
+  const bool last = grid_reduce<3, false>(v, partials, &scal->cnt[1], sh_red, tot);
+  if (last && threadIdx.x == 0) { scal->sums[0] = tot[0]; scal->sums[1] = tot[1]; scal->sums[2] = tot[2]; }
+  double vm[1] = {s_max}, totm[1];
+  if (grid_reduce<1, true>(vm, partials + 3 * gridDim.x, &scal->cnt[2], sh_red, totm)) {
+    if (threadIdx.x == 0) scal->rmax = totm[0];
   }
 }
 
-__global__ void k_pcg_start(PcgScalars* scal, double rtol) {
+// stop rule: ||r||_2 <= rtol*||rhs||_2  OR  ||r||_inf <= atol_inf
+__global__ void k_pcg_start(PcgScalars* scal, double rtol, double atol_inf) {
   scal->rz[0] = scal->sums[0];
   scal->rr = scal->sums[1];
   scal->bb = scal->sums[2];
   scal->thresh2 = rtol * rtol * scal->sums[2];
+  scal->thresh_inf = atol_inf;
   scal->iters = 0;
   scal->breakdown = 0;
-  scal->done = (scal->sums[1] <= scal->thresh2) ? 1 : 0;
+  scal->done = (scal->sums[1] <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
 }
 
 // x += alpha p; r -= alpha q; local sums {r.D^-1 r, r.r}
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const 
     return;
   }
   const double alpha = rz / pq;
-  double s_rz = 0.0, s_rr = 0.0;
+  double s_rz = 0.0, s_rr = 0.0, s_max = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double pi = p[i], qi = q[i];
     const double xi = x[i] + alpha * pi;
@@ -557,10 +563,14 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const 
     r[i] = ri;
     s_rz += ri * (dinv[i] * ri);
     s_rr += ri * ri;
+    s_max = fmax(s_max, fabs(ri));
   }
   double v[2] = {s_rz, s_rr}, tot[2];
-  if (grid_reduce<2, false>(v, partials, &scal->cnt[1], sh_red, tot)) {
-    if (threadIdx.x == 0) { scal->sums[1] = tot[0]; scal->sums[2] = tot[1]; }
+  const bool last = grid_reduce<2, false>(v, partials, &scal->cnt[1], sh_red, tot);
+  if (last && threadIdx.x == 0) { scal->sums[1] = tot[0]; scal->sums[2] = tot[1]; }
+  double vm[1] = {s_max}, totm[1];
+  if (grid_reduce<1, true>(vm, partials + 2 * gridDim.x, &scal->cnt[2], sh_red, totm)) {
+    if (threadIdx.x == 0) scal->rmax = totm[0];
   }
 }
 
@@ -576,7 +586,7 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_direction(int n, int par, int
   }
   const double rz_new = scal->sums[1], rr = scal->sums[2];
   const double rz_old = scal->rz[par];
-  const bool stop = (rr <= scal->thresh2) || (it + 1 >= max_it) || !(rr == rr);
+  const bool stop = (rr <= scal->thresh2) || (scal->rmax <= scal->thresh_inf) || (it + 1 >= max_it) || !(rr == rr);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     scal->rz[par ^ 1] = rz_new;
     scal->rr = rr;
@@ -602,6 +612,7 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
   int g2 = vec_grid(ctx, n, kVecBlock);
   k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal);
   if ((rc = allreduce_sum(ctx, &ctx->scal->sums[1], 2))) return rc;
+  if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
   k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->r, dinv, ctx->p, ctx->scal);
   ctx->stats.kernel_launches += 3;
   ctx->stats.spmv_total++;
@@ -609,7 +620,7 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
 }
 
 int pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
-              double rtol, int64_t max_it, int64_t* iters_out, double* relres_out) {
+              double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out) {
   const int n = ctx->n_own;
   int rc;
   if (max_it <= 0) max_it = 200000;
@@ -626,7 +637,8 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
     k_pcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, dinv, ctx->r, ctx->p, ctx->partials, ctx->scal);
   }
   if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 3))) return rc;
-  k_pcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol);
+  if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
+  k_pcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf);
   ctx->stats.kernel_launches += 2;
   DDPS_CUDA(cudaGetLastError());
 
@@ -652,7 +664,7 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
     ctx->fail(DDPS_ERR_BREAKDOWN, "PCG breakdown: p.Ap <= 0 (operator not SPD; u or v negative? SURVEY H3)");
     return DDPS_ERR_BREAKDOWN;
   }
-  if (!(S.rr <= S.thresh2)) {
+  if (!(S.rr <= S.thresh2 || S.rmax <= S.thresh_inf)) {
     ctx->fail(DDPS_ERR_NOCONV, "PCG hit the iteration cap (" + std::to_string(S.iters) + " its, relres " +
                                    std::to_string(S.bb > 0 ? sqrt(S.rr / S.bb) : 0.0) + ")");
     return DDPS_ERR_NOCONV;

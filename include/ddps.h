@@ -80,7 +80,8 @@ enum ddps_vector {
 
 typedef struct ddps_solver_opts {
   double lin_rtol;      /* PCG stop for the linear continuity solves: ||r||_2 <= lin_rtol*||b||_2   (default 1e-13) */
-  double newton_eta;    /* PCG stop for Newton corrections:          ||r||_2 <= newton_eta*||F||_2 (default 1e-10) */
+  double newton_eta;    /* PCG stop for Newton corrections: ||r||_inf <= 0.1*tol (so a linear problem converges in one
+                           Newton step like the reference's direct solve) OR ||r||_2 <= newton_eta*||F||_2 (default 1e-15) */
   int64_t lin_max_it;   /* PCG iteration cap per solve (default 200000) */
   int32_t max_newton;   /* Newton cap per solve, 0 = 1000 (the reference has none, src:368,1040) */
   int32_t max_gummel;   /* Gummel cap, 0 = 1000 (the reference has none, src:649) */

@@ -61,7 +61,6 @@ def test_MV_matches_golden(D, case):
         assert rel_max(M.data, G.data) <= CSR_TOL
         # Dirichlet rows are identity rows
         n0 = z["n"] - 1
-        assert np.all(M[n0].diagonal(0) == 0) or True
         Md = M.tocsr()
         for d in n0[:10]:
             row = Md.getrow(d)
@@ -164,7 +163,8 @@ def test_semlin_poly_functor(D, O):
     om = oracle_mesh(mesh)
     f = D.PolyRHS([lambda x, y: 1.0 + x * y, lambda x, y: 0 * x, lambda x, y: -0.5 + 0 * x])
     A = [lambda t: 2.0, lambda t: 0.0, lambda t: 0.0, lambda t: 0.5]
-    bd = [[1, 2, 3, 4], ["D", "N", "D", "D"], [lambda x, y: 0.1 * x, lambda x, y: 0.3 + 0 * x, lambda x, y: 0 * x, lambda x, y: 0.2 * y]]
+    gd = lambda x, y: 0.1 * x + 0.2 * y          # one global function: shared corner nodes get one value (Q5)
+    bd = [[1, 2, 3, 4], ["D", "N", "D", "D"], [gd, lambda x, y: 0.3 + 0 * x, gd, gd]]
     V = D.solve_semlin_poisson(mesh, A, bd, f, f.derivative(), 1e-13, verbose=False)
     Vo = O.solve_semlin_poisson(om, A, bd, f, f.derivative(), 1e-13)
     assert rel_l2(V, Vo) <= FIELD_TOL
@@ -261,11 +261,12 @@ def test_structured_large_properties(D):
         isD[s._ddpe_n - 1] = True
         ones = np.ones(mesh.nq)
         r = A @ ones
-        # rows far from the contacts: A*1 = 0 exactly in exact arithmetic
-        touch = np.asarray(abs(A)[:, isD].sum(axis=1)).ravel() > 0
-        far = ~isD
-        scale = np.abs(A).max()
-        assert np.max(np.abs(r[far] + (b[far] != 0) * 0)) <= 1e-9 * scale or True
+        # the un-eliminated stiffness annihilates constants: on rows outside D, (A*1)_i + lift_i(gD=1) = 0,
+        # so rows that do not touch a contact have A*1 = 0 up to rounding
+        touch = np.asarray(abs(A)[:, isD].sum(axis=1)).ravel() > 0      # eliminated columns are explicit zeros
+        far = ~isD & (b == 0)
+        assert far.sum() > 0.9 * mesh.nq
+        assert np.max(np.abs(r[far])) <= 1e-10 * np.abs(A.data).max()
         assert np.all(r[isD] == 1.0)
 
 
@@ -300,7 +301,7 @@ def test_pcg_breakdown_is_reported(D):
     pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=0.5)
     with _ddpe_session(D, mesh, pr) as s:
         V = np.zeros(mesh.nq)
-        bad = -1e6 * np.ones(mesh.nq)
+        bad = -2.95 * np.ones(mesh.nq)    # g_k = -v0/(tau_p(u0+1)+tau_n(v0+1)) = +59 -> M - J0 indefinite
         s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, np.ones(mesh.nq), bad)
         with pytest.raises(D.DDPSError) as ei:
             s.debug_pcg(np.ones(mesh.nq), rtol=1e-10, max_it=500)
