@@ -28,7 +28,7 @@ class Stats(C.Structure):
     _fields_ = [("outer_iters", C.c_int32), ("newton_total", C.c_int32), ("pcg_total", C.c_int64),
                 ("spmv_total", C.c_int64), ("kernel_launches", C.c_int64), ("control", C.c_double),
                 ("t_setup_ms", C.c_double), ("t_solve_ms", C.c_double), ("t_asm_ms", C.c_double),
-                ("t_pcg_ms", C.c_double), ("status", C.c_int32), ("n_negative_area", C.c_int32),
+                ("t_pcg_ms", C.c_double), ("t_wall_ms", C.c_double), ("status", C.c_int32), ("n_negative_area", C.c_int32),
                 ("reserved", C.c_int32 * 8)]
 
     def as_dict(self):

@@ -135,6 +135,22 @@ def _midpoints(mesh: Mesh):
     return mx, my
 
 
+def sample_ddpe(mesh: Mesh, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun):
+    """One-time host setup of solve_ddpe: evaluate the spatial closures where the reference
+    evaluates them (boundary nodes, centroids, edge midpoints) and return plain arrays."""
+    _, _, gD, n = aquire_boundary(mesh, Vbddata)                             # src:640
+    nu, gDu = dirichlet_nodes(mesh, ubddata)                                 # src:532-544
+    nv, gDv = dirichlet_nodes(mesh, vbddata)
+    if len(gDu) != len(n) or len(gDv) != len(n):
+        raise ValueError("DimensionMismatch: the u/v bddata must mark the same segments 'D' as the V bddata (src:563)")
+    cx, cy = _centroids(mesh)
+    mx, my = _midpoints(mesh)
+    return dict(n=n, gD_V=gD, gD_u=gDu, gD_v=gDv,
+                lambda2=_sample2(lam, cx, cy) ** 2,                          # src:254
+                mu_p=_sample2(mu_p, cx, cy), mu_n=_sample2(mu_n, cx, cy),    # src:467
+                C_mid=np.ascontiguousarray(_sample2(Cfun, mx, my)))          # src:341-343
+
+
 # --------------------------------------------------------------------------------------------
 # Session: one library context (= one GPU)
 # --------------------------------------------------------------------------------------------
@@ -212,23 +228,19 @@ class Session:
 
     # -- problem setup (host sampling of the spatial closures) --
     def setup_ddpe(self, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun):
-        mesh = self.mesh
-        _, _, gD, n = aquire_boundary(mesh, Vbddata)                         # src:640
-        nu, gDu = dirichlet_nodes(mesh, ubddata)                             # src:532-544
-        nv, gDv = dirichlet_nodes(mesh, vbddata)
-        if len(gDu) != len(n) or len(gDv) != len(n):
-            raise ValueError("DimensionMismatch: the u/v bddata must mark the same segments 'D' as the V bddata (src:563)")
+        self.upload_ddpe(sample_ddpe(self.mesh, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun))
+
+    def upload_ddpe(self, smp):
+        """Hand the sampled arrays of ``sample_ddpe`` to the library (host buffers -> HBM)."""
         # the reference pairs gD_u positionally with V's node list n (src:563-564)
-        self.set_dirichlet(FIELD_V, n, gD)
-        self.set_dirichlet(FIELD_U, n, gDu)
-        self.set_dirichlet(FIELD_W, n, gDv)
-        cx, cy = _centroids(mesh)
-        self.set_coeff(COEFF_LAMBDA2, _sample2(lam, cx, cy) ** 2)            # src:254
-        self.set_coeff(COEFF_MU_P, _sample2(mu_p, cx, cy))                   # src:467
-        self.set_coeff(COEFF_MU_N, _sample2(mu_n, cx, cy))
-        mx, my = _midpoints(mesh)
-        self.set_coeff(COEFF_C_MID, _sample2(Cfun, mx, my))                  # src:341-343
-        self._ddpe_n = n
+        self.set_dirichlet(FIELD_V, smp["n"], smp["gD_V"])
+        self.set_dirichlet(FIELD_U, smp["n"], smp["gD_u"])
+        self.set_dirichlet(FIELD_W, smp["n"], smp["gD_v"])
+        self.set_coeff(COEFF_LAMBDA2, smp["lambda2"])
+        self.set_coeff(COEFF_MU_P, smp["mu_p"])
+        self.set_coeff(COEFF_MU_N, smp["mu_n"])
+        self.set_coeff(COEFF_C_MID, smp["C_mid"])
+        self._ddpe_n = smp["n"]
 
     def ddpe_begin(self, rec_mode, delta, tau_p, tau_n, tol):
         self._check(self.lib.ddps_ddpe_begin(self.h, REC_MODES[str(rec_mode)], float(delta), float(tau_p),
@@ -260,6 +272,11 @@ class Session:
         if not isinstance(f, (SinhRHS, PolyRHS)):
             raise TypeError("f must be a registered functor (SinhRHS / PolyRHS): arbitrary closures cannot run on "
                             "the device and this path has no CPU fallback")
+        # g is evaluated on the device from the functor's parameters: make sure the closure the caller passed is
+        # that derivative (the reference would silently use whatever g it is given, src:1046)
+        xs, ys, us = np.array([0.1, -0.3, 0.7]), np.array([0.2, 0.5, -0.4]), np.array([0.3, -0.6, 1.1])
+        if not np.allclose(np.asarray(g(xs, ys, us), dtype=float) + 0 * xs, f.derivative()(xs, ys, us), rtol=1e-10, atol=1e-12):
+            raise ValueError("g must be the u-derivative of the registered functor f (use f.derivative())")
         gtag = mesh.elements[4].astype(np.float64)
         utag = np.unique(gtag)
         a11 = {t: float(A[0](t)) for t in utag}                              # src:901 (A is called on the geometric tag)

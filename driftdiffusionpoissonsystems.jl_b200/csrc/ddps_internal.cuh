@@ -94,7 +94,7 @@ struct HaloPlan {
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
   int num_sms = 148;
   std::string err;
   int err_code = 0;
@@ -221,6 +221,7 @@ int launch_prep_uv(Context* ctx, double sign, const double* V, const double* oth
 int launch_prep_semlin(Context* ctx, const double* V);
 
 int launch_spmv(Context* ctx, const double* val, const double* x, double* y);
+int launch_spmv_dot(Context* ctx, const double* val, const double* x, double* y);  // the PCG variant (fused p.Ap)
 int launch_axpy(Context* ctx, double a, const double* x, double* y, int n);          // y += a*x
 int launch_negate_copy(Context* ctx, const double* x, double* y, double s, int n);   // y = s*x
 int launch_max_abs_diff3(Context* ctx, const double* a0, const double* a1, const double* b0, const double* b1,

@@ -404,8 +404,7 @@ __global__ void __launch_bounds__(kVecBlock) k_spmv(int nrows, int nslices, cons
 static inline int vec_grid(Context* ctx, int64_t work_items, int block) {
   int64_t need = (work_items + block - 1) / block;
   int64_t cap = (int64_t)ctx->num_sms * (2048 / block);
-  int g = (int)std::max<int64_t>(1, std::min(need, cap));
-  return std::min(g, ctx->partial_cap > 0 ? ctx->partial_cap : g);
+  return (int)std::max<int64_t>(1, std::min(need, cap));
 }
 
 int launch_spmv(Context* ctx, const double* val, const double* x, double* y) {
@@ -413,6 +412,17 @@ int launch_spmv(Context* ctx, const double* val, const double* x, double* y) {
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   k_spmv<false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr);
+  ctx->stats.kernel_launches++;
+  ctx->stats.spmv_total++;
+  DDPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_spmv_dot(Context* ctx, const double* val, const double* x, double* y) {
+  const Pattern& P = ctx->pat;
+  if (!P.nslices) return 0;
+  int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
+  k_spmv<true><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());

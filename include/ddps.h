@@ -102,6 +102,7 @@ typedef struct ddps_stats {
   double t_solve_ms;       /* device-resident loop, CUDA events on the library stream */
   double t_asm_ms;         /* summed CUDA-event time of assembly kernels */
   double t_pcg_ms;         /* summed CUDA-event time of PCG */
+  double t_wall_ms;        /* host wall clock around the same region as t_solve_ms */
   int32_t status;          /* DDPS_OK / DDPS_ERR_NOCONV / DDPS_ERR_BREAKDOWN */
   int32_t n_negative_area; /* elements with signed area < 0 (Q2: mass uses signed ar, src:375) */
   int32_t reserved[8];
@@ -182,7 +183,8 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
 
 /* ---- in-library kernel timing (CUDA events on the library's own stream) --------------------
  * kernel 0: SpMV on DDPS_MAT_OP; 1: continuity-system assembly (uvsolve A+b, src:433-588);
- * 2: one full PCG iteration; 3: Newton-system assembly (Vsolve, src:368-420); 4: base stiffness.
+ * 2: one full PCG iteration; 3: Newton-system assembly (Vsolve, src:368-420); 4: base stiffness;
+ * 5: the PCG's SpMV with the fused p.Ap dot.
  * Runs `reps` launches after `warm` untimed ones and returns the mean milliseconds per launch and
  * the algorithmic bytes of one launch (definition in DESIGN.md). */
 int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_per_launch, double* algo_bytes);
