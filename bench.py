@@ -136,6 +136,9 @@ def main():
     ap.add_argument("--workload", default="s16", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pcg-cap", type=int, default=0,
+                    help="PROFILING ONLY: cap every PCG solve at this many iterations (keeps an ncu launch list short); "
+                         "the printed value is then not a benchmark number")
     args = ap.parse_args()
     nx, ny = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -170,6 +173,8 @@ def main():
     mesh = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
     smp = D.api.sample_ddpe(mesh, pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
     s = D.Session(local, comm=comm)
+    if args.pcg_cap > 0:
+        s.set_opts(lin_max_it=args.pcg_cap, lin_cap_ok=1, max_newton=3)
     s.set_mesh(mesh)
     s.upload_ddpe(smp)
     s.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
@@ -267,6 +272,8 @@ def main():
                            "solver": "Jacobi-PCG, lin_rtol 1e-13, Newton corrections to 0.1*tol"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "pcg_iterations": int(pcg_its),
                 "control": [float(c) for c in ctrl], "roofline": roofline, "cpu_baseline": cpu}
+        if args.pcg_cap > 0:
+            line["invalid"] = f"profiling run: PCG capped at {args.pcg_cap} iterations per solve"
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

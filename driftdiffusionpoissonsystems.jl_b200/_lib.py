@@ -21,7 +21,7 @@ c_int32_p = C.POINTER(C.c_int32)
 class SolverOpts(C.Structure):
     _fields_ = [("lin_rtol", C.c_double), ("newton_eta", C.c_double), ("lin_max_it", C.c_int64),
                 ("max_newton", C.c_int32), ("max_gummel", C.c_int32), ("check_every", C.c_int32),
-                ("warm_start", C.c_int32), ("verbose", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("warm_start", C.c_int32), ("verbose", C.c_int32), ("lin_cap_ok", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class Stats(C.Structure):
@@ -47,6 +47,8 @@ SIGNATURES = {
     "ddps_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "ddps_mesh_set": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_int64_p, C.c_int64]),
     "ddps_partition_nodes": (C.c_int, [c_double_p, C.c_int64, C.c_int, c_int32_p]),
+    "ddps_partition_plan": (C.c_int, [c_double_p, C.c_int64, c_int64_p, C.c_int64, C.c_int, C.c_int, c_int64_p, c_int64_p,
+                                      c_int32_p, c_int64_p, c_int64_p, c_int64_p]),
     "ddps_dirichlet_set": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_double_p, C.c_int64]),
     "ddps_coeff_set": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int64]),
     "ddps_functor_set": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int]),

@@ -113,6 +113,74 @@ int download_nodal(Context* ctx, const double* src_local, double* dst_global) {
   return rc;
 }
 
+
+// ---- node partition + local mesh extraction (host code; also behind ddps_partition_plan) -------
+struct LocalMesh {
+  int n_own = 0, n_loc = 0;
+  std::vector<int64_t> loc2glob, elem_glob;
+  std::vector<int4> elem;
+  std::vector<int> peers, send_off, recv_off, send_idx;
+};
+
+// Rank `me` owns the nodes RCB assigns to it and keeps every triangle that touches an owned node
+// (one redundantly-assembled ghost layer => no communication in assembly).  Local numbering:
+// owned nodes in increasing global id, then ghosts sorted by (owner, global id); triangles in
+// increasing global id (so every row sums its triangles in the same order as on one GPU).
+// Send list to peer q = my owned corners of triangles that touch a q-owned node, sorted by global id
+// -- exactly q's ghost block for me, in the same order, so no setup communication is needed.
+int build_local_mesh(const double* nodes, int64_t nq, const int64_t* elements, int64_t nme, int nparts, int me,
+                     LocalMesh& L, std::string& err) {
+  std::vector<int32_t> owner(nq);
+  partition_nodes_rcb(nodes, nq, nparts, owner.data());
+  std::vector<int32_t> g2l(nq, -1);
+  std::vector<std::pair<int, int64_t>> ghosts, sends;   // (peer, global id)
+  for (int64_t e = 0; e < nme; ++e) {
+    const int64_t* c = elements + 5 * e;
+    int64_t g[3] = {c[0] - 1, c[1] - 1, c[2] - 1};
+    for (int k = 0; k < 3; ++k)
+      if (g[k] < 0 || g[k] >= nq) { err = "element " + std::to_string(e + 1) + " references a node outside 1..nq"; return -1; }
+    int o[3] = {owner[g[0]], owner[g[1]], owner[g[2]]};
+    if (o[0] != me && o[1] != me && o[2] != me) continue;
+    L.elem_glob.push_back(e);
+    for (int k = 0; k < 3; ++k) {
+      if (o[k] != me) ghosts.emplace_back(o[k], g[k]);
+      else
+        for (int j = 0; j < 3; ++j)
+          if (o[j] != me) sends.emplace_back(o[j], g[k]);
+    }
+  }
+  auto uniq = [](std::vector<std::pair<int, int64_t>>& v) {
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+  };
+  uniq(ghosts); uniq(sends);
+  for (int64_t i = 0; i < nq; ++i) if (owner[i] == me) ++L.n_own;
+  L.n_loc = L.n_own + (int)ghosts.size();
+  L.loc2glob.resize(L.n_loc);
+  int k = 0;
+  for (int64_t i = 0; i < nq; ++i) if (owner[i] == me) { g2l[i] = k; L.loc2glob[k] = i; ++k; }
+  for (auto& pr : ghosts) { g2l[pr.second] = k; L.loc2glob[k] = pr.second; ++k; }
+  for (auto& pr : ghosts) L.peers.push_back(pr.first);
+  for (auto& pr : sends) L.peers.push_back(pr.first);
+  std::sort(L.peers.begin(), L.peers.end());
+  L.peers.erase(std::unique(L.peers.begin(), L.peers.end()), L.peers.end());
+  const int nn = (int)L.peers.size();
+  L.send_off.assign(nn + 1, 0); L.recv_off.assign(nn + 1, 0);
+  for (int j = 0; j < nn; ++j) {
+    for (auto& pr : sends) if (pr.first == L.peers[j]) L.send_idx.push_back(g2l[pr.second]);
+    L.send_off[j + 1] = (int)L.send_idx.size();
+    int cnt = 0;
+    for (auto& pr : ghosts) if (pr.first == L.peers[j]) ++cnt;
+    L.recv_off[j + 1] = L.recv_off[j] + cnt;   // ghosts are sorted by (peer, gid) = local ghost order
+  }
+  L.elem.resize(L.elem_glob.size());
+  for (size_t i = 0; i < L.elem_glob.size(); ++i) {
+    const int64_t* c = elements + 5 * L.elem_glob[i];
+    L.elem[i] = make_int4(g2l[c[0] - 1], g2l[c[1] - 1], g2l[c[2] - 1], (int)c[4]);
+  }
+  return 0;
+}
+
 AsmArgs base_args(Context* ctx) {
   AsmArgs a;
   memset(&a, 0, sizeof(a));
@@ -232,7 +300,11 @@ int vsolve(Context* ctx) {
     if ((rc = fetch_resid_norm(ctx, &res))) return rc;
     ctx->stats.t_asm_ms += ta.ms();
     if (!(res > ctx->tol)) break;                                                            // src:368
-    if (newton >= cap) { ctx->fail(DDPS_ERR_NOCONV, "Vsolve: Newton iteration cap reached"); return DDPS_ERR_NOCONV; }
+    if (newton >= cap) {
+      if (ctx->opts.lin_cap_ok) break;   // profiling runs only
+      ctx->fail(DDPS_ERR_NOCONV, "Vsolve: Newton iteration cap reached");
+      return DDPS_ERR_NOCONV;
+    }
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
     // Newton correction: the linear residual only has to be below the Newton tolerance (so that, like the
     // reference's direct solve, a linear problem converges in one step); newton_eta is a relative floor.
@@ -383,6 +455,24 @@ int ddps_partition_nodes(const double* nodes, int64_t nq, int nparts, int32_t* o
   return DDPS_OK;
 }
 
+int ddps_partition_plan(const double* nodes, int64_t nq, const int64_t* elements, int64_t nme, int nparts, int rank,
+                        int64_t counts[4], int64_t* loc2glob, int32_t* peers, int64_t* send_counts, int64_t* recv_counts,
+                        int64_t* send_glob) {
+  if (!nodes || !elements || !counts || nq <= 0 || nme <= 0 || nparts < 1 || rank < 0 || rank >= nparts) return DDPS_ERR_ARG;
+  LocalMesh L;
+  std::string err;
+  if (build_local_mesh(nodes, nq, elements, nme, nparts, rank, L, err)) return DDPS_ERR_ARG;
+  counts[0] = L.n_own; counts[1] = L.n_loc - L.n_own; counts[2] = (int64_t)L.elem_glob.size(); counts[3] = (int64_t)L.peers.size();
+  if (loc2glob) for (int i = 0; i < L.n_loc; ++i) loc2glob[i] = L.loc2glob[i];
+  for (size_t j = 0; j < L.peers.size(); ++j) {
+    if (peers) peers[j] = L.peers[j];
+    if (send_counts) send_counts[j] = L.send_off[j + 1] - L.send_off[j];
+    if (recv_counts) recv_counts[j] = L.recv_off[j + 1] - L.recv_off[j];
+  }
+  if (send_glob) for (size_t i = 0; i < L.send_idx.size(); ++i) send_glob[i] = L.loc2glob[L.send_idx[i]];
+  return DDPS_OK;
+}
+
 int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t* elements, int64_t nme) {
   if (!ctx) return DDPS_ERR_ARG;
   cudaSetDevice(ctx->device);
@@ -410,73 +500,21 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     if ((rc = dev_alloc(ctx, &ctx->xy, (size_t)nq))) return rc;
     if ((rc = upload(ctx, (double*)ctx->xy, nodes, (size_t)2 * nq))) return rc;
   } else {
-    // ---- node partition by recursive coordinate bisection; every rank computes the same owner[] ----
-    std::vector<int32_t> owner(nq);
-    partition_nodes_rcb(nodes, nq, ctx->nranks, owner.data());
-    const int me = ctx->rank;
-    std::vector<int32_t> g2l(nq, -1);
-    std::vector<std::pair<int, int64_t>> ghosts, sends;   // (peer, global id)
-    std::vector<int64_t> eg;
-    for (int64_t e = 0; e < nme; ++e) {
-      const int64_t* c = elements + 5 * e;
-      int64_t g[3] = {c[0] - 1, c[1] - 1, c[2] - 1};
-      for (int k = 0; k < 3; ++k)
-        if (g[k] < 0 || g[k] >= nq) {
-          ctx->fail(DDPS_ERR_ARG, "element " + std::to_string(e + 1) + " references a node outside 1..nq");
-          return DDPS_ERR_ARG;
-        }
-      int o[3] = {owner[g[0]], owner[g[1]], owner[g[2]]};
-      if (o[0] != me && o[1] != me && o[2] != me) continue;
-      eg.push_back(e);
-      for (int k = 0; k < 3; ++k) {
-        if (o[k] != me) ghosts.emplace_back(o[k], g[k]);
-        else
-          for (int j = 0; j < 3; ++j)
-            if (o[j] != me) sends.emplace_back(o[j], g[k]);
-      }
-    }
-    auto uniq = [](std::vector<std::pair<int, int64_t>>& v) {
-      std::sort(v.begin(), v.end());
-      v.erase(std::unique(v.begin(), v.end()), v.end());
-    };
-    uniq(ghosts); uniq(sends);
-    int n_own = 0;
-    for (int64_t i = 0; i < nq; ++i) if (owner[i] == me) ++n_own;
-    ctx->n_own = n_own;
-    ctx->n_loc = n_own + (int)ghosts.size();
-    ctx->loc2glob.resize(ctx->n_loc);
-    int k = 0;
-    for (int64_t i = 0; i < nq; ++i) if (owner[i] == me) { g2l[i] = k; ctx->loc2glob[k] = i; ++k; }
-    for (auto& pr : ghosts) { g2l[pr.second] = k; ctx->loc2glob[k] = pr.second; ++k; }
-    // halo plan: neighbours = union of peers in ghosts and sends
-    std::vector<int> peers;
-    for (auto& pr : ghosts) peers.push_back(pr.first);
-    for (auto& pr : sends) peers.push_back(pr.first);
-    std::sort(peers.begin(), peers.end());
-    peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+    LocalMesh L;
+    std::string perr;
+    if (build_local_mesh(nodes, nq, elements, nme, ctx->nranks, ctx->rank, L, perr)) { ctx->fail(DDPS_ERR_ARG, perr); return DDPS_ERR_ARG; }
+    ctx->n_own = L.n_own;
+    ctx->n_loc = L.n_loc;
+    ctx->loc2glob = L.loc2glob;
     HaloPlan& H = ctx->halo;
-    H.nneigh = (int)peers.size(); H.peer = peers;
-    H.send_off.assign(H.nneigh + 1, 0); H.recv_off.assign(H.nneigh + 1, 0);
-    std::vector<int> sidx;
-    for (int j = 0; j < H.nneigh; ++j) {
-      for (auto& pr : sends) if (pr.first == peers[j]) sidx.push_back(g2l[pr.second]);
-      H.send_off[j + 1] = (int)sidx.size();
-      int cnt = 0;
-      for (auto& pr : ghosts) if (pr.first == peers[j]) ++cnt;
-      H.recv_off[j + 1] = H.recv_off[j] + cnt;   // ghosts are sorted by (peer, gid) = local ghost order
-    }
-    H.nsend = (int)sidx.size();
-    if ((rc = dev_alloc(ctx, &H.send_idx, sidx.size()))) return rc;
-    if ((rc = dev_alloc(ctx, &H.send_buf, sidx.size()))) return rc;
-    if ((rc = upload(ctx, H.send_idx, sidx.data(), sidx.size()))) return rc;
-    // local mesh
-    ctx->nme = (int)eg.size();
-    ctx->elem_glob = eg;
-    hel.resize(eg.size());
-    for (size_t i = 0; i < eg.size(); ++i) {
-      const int64_t* c = elements + 5 * eg[i];
-      hel[i] = make_int4(g2l[c[0] - 1], g2l[c[1] - 1], g2l[c[2] - 1], (int)c[4]);
-    }
+    H.nneigh = (int)L.peers.size(); H.peer = L.peers; H.send_off = L.send_off; H.recv_off = L.recv_off;
+    H.nsend = (int)L.send_idx.size();
+    if ((rc = dev_alloc(ctx, &H.send_idx, L.send_idx.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &H.send_buf, L.send_idx.size()))) return rc;
+    if ((rc = upload(ctx, H.send_idx, L.send_idx.data(), L.send_idx.size()))) return rc;
+    ctx->nme = (int)L.elem_glob.size();
+    ctx->elem_glob = L.elem_glob;
+    hel = L.elem;
     std::vector<double> hxy((size_t)2 * ctx->n_loc);
     for (int i = 0; i < ctx->n_loc; ++i) { hxy[2 * i] = nodes[2 * ctx->loc2glob[i]]; hxy[2 * i + 1] = nodes[2 * ctx->loc2glob[i] + 1]; }
     if ((rc = dev_alloc(ctx, &ctx->xy, (size_t)ctx->n_loc))) return rc;

@@ -53,6 +53,7 @@ struct Pattern {
   int64_t nnz = 0;      // true nonzeros of the owned rows
   int64_t nentries = 0; // stored entries incl. padding (= slice_ptr[nslices])
   int max_row_len = 0;
+  int max_inc = 0;      // largest number of triangles around a node
   int* slice_ptr = nullptr;  // [nslices+1]
   int* col = nullptr;        // [nentries] slice-interleaved
   int* rowptr = nullptr;     // [nrows+1] plain CSR (export + slot search)
@@ -60,7 +61,7 @@ struct Pattern {
   // incidence lists
   int64_t inc_entries = 0;
   int* inc_slice_ptr = nullptr;  // [nslices+1]
-  int2* inc = nullptr;           // [inc_entries] {tri*4+corner | -1, slot_self | slot_next<<8 | slot_prev<<16}
+  int4* inc = nullptr;           // [inc_entries] {tri*4+corner | -1, slot_self | slot_next<<8 | slot_prev<<16 | ord bits, next node, prev node}
 };
 
 // device-side scalar block of one PCG solve (all control flow stays on the device)
@@ -177,7 +178,7 @@ struct AsmArgs {
   const int* slice_ptr;
   const int* col;
   const int* inc_slice_ptr;
-  const int2* inc;
+  const int4* inc;
   const double2* xy;
   const int4* elem;
   const unsigned char* isD;

@@ -83,152 +83,222 @@ __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p);
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 
 // ------------------------------------------------------------------------------------------------
-// Row-major fused assembly
+// Row-major fused assembly.
+//
+// Thread mapping: one CTA per 32-row slice; warp k of the CTA handles incidence k (the k-th incident
+// triangle, in increasing triangle order) of ALL 32 rows, lane = row.  Every stream that is stored
+// slice-interleaved (incidence records, matrix values, columns) is therefore read/written as one
+// fully coalesced 256-byte warp access, neighbouring lanes gather neighbouring triangles/nodes, and
+// a row's ~6 dependent load chains run in 6 different warps instead of back to back in one thread.
+//
+// Deterministic, atomic-free scatter: an off-diagonal entry (i,j) receives at most two contributions
+// (the two triangles sharing edge ij; checked at setup).  The setup marks every contribution as the
+// first or the second one in increasing triangle order, the kernel stores them into two separate
+// shared-memory planes (accA/accB) and adds A+B after ONE barrier.  The diagonal, the load and the
+// lifting receive one contribution per incident triangle; those are staged per incidence index and
+// summed in incidence order.  The result is bitwise reproducible and uses the same summation order
+// as the reference's sparse() (increasing triangle id per entry).
 // ------------------------------------------------------------------------------------------------
 template <int STIFF, bool MASS, int RHS, bool RESID>
-__global__ void __launch_bounds__(kAsmBlock) k_assemble(const AsmArgs P) {
-  extern __shared__ double acc[];  // [w][kAsmBlock], column tid is private to the thread
-  __shared__ double sh_red[32];
-  const int tid = threadIdx.x;
-  const int row = blockIdx.x * kAsmBlock + tid;
-  const int slice = row >> 5, lane = row & 31;
-  double fres = 0.0;
-  if (slice < P.nslices) {
-    const int base = P.slice_ptr[slice];
-    const int w = (P.slice_ptr[slice + 1] - base) >> 5;
-    for (int k = 0; k < w; ++k) acc[k * kAsmBlock + tid] = 0.0;
-    if (row < P.nrows) {
-      const bool rowD = P.isD[row] != 0;
-      const int ibase = P.inc_slice_ptr[slice];
-      const int iw = (P.inc_slice_ptr[slice + 1] - ibase) >> 5;
-      double bsum = 0.0, lift = 0.0;
-      int sdiag = 0;
-      // own-node values of the rhs functor
-      double own_u = 0.0, own_v = 0.0, own_eh = 0.0, own_ehi = 0.0;
-      if (RHS == RHS_DDP || RHS == RHS_SRH) {
-        own_u = P.fu[row]; own_v = P.fv[row]; own_eh = P.EH[row]; own_ehi = P.EHi[row];
-      } else if (RHS == RHS_SINH || RHS == RHS_POLY) {
-        own_eh = P.EH[row];
-      }
-      for (int k = 0; k < iw; ++k) {
-        const int2 rec = P.inc[ibase + k * 32 + lane];
-        if (rec.x < 0) continue;
-        const int e = rec.x >> 2, a = rec.x & 3;
-        const int4 el = P.elem[e];
-        const double2 q1 = P.xy[el.x], q2 = P.xy[el.y], q3 = P.xy[el.z];
-        // edge vectors and signed area, src:243-246
-        const double ux = q2.x - q3.x, uy = q2.y - q3.y;
-        const double vx = q3.x - q1.x, vy = q3.y - q1.y;
-        const double wx = q1.x - q2.x, wy = q1.y - q2.y;
-        const double ar = (ux * vy - uy * vx) / 2.0;
-        const int nb = (a == 0) ? el.y : (a == 1) ? el.z : el.x;  // next corner (cyclic)
-        const int nc = (a == 0) ? el.z : (a == 1) ? el.x : el.y;  // previous corner
-        const int s_self = rec.y & 255, s_next = (rec.y >> 8) & 255, s_prev = (rec.y >> 16) & 255;
-        sdiag = s_self;
-        double c_self = 0.0, c_next = 0.0, c_prev = 0.0;  // contributions to A = M_elim - J0
-        if (STIFF != STIFF_BASE) {
-          double phx, phy;
-          if (STIFF == STIFF_COEF) { phx = P.phx[e]; phy = P.phy[e]; }
-          else { phx = P.phx[e] * (P.E3[el.x] * P.E3[el.y] * P.E3[el.z]); phy = phx; }  // src:469
-          const double ar4 = fabs(ar * 4.0);  // src:257
-          // canonical lower-triangle entries K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/ar4, i>=j
-          // (src:260-266); select the row of corner a: self, next, prev.
-          const double sx = (a == 0) ? ux : (a == 1) ? vx : wx, sy = (a == 0) ? uy : (a == 1) ? vy : wy;
-          // (hi,lo) edge pair for the (a,next) and (a,prev) entries
-          const double nhx = (a == 0) ? vx : wx, nhy = (a == 0) ? vy : wy;           // next: (2,1),(3,2),(3,1)
-          const double nlx = (a == 1) ? vx : ux, nly = (a == 1) ? vy : uy;
-          const double phx_ = phx, phy_ = phy;
-          const double khx = (a == 2) ? wx : (a == 0) ? wx : vx, khy = (a == 2) ? wy : (a == 0) ? wy : vy;  // prev: (3,1),(2,1),(3,2)
-          const double klx = (a == 2) ? vx : ux, kly = (a == 2) ? vy : uy;
-          const double k_self = (sx * phx_ * sx + sy * phy_ * sy) / ar4;
-          const double k_next = (nhx * phx_ * nlx + nhy * phy_ * nly) / ar4;
-          const double k_prev = (khx * phx_ * klx + khy * phy_ * kly) / ar4;
-          const bool nbD = P.isD[nb] != 0, ncD = P.isD[nc] != 0;
-          // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
-          c_self = rowD ? 0.0 : k_self;
-          c_next = (rowD || nbD) ? 0.0 : k_next;
-          c_prev = (rowD || ncD) ? 0.0 : k_prev;
-          // boundary lifting b -= K[:,D]*gD on rows outside D, src:362
-          if (!rowD) {
-            if (nbD) lift += k_next * P.gD[nb];
-            if (ncD) lift += k_prev * P.gD[nc];
-          }
-        }
-        if (MASS) {
-          // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never
-          // eliminated (Q3)
-          const double W1 = P.gw[el.x] * ar / 30.0, W2 = P.gw[el.y] * ar / 30.0, W3 = P.gw[el.z] * ar / 30.0;
-          double m_self, m_next, m_prev;
-          if (a == 0) { m_self = 3.0 * W1 + W2 + W3; m_next = W1 + W2 + W3 / 2.0; m_prev = W1 + W2 / 2.0 + W3; }
-          else if (a == 1) { m_self = W1 + 3.0 * W2 + W3; m_next = W1 / 2.0 + W2 + W3; m_prev = W1 + W2 + W3 / 2.0; }
-          else { m_self = W1 + W2 + 3.0 * W3; m_next = W1 + W2 / 2.0 + W3; m_prev = W1 / 2.0 + W2 + W3; }
-          c_self -= m_self; c_next -= m_next; c_prev -= m_prev;
-        }
-        if (STIFF != STIFF_BASE || MASS) {
-          acc[s_self * kAsmBlock + tid] += c_self;
-          acc[s_next * kAsmBlock + tid] += c_next;
-          acc[s_prev * kAsmBlock + tid] += c_prev;
-        }
-        // lumped edge-midpoint load: corner a takes the midpoint between a and next (src:345-350, Q1)
-        if (RHS != RHS_NONE && RHS != RHS_ZERO) {
-          double f;
-          if (RHS == RHS_DDP) {   // src:341-343
-            const double ua = (own_u + P.fu[nb]) / 2.0, va = (own_v + P.fv[nb]) / 2.0;
-            const double eS = own_eh * P.EH[nb], eSi = own_ehi * P.EHi[nb];
-            f = P.par0 * (eSi * va - eS * ua) + P.mid[3 * (size_t)e + a];
-          } else if (RHS == RHS_SRH) {  // src:517-519
-            const double ua = (own_u + P.fu[nb]) / 2.0, va = (own_v + P.fv[nb]) / 2.0;
-            const double eS = own_eh * P.EH[nb], eSi = own_ehi * P.EHi[nb];
-            f = 1.0 / (P.par0 * (eS * ua + 1.0) + P.par1 * (eSi * va + 1.0));
-          } else if (RHS == RHS_SINH) {  // registered functor, test:95
-            const double S = (own_eh + P.EH[nb]) / 2.0;
-            f = P.mid[3 * (size_t)e + a] + P.par0 * sinh(P.par1 * S);
-          } else {  // RHS_POLY, README:107-108
-            const double S = (own_eh + P.EH[nb]) / 2.0;
-            const int deg = (int)P.par0;
-            f = P.mid_poly[deg][3 * (size_t)e + a];
-            for (int d = deg - 1; d >= 0; --d) f = f * S + P.mid_poly[d][3 * (size_t)e + a];
-          }
-          bsum += f * fabs(ar) / 3.0;  // src:349
-        }
-      }
-      // ---- finalize the row ----
-      if (STIFF != STIFF_BASE && rowD) acc[sdiag * kAsmBlock + tid] += 1.0;  // src:279-281
-      double diag = 0.0, mv = 0.0;
-      for (int k = 0; k < w; ++k) {
-        const int idx = base + k * 32 + lane;
-        double a_k = acc[k * kAsmBlock + tid];
-        if (STIFF == STIFF_BASE) {
-          const double m_k = ld_stream(P.base_val + idx);
-          if (RESID) mv += m_k * P.xvec[ld_stream(P.col + idx)];
-          a_k += m_k;
-        }
-        if (k == sdiag) diag = a_k;
-        P.out_val[idx] = a_k;
-      }
-      if (P.dinv) P.dinv[row] = 1.0 / diag;
-      if (STIFF != STIFF_BASE && P.lift_out) P.lift_out[row] = lift;
-      if (RHS != RHS_NONE) {
-        if (STIFF == STIFF_BASE) lift = P.lift_in[row];
-        double bi = bsum;
-        if (P.nodal_const) bi += P.nodal_const[row];   // Neumann loads, src:994-996
-        bi -= lift;                                    // src:362
-        if (rowD) bi = P.gD[row];                      // src:363
-        P.b[row] = bi;
-        if (RESID) {
-          const double F = mv - bi;                    // src:368
-          P.resid[row] = F;
-          fres = fabs(F);
-        }
-      }
-    } else {
-      for (int k = 0; k < w; ++k) P.out_val[base + k * 32 + lane] = 0.0;
-    }
+__global__ void __launch_bounds__(256) k_assemble(const AsmArgs P) {
+  extern __shared__ double sm[];
+  __shared__ int s_diag[32];
+  __shared__ double s_dsum[32], s_bsum[32], s_lsum[32], s_dval[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int slice = blockIdx.x;
+  const int row = slice * 32 + lane;
+  const bool live = row < P.nrows;
+  const int base = P.slice_ptr[slice];
+  const int w = (P.slice_ptr[slice + 1] - base) >> 5;
+  const int ibase = P.inc_slice_ptr[slice];
+  const int iw = (P.inc_slice_ptr[slice + 1] - ibase) >> 5;
+  double* accA = sm;                    // [w][32] first contribution of every off-diagonal slot
+  double* accB = accA + w * 32;         // [w][32] second contribution
+  double* stS = accB + w * 32;          // [nw][32] diagonal contribution of incidence k
+  double* stB = stS + nw * 32;          // [nw][32] load contribution
+  double* stL = stB + nw * 32;          // [nw][32] lifting contribution
+  double* prod = stL + nw * 32;         // [w][32] base*x products (RESID)
+
+  // ---- load stage 1: everything that does not depend on another load is issued up front -----------
+  // (the kernel is latency-bound: a CTA's life is [#dependent load stages] x [DRAM latency], so the
+  //  chain is kept at two stages: {records, own-node data, matrix slot} -> {neighbour data, x gather})
+  const int k_first = warp;                                  // incidence handled in pass 0
+  int4 rec = make_int4(-1, 0, 0, 0);
+  if (k_first < iw && live) rec = P.inc[ibase + k_first * 32 + lane];
+  const int rr = live ? row : 0;
+  const double2 q_own = P.xy[rr];
+  const bool rowD = live && P.isD[rr] != 0;
+  double own_g = 0.0, own_e3 = 0.0, own_u = 0.0, own_v = 0.0, own_eh = 0.0, own_ehi = 0.0;
+  if (MASS) own_g = P.gw[rr];
+  if (STIFF == STIFF_EXPV) own_e3 = P.E3[rr];
+  if (RHS == RHS_DDP || RHS == RHS_SRH) { own_u = P.fu[rr]; own_v = P.fv[rr]; own_eh = P.EH[rr]; own_ehi = P.EHi[rr]; }
+  if (RHS == RHS_SINH || RHS == RHS_POLY) own_eh = P.EH[rr];
+  double m_slot = 0.0;   // base matrix entry of the slot this warp writes first (slot = warp)
+  int c_slot = 0;
+  if (STIFF == STIFF_BASE && warp < w) {
+    m_slot = ld_stream(P.base_val + base + warp * 32 + lane);
+    if (RESID) c_slot = ld_stream(P.col + base + warp * 32 + lane);
   }
-  if (RESID) {
-    double v[1] = {fres}, tot[1];
-    if (grid_reduce<1, true>(v, P.partial_max, &P.scal->cnt[3], sh_red, tot)) {
-      if (threadIdx.x == 0) P.scal->norm_inf = tot[0];
+  double fin_lift = 0.0, fin_gd = 0.0, fin_nc = 0.0;
+  if (warp == 0 && RHS != RHS_NONE) {
+    if (STIFF == STIFF_BASE) fin_lift = P.lift_in[rr];
+    fin_gd = P.gD[rr];
+    if (P.nodal_const) fin_nc = P.nodal_const[rr];
+  }
+  for (int k = warp; k < 2 * w; k += nw) accA[k * 32 + lane] = 0.0;
+  if (warp == 0) { s_diag[lane] = 0; s_dsum[lane] = 0.0; s_bsum[lane] = 0.0; s_lsum[lane] = 0.0; }
+  // ---- load stage 2 (needs the column index) ----
+  double x_slot = 0.0;
+  if (STIFF == STIFF_BASE && RESID && warp < w) x_slot = P.xvec[c_slot];
+  __syncthreads();
+
+  for (int k0 = 0; k0 < iw; k0 += nw) {
+    const int k = k0 + warp;
+    if (k0 > 0) { rec = make_int4(-1, 0, 0, 0); if (k < iw && live) rec = P.inc[ibase + k * 32 + lane]; }
+    double c_self = 0.0, bv = 0.0, lv = 0.0;
+    if (rec.x >= 0) {
+      const int e = rec.x >> 2, a = rec.x & 3;
+      const int nb = rec.z, nc = rec.w;                      // next / previous corner (cyclic)
+      const double2 q_b = P.xy[nb], q_c = P.xy[nc];
+      // canonical corner order (1,2,3) of the triangle: corner a is this row
+      const double2 q1 = (a == 0) ? q_own : (a == 1) ? q_c : q_b;
+      const double2 q2 = (a == 0) ? q_b : (a == 1) ? q_own : q_c;
+      const double2 q3 = (a == 0) ? q_c : (a == 1) ? q_b : q_own;
+      // edge vectors and signed area, src:243-246
+      const double ux = q2.x - q3.x, uy = q2.y - q3.y;
+      const double vx = q3.x - q1.x, vy = q3.y - q1.y;
+      const double wx = q1.x - q2.x, wy = q1.y - q2.y;
+      const double ar = (ux * vy - uy * vx) * 0.5;
+      const int s_self = rec.y & 255, s_next = (rec.y >> 8) & 255, s_prev = (rec.y >> 16) & 255;
+      double c_next = 0.0, c_prev = 0.0;
+      if (STIFF != STIFF_BASE) {
+        double phx, phy;
+        if (STIFF == STIFF_COEF) { phx = P.phx[e]; phy = P.phy[e]; }
+        else {
+          // exp((V1+V2+V3)/3) as the product of the nodal factors in canonical corner order, src:469
+          const double eb = P.E3[nb], ec = P.E3[nc];
+          const double e1 = (a == 0) ? own_e3 : (a == 1) ? ec : eb;
+          const double e2 = (a == 0) ? eb : (a == 1) ? own_e3 : ec;
+          const double e3 = (a == 0) ? ec : (a == 1) ? eb : own_e3;
+          phx = P.phx[e] * (e1 * e2 * e3); phy = phx;
+        }
+        const double inv4 = 1.0 / fabs(ar * 4.0);  // src:257 (one division per triangle; <= 1 ulp vs x/ar4)
+        // canonical lower-triangle entries K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar|, i>=j
+        // (src:260-266); select the row of corner a: self, next, prev.
+        const double sx = (a == 0) ? ux : (a == 1) ? vx : wx, sy = (a == 0) ? uy : (a == 1) ? vy : wy;
+        const double nhx = (a == 0) ? vx : wx, nhy = (a == 0) ? vy : wy;   // (a,next): (2,1),(3,2),(3,1)
+        const double nlx = (a == 1) ? vx : ux, nly = (a == 1) ? vy : uy;
+        const double khx = (a == 1) ? vx : wx, khy = (a == 1) ? vy : wy;   // (a,prev): (3,1),(2,1),(3,2)
+        const double klx = (a == 2) ? vx : ux, kly = (a == 2) ? vy : uy;
+        const double k_self = (sx * phx * sx + sy * phy * sy) * inv4;
+        const double k_next = (nhx * phx * nlx + nhy * phy * nly) * inv4;
+        const double k_prev = (khx * phx * klx + khy * phy * kly) * inv4;
+        const bool nbD = P.isD[nb] != 0, ncD = P.isD[nc] != 0;
+        // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
+        c_self = rowD ? 0.0 : k_self;
+        c_next = (rowD || nbD) ? 0.0 : k_next;
+        c_prev = (rowD || ncD) ? 0.0 : k_prev;
+        // boundary lifting b -= K[:,D]*gD on rows outside D, src:362
+        if (!rowD) {
+          if (nbD) lv += k_next * P.gD[nb];
+          if (ncD) lv += k_prev * P.gD[nc];
+        }
+      }
+      if (MASS) {
+        // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never
+        // eliminated (Q3).  In the row's own frame: self = 3Wa+Wb+Wc, (a,b) = Wa+Wb+Wc/2.
+        const double ar30 = ar * (1.0 / 30.0);
+        const double Wa = own_g * ar30, Wb = P.gw[nb] * ar30, Wc = P.gw[nc] * ar30;
+        // canonical addition order of src:380-386 (W1,W2,W3 left to right)
+        const double W1 = (a == 0) ? Wa : (a == 1) ? Wc : Wb;
+        const double W2 = (a == 0) ? Wb : (a == 1) ? Wa : Wc;
+        const double W3 = (a == 0) ? Wc : (a == 1) ? Wb : Wa;
+        double m_self, m_next, m_prev;
+        if (a == 0) { m_self = 3.0 * W1 + W2 + W3; m_next = W1 + W2 + W3 * 0.5; m_prev = W1 + W2 * 0.5 + W3; }
+        else if (a == 1) { m_self = W1 + 3.0 * W2 + W3; m_next = W1 * 0.5 + W2 + W3; m_prev = W1 + W2 + W3 * 0.5; }
+        else { m_self = W1 + W2 + 3.0 * W3; m_next = W1 + W2 * 0.5 + W3; m_prev = W1 * 0.5 + W2 + W3; }
+        c_self -= m_self; c_next -= m_next; c_prev -= m_prev;
+      }
+      // lumped edge-midpoint load: corner a takes the midpoint between a and next (src:345-350, Q1)
+      if (RHS != RHS_NONE && RHS != RHS_ZERO) {
+        double f;
+        if (RHS == RHS_DDP) {   // src:341-343
+          const double ua = (own_u + P.fu[nb]) * 0.5, va = (own_v + P.fv[nb]) * 0.5;
+          const double eS = own_eh * P.EH[nb], eSi = own_ehi * P.EHi[nb];
+          f = P.par0 * (eSi * va - eS * ua) + P.mid[3 * e + a];
+        } else if (RHS == RHS_SRH) {  // src:517-519
+          const double ua = (own_u + P.fu[nb]) * 0.5, va = (own_v + P.fv[nb]) * 0.5;
+          const double eS = own_eh * P.EH[nb], eSi = own_ehi * P.EHi[nb];
+          f = 1.0 / (P.par0 * (eS * ua + 1.0) + P.par1 * (eSi * va + 1.0));
+        } else if (RHS == RHS_SINH) {  // registered functor, test:95
+          const double S = (own_eh + P.EH[nb]) * 0.5;
+          f = P.mid[3 * e + a] + P.par0 * sinh(P.par1 * S);
+        } else {  // RHS_POLY, README:107-108
+          const double S = (own_eh + P.EH[nb]) * 0.5;
+          const int deg = (int)P.par0;
+          f = P.mid_poly[deg][3 * e + a];
+          for (int d = deg - 1; d >= 0; --d) f = f * S + P.mid_poly[d][3 * e + a];
+        }
+        bv = f * (fabs(ar) * (1.0 / 3.0));  // src:349
+      }
+      if (STIFF != STIFF_BASE || MASS) {
+        // first / second contributor planes (ordinal bits resolved at setup)
+        double* pn = (rec.y & (1 << 24)) ? accB : accA;
+        double* pp = (rec.y & (1 << 25)) ? accB : accA;
+        pn[s_next * 32 + lane] = c_next;
+        pp[s_prev * 32 + lane] = c_prev;
+      }
+      s_diag[lane] = s_self;
+    }
+    stS[warp * 32 + lane] = c_self;
+    stB[warp * 32 + lane] = bv;
+    stL[warp * 32 + lane] = lv;
+    __syncthreads();
+    if (warp == 0) {   // ordered sums of this pass (incidence order)
+      double ds = s_dsum[lane], bs = s_bsum[lane], ls = s_lsum[lane];
+      const int cnt = min(nw, iw - k0);
+      for (int kk = 0; kk < cnt; ++kk) { ds += stS[kk * 32 + lane]; bs += stB[kk * 32 + lane]; ls += stL[kk * 32 + lane]; }
+      s_dsum[lane] = ds; s_bsum[lane] = bs; s_lsum[lane] = ls;
+    }
+    __syncthreads();
+  }
+
+  // ---- write the slice: warp k streams slot k of all 32 rows ----
+  for (int k = warp; k < w; k += nw) {
+    const int idx = base + k * 32 + lane;
+    const bool isdiag = live && (k == s_diag[lane]);
+    double a_k = isdiag ? s_dsum[lane] : accA[k * 32 + lane] + accB[k * 32 + lane];
+    if (STIFF == STIFF_BASE) {
+      double m_k = m_slot, x_k = x_slot;
+      if (k != warp) {   // slots beyond the first nw (rows longer than the CTA's warp count)
+        m_k = ld_stream(P.base_val + idx);
+        if (RESID) x_k = P.xvec[ld_stream(P.col + idx)];
+      }
+      if (RESID) prod[k * 32 + lane] = live ? m_k * x_k : 0.0;
+      a_k += m_k;
+    } else if (isdiag && rowD) {
+      a_k += 1.0;   // src:279-281
+    }
+    if (!live) a_k = 0.0;
+    P.out_val[idx] = a_k;
+    if (isdiag) s_dval[lane] = a_k;
+  }
+  __syncthreads();
+  if (warp == 0 && live) {
+    if (P.dinv) P.dinv[row] = 1.0 / s_dval[lane];
+    double lift = s_lsum[lane];
+    if (STIFF != STIFF_BASE && P.lift_out) P.lift_out[row] = lift;
+    if (RHS != RHS_NONE) {
+      if (STIFF == STIFF_BASE) lift = fin_lift;
+      double bi = s_bsum[lane] + fin_nc;             // Neumann loads, src:994-996
+      bi -= lift;                                    // src:362
+      if (rowD) bi = fin_gd;                         // src:363
+      P.b[row] = bi;
+      if (RESID) {
+        double mv = 0.0;
+        for (int k = 0; k < w; ++k) mv += prod[k * 32 + lane];
+        P.resid[row] = mv - bi;                      // src:368
+      }
     }
   }
 }
@@ -236,11 +306,10 @@ __global__ void __launch_bounds__(kAsmBlock) k_assemble(const AsmArgs P) {
 template <int STIFF, bool MASS, int RHS, bool RESID>
 static int launch_asm(Context* ctx, const AsmArgs& a) {
   const Pattern& P = ctx->pat;
-  int blocks = (P.nslices * 32 + kAsmBlock - 1) / kAsmBlock;
-  if (blocks == 0) return 0;
-  if (RESID && blocks > ctx->partial_cap) { ctx->fail(DDPS_ERR_STATE, "partials buffer too small"); return DDPS_ERR_STATE; }
-  size_t smem = (size_t)P.max_row_len * kAsmBlock * sizeof(double);
-  k_assemble<STIFF, MASS, RHS, RESID><<<blocks, kAsmBlock, smem, ctx->stream>>>(a);
+  if (P.nslices == 0) return 0;
+  const int nw = std::max(1, std::min(8, P.max_inc));
+  size_t smem = (size_t)((RESID ? 3 : 2) * P.max_row_len + 3 * nw) * 32 * sizeof(double);
+  k_assemble<STIFF, MASS, RHS, RESID><<<P.nslices, 32 * nw, smem, ctx->stream>>>(a);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
   return 0;
@@ -507,7 +576,7 @@ int launch_max_abs(Context* ctx, const double* a, int n, double* host_out) {
   return fetch_norm_inf(ctx, host_out);
 }
 
-int fetch_resid_norm(Context* ctx, double* host_out) { return fetch_norm_inf(ctx, host_out); }
+int fetch_resid_norm(Context* ctx, double* host_out) { return launch_max_abs(ctx, ctx->resid, ctx->n_own, host_out); }
 
 // ------------------------------------------------------------------------------------------------
 // Jacobi-preconditioned CG (K9), all control flow on the device
@@ -674,7 +743,7 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
     ctx->fail(DDPS_ERR_BREAKDOWN, "PCG breakdown: p.Ap <= 0 (operator not SPD; u or v negative? SURVEY H3)");
     return DDPS_ERR_BREAKDOWN;
   }
-  if (!(S.rr <= S.thresh2 || S.rmax <= S.thresh_inf)) {
+  if (!(S.rr <= S.thresh2 || S.rmax <= S.thresh_inf) && !ctx->opts.lin_cap_ok) {
     ctx->fail(DDPS_ERR_NOCONV, "PCG hit the iteration cap (" + std::to_string(S.iters) + " its, relres " +
                                    std::to_string(S.bb > 0 ? sqrt(S.rr / S.bb) : 0.0) + ")");
     return DDPS_ERR_NOCONV;

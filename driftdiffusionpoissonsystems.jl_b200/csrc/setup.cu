@@ -103,7 +103,7 @@ __device__ __forceinline__ int find_slot(const int* __restrict__ cols, int len, 
 __global__ void k_fill_incidence(const int* __restrict__ inc_ptr, const int* __restrict__ inc_vals,
                                  const int4* __restrict__ elem, const int* __restrict__ rowptr,
                                  const int* __restrict__ csrcol, int nrows, int nslices,
-                                 const int* __restrict__ inc_slice_ptr, int2* __restrict__ inc) {
+                                 const int* __restrict__ inc_slice_ptr, int4* __restrict__ inc, int* __restrict__ bad) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   int slice = row >> 5, lane = row & 31;
   if (slice >= nslices) return;
@@ -115,7 +115,7 @@ __global__ void k_fill_incidence(const int* __restrict__ inc_ptr, const int* __r
     rbeg = rowptr[row]; rlen = rowptr[row + 1] - rbeg;
   }
   for (int k = 0; k < w; ++k) {
-    int2 rec = make_int2(-1, 0);
+    int4 rec = make_int4(-1, 0, 0, 0);
     if (k < len) {
       int packed = inc_vals[beg + k];
       int e = packed >> 2, a = packed & 3;
@@ -125,7 +125,17 @@ __global__ void k_fill_incidence(const int* __restrict__ inc_ptr, const int* __r
       int ss = find_slot(csrcol + rbeg, rlen, row);
       int sb = find_slot(csrcol + rbeg, rlen, nb);
       int sc = find_slot(csrcol + rbeg, rlen, nc);
-      rec = make_int2(packed, ss | (sb << 8) | (sc << 16));
+      // ordinal (0 = first, 1 = second contributor in increasing triangle order) of this triangle's
+      // contribution to the off-diagonal entries (row,nb) and (row,nc): count earlier incident
+      // triangles that contain the same neighbour.  An edge of a valid triangulation has <= 2 triangles.
+      int ob = 0, oc = 0;
+      for (int j = 0; j < k; ++j) {
+        int4 e2 = elem[inc_vals[beg + j] >> 2];
+        if (e2.x == nb || e2.y == nb || e2.z == nb) ++ob;
+        if (e2.x == nc || e2.y == nc || e2.z == nc) ++oc;
+      }
+      if (ob > 1 || oc > 1) atomicAdd(bad, 1);
+      rec = make_int4(packed, ss | (sb << 8) | (sc << 16) | ((ob & 1) << 24) | ((oc & 1) << 25), nb, nc);
     }
     inc[base + k * 32 + lane] = rec;
   }
@@ -251,6 +261,7 @@ int build_pattern(Context* ctx) {
   int maxdeg = 0;
   rc = make_slices(inc_ptr, &P.inc_slice_ptr, &P.inc_entries, &maxdeg);
   if (rc) return rc;
+  P.max_inc = maxdeg;
   {
     int* d_min = d_max;
     int big = 1 << 30;
@@ -264,10 +275,17 @@ int build_pattern(Context* ctx) {
       return DDPS_ERR_ARG;
     }
   }
-  DDPS_CUDA(cudaMalloc(&P.inc, std::max<size_t>(P.inc_entries, 1) * sizeof(int2)));
+  DDPS_CUDA(cudaMalloc(&P.inc, std::max<size_t>(P.inc_entries, 1) * sizeof(int4)));
+  DDPS_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
   k_fill_incidence<<<(nsl * 32 + T - 1) / T, T, 0, st>>>(inc_ptr, iv_out, ctx->elem, P.rowptr, P.csrcol, n_own, nsl,
-                                                        P.inc_slice_ptr, P.inc);
+                                                        P.inc_slice_ptr, P.inc, d_max);
+  int nbad = 0;
+  DDPS_CUDA(cudaMemcpyAsync(&nbad, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
   DDPS_CUDA(cudaStreamSynchronize(st));
+  if (nbad) {
+    ctx->fail(DDPS_ERR_ARG, "mesh is not a valid triangulation: an edge is shared by more than two triangles");
+    return DDPS_ERR_ARG;
+  }
   DDPS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -88,7 +88,8 @@ typedef struct ddps_solver_opts {
   int32_t check_every;  /* PCG iterations between host polls of the device-side done flag (default 32) */
   int32_t warm_start;   /* 1: continuity solves start PCG from the previous iterate (same solution) (default 1) */
   int32_t verbose;      /* 1: print "iteration k, tolerance: c" lines like src:655,1093 */
-  int32_t reserved[7];
+  int32_t lin_cap_ok;   /* 1: PCG / Newton solves that hit their caps are accepted instead of failing (profiling runs only) */
+  int32_t reserved[6];
 } ddps_solver_opts;
 
 typedef struct ddps_stats {
@@ -132,6 +133,15 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
 /* Host-only partition query (runs without a GPU context's kernels; used by the CPU tests):
  * owner[nq] <- rank owning each node under recursive coordinate bisection into nparts parts. */
 int ddps_partition_nodes(const double* nodes, int64_t nq, int nparts, int32_t* owner);
+
+/* Host-only: the local mesh + halo plan rank `rank` of `nparts` derives from the global mesh (the same
+ * code ddps_mesh_set runs).  counts = {n_own, n_ghost, nme_local, n_neighbours}; loc2glob[n_own+n_ghost]
+ * (0-based global ids: owned first, then ghosts grouped by owner); peers/send_counts/recv_counts
+ * [n_neighbours]; send_glob = global ids this rank sends, grouped by peer in peers[] order.  Any
+ * output pointer may be NULL.  Capacity nq (loc2glob, send_glob) / nparts (the others) suffices. */
+int ddps_partition_plan(const double* nodes, int64_t nq, const int64_t* elements, int64_t nme, int nparts, int rank,
+                        int64_t counts[4], int64_t* loc2glob, int32_t* peers, int64_t* send_counts, int64_t* recv_counts,
+                        int64_t* send_glob);
 
 /* ---- boundary + coefficient uploads (host shim output of aquire_boundary, src:162-218) ---- */
 int ddps_dirichlet_set(ddps_ctx* ctx, int field, const int64_t* idx1, const double* val, int64_t nd);

@@ -1,7 +1,7 @@
 """Scale probe (not part of the product): timings at a given structured mesh size."""
 import sys, time, json
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import ddps_b200 as D
 
 nx, ny = int(sys.argv[1]), int(sys.argv[2])
