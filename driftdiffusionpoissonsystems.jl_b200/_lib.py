@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddps_b200.so")
+LIB_PATH = os.environ.get("DDPS_B200_LIB", os.path.join(_HERE, "libddps_b200.so"))
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)

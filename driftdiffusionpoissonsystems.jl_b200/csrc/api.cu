@@ -33,6 +33,7 @@ template <typename T>
 void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
 void free_mesh(Context* ctx) {
+  p2p_teardown(ctx);
   free_pattern(ctx);
   dev_free(ctx->xy); dev_free(ctx->elem); dev_free(ctx->d_own_glob);
   dev_free(ctx->isD);
@@ -569,6 +570,7 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
   ctx->partial_cap = std::max(asm_blocks, 4 * ctx->num_sms * 16) + 64;
   if ((rc = dev_alloc(ctx, &ctx->partials, (size_t)ctx->partial_cap))) return rc;
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if ((rc = p2p_setup(ctx))) return rc;
   ctx->have_mesh = true;
   ctx->stats.t_setup_ms = now_ms() - t0;
   return DDPS_OK;

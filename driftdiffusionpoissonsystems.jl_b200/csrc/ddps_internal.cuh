@@ -80,6 +80,41 @@ struct PcgScalars {
   double norm_inf;  // generic max-norm result
   double rmax;      // ||r||_inf of the PCG residual
   double thresh_inf;
+  double norm_aux2;
+};
+
+// ---- peer-memory (NVLink P2P via CUDA IPC) windows for the fused halo push + scalar allreduce ----
+constexpr int kMaxRanks = 8;
+struct P2PWin {                                  // one per rank, written by the peers
+  unsigned long long halo_flag[kMaxRanks];       // [src] tag of the last halo src pushed into my ghost block
+  unsigned long long redA_flag[kMaxRanks];       // [src] tag of src's p.Ap partial
+  unsigned long long redB_flag[kMaxRanks];       // [src] tag of src's {r.z, r.r, max|r|} partials
+  double redA[kMaxRanks][4];
+  double redB[kMaxRanks][4];
+  int error;
+  int pad;
+};
+struct P2PDev {                                  // by-value kernel argument
+  int nranks, rank, nneigh;
+  int neigh[kMaxRanks];
+  P2PWin* win[kMaxRanks];                        // win[rank] is local, the others are IPC mappings
+  unsigned long long tag_halo, tagA, tagB;
+};
+struct PushArgs {
+  int nneigh;
+  int off[kMaxRanks + 1];
+  double* dst[kMaxRanks];
+  unsigned long long* flag[kMaxRanks];
+  unsigned long long tag;
+};
+struct P2PHost {
+  bool enabled = false;
+  P2PWin* win_local = nullptr;
+  P2PWin* win_peer[kMaxRanks] = {nullptr};
+  double* p_peer[kMaxRanks] = {nullptr};
+  PushArgs push;
+  P2PDev dev;
+  unsigned long long tag = 0;
 };
 
 struct HaloPlan {
@@ -108,6 +143,7 @@ struct Context {
   ncclComm_t comm = nullptr;
 #endif
   HaloPlan halo;
+  P2PHost p2p;
 
   // mesh (local part)
   bool have_mesh = false;
@@ -174,7 +210,7 @@ void partition_nodes_rcb(const double* nodes, int64_t nq, int nparts, int32_t* o
 
 // ---- kernels.cu ----
 struct AsmArgs {
-  int nrows, nslices;
+  int nrows, nslices, wmax;
   const int* slice_ptr;
   const int* col;
   const int* inc_slice_ptr;
@@ -242,6 +278,9 @@ int allreduce_max(Context* ctx, double* dev, int count);
 int comm_init(Context* ctx, const char* id128, int rank, int nranks);
 int comm_unique_id(char* id128);
 void comm_destroy(Context* ctx);
+int p2p_setup(Context* ctx);      // after the vectors are allocated (needs ctx->p)
+int p2p_teardown(Context* ctx);   // before they are freed
+int comm_barrier(Context* ctx);
 
 }  // namespace ddps
 

@@ -13,6 +13,8 @@
 //   k_pcg_update / k_pcg_direction    fused vector updates + dots of Jacobi-PCG (K9)
 //   nodal prep kernels                exp(+-V/2), exp(+-V/3) and the nodal mass weights g_k, so
 //                                     the element loops contain no transcendental at all.
+#include <cuda_pipeline.h>
+
 #include "ddps_internal.cuh"
 
 namespace ddps {
@@ -79,237 +81,382 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, u
   return true;
 }
 
+// Same with a per-component operation: bit i of MAXMASK set -> component i is a max, else a sum.
+template <int NV, unsigned MAXMASK>
+__device__ __forceinline__ bool grid_reduce_mixed(double (&v)[NV], double* partials, unsigned* ticket, double* sh,
+                                                  double (&total)[NV]) {
+  __shared__ bool s_last;
+  double bv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) bv[i] = ((MAXMASK >> i) & 1) ? block_reduce<true>(v[i], sh) : block_reduce<false>(v[i], sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) partials[(size_t)i * gridDim.x + blockIdx.x] = bv[i];
+    __threadfence();
+    unsigned t = atomicInc(ticket, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const bool mx = (MAXMASK >> i) & 1;
+    double s = 0.0;
+    const volatile double* pp = partials + (size_t)i * gridDim.x;
+    for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) s = mx ? fmax(s, pp[j]) : s + pp[j];
+    total[i] = mx ? block_reduce<true>(s, sh) : block_reduce<false>(s, sh);
+  }
+  return true;
+}
+
+// ---- peer-memory collectives (multi-GPU): flags + payload live in every rank's P2PWin -----------------
+// Writer: payload stores, __threadfence_system, flag store.  Reader: spin on the local flag (peers write
+// it over NVLink), fence, read payload.  Tags increase monotonically, one per use, so a slot is never
+// ambiguous; the data dependencies of CG (every rank needs every other rank's previous partial before it
+// can produce the next one) make single buffering safe.  A spin gives up after ~10 s and raises an error
+// flag instead of hanging the GPU.
+__device__ __forceinline__ bool spin_until(const volatile unsigned long long* flag, unsigned long long tag) {
+  const long long t0 = clock64();
+  while (*flag < tag) {
+    if (clock64() - t0 > 20000000000LL) return false;
+  }
+  return true;
+}
+
+// thread 0 of the calling (last) block publishes NV doubles to every rank's window
+template <int NV>
+__device__ __forceinline__ void p2p_publish(const P2PDev& pd, int phase, unsigned long long tag, const double (&v)[NV]) {
+  for (int r = 0; r < pd.nranks; ++r) {
+    P2PWin* W = pd.win[r];
+    volatile double* dst = phase == 0 ? W->redA[pd.rank] : W->redB[pd.rank];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dst[i] = v[i];
+  }
+  __threadfence_system();
+  for (int r = 0; r < pd.nranks; ++r) {
+    P2PWin* W = pd.win[r];
+    volatile unsigned long long* f = phase == 0 ? &W->redA_flag[pd.rank] : &W->redB_flag[pd.rank];
+    *f = tag;
+  }
+}
+
+// every block: thread 0 waits for all ranks' partials and combines them in RANK ORDER (deterministic and
+// identical on every rank); result broadcast through shared memory.  Returns false on timeout.
+template <int NV, unsigned MAXMASK>
+__device__ __forceinline__ bool p2p_gather(const P2PDev& pd, int phase, unsigned long long tag, double (&out)[NV],
+                                           double* sh) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    P2PWin* W = pd.win[pd.rank];
+    bool ok = true;
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (int r = 0; r < pd.nranks; ++r) {
+      ok = ok && spin_until(phase == 0 ? &W->redA_flag[r] : &W->redB_flag[r], tag);
+      __threadfence();
+      const volatile double* src = phase == 0 ? W->redA[r] : W->redB[r];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = ((MAXMASK >> i) & 1) ? fmax(acc[i], src[i]) : acc[i] + src[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[i] = acc[i];
+    s_ok = ok ? 1 : 0;
+    if (!ok) W->error = 1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) out[i] = sh[i];
+  const bool ok = s_ok != 0;
+  __syncthreads();
+  return ok;
+}
+
+// push the owned boundary values of the search direction straight into the neighbours' ghost blocks
+__global__ void __launch_bounds__(1024) k_halo_push(const PushArgs A, const int* __restrict__ send_idx,
+                                                     const double* __restrict__ p, const PcgScalars* scal) {
+  if (scal->done) return;
+  const int j = blockIdx.x;
+  const int n = A.off[j + 1] - A.off[j];
+  double* dst = A.dst[j];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = p[send_idx[A.off[j] + i]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *(volatile unsigned long long*)A.flag[j] = A.tag;
+}
+
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 
 // ------------------------------------------------------------------------------------------------
 // Row-major fused assembly.
 //
-// Thread mapping: one CTA per 32-row slice; warp k of the CTA handles incidence k (the k-th incident
-// triangle, in increasing triangle order) of ALL 32 rows, lane = row.  Every stream that is stored
-// slice-interleaved (incidence records, matrix values, columns) is therefore read/written as one
-// fully coalesced 256-byte warp access, neighbouring lanes gather neighbouring triangles/nodes, and
-// a row's ~6 dependent load chains run in 6 different warps instead of back to back in one thread.
-//
-// Deterministic, atomic-free scatter: an off-diagonal entry (i,j) receives at most two contributions
-// (the two triangles sharing edge ij; checked at setup).  The setup marks every contribution as the
-// first or the second one in increasing triangle order, the kernel stores them into two separate
-// shared-memory planes (accA/accB) and adds A+B after ONE barrier.  The diagonal, the load and the
-// lifting receive one contribution per incident triangle; those are staged per incidence index and
-// summed in incidence order.  The result is bitwise reproducible and uses the same summation order
-// as the reference's sparse() (increasing triangle id per entry).
+// One thread per matrix row, one warp per 32-row slice, persistent warps striding over the slices.
+// The kernel is latency-bound, not byte-bound (ncu: every data-dependent load level costs one DRAM
+// latency and nothing else is saturated), so it is organised around the number of DEPENDENT load
+// levels per slice and the number of slices in flight per SM:
+//   level 0  the slice's incidence records -- prefetched one slice ahead with cp.async into a
+//            per-warp shared-memory ring, so this level is off the critical path;
+//   level 1  for a batch of BATCH incidences at a time: every gather the batch needs (neighbour
+//            coordinates, nodal factors, per-triangle coefficients) is issued before any is used;
+//   level 2  (Newton systems only) columns+values of the base matrix, then the x gather.
+// Contributions are accumulated in incidence order into the thread's PRIVATE shared-memory column
+// (slots resolved at setup): no atomics, no staging buffer, bitwise reproducible, same summation
+// order as the reference's sparse() (increasing triangle id per entry).  All slice-
+// interleaved streams (records, values, columns) are fully coalesced 256/512-byte warp accesses.
 // ------------------------------------------------------------------------------------------------
+constexpr int kAsmWarps = kAsmBlock / 32;
+#ifndef DDPS_ASM_BATCH
+#define DDPS_ASM_BATCH 2
+#endif
+#ifndef DDPS_ASM_MINBLOCKS
+#define DDPS_ASM_MINBLOCKS 1
+#endif
+constexpr int kAsmBatch = DDPS_ASM_BATCH;
+
+struct IncData {           // everything one incidence needs from memory (level-1 gathers)
+  double2 qb, qc;
+  double phx, phy, eb, ec, gb, gc, ub, vb, ehb, ehib, mid;
+  bool bD, cD;
+};
+
 template <int STIFF, bool MASS, int RHS, bool RESID>
-__global__ void __launch_bounds__(256) k_assemble(const AsmArgs P) {
+__global__ void __launch_bounds__(kAsmBlock, DDPS_ASM_MINBLOCKS) k_assemble(const AsmArgs P, const int ring_w) {
   extern __shared__ double sm[];
-  __shared__ int s_diag[32];
-  __shared__ double s_dsum[32], s_bsum[32], s_lsum[32], s_dval[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int slice = blockIdx.x;
-  const int row = slice * 32 + lane;
-  const bool live = row < P.nrows;
-  const int base = P.slice_ptr[slice];
-  const int w = (P.slice_ptr[slice + 1] - base) >> 5;
-  const int ibase = P.inc_slice_ptr[slice];
-  const int iw = (P.inc_slice_ptr[slice + 1] - ibase) >> 5;
-  double* accA = sm;                    // [w][32] first contribution of every off-diagonal slot
-  double* accB = accA + w * 32;         // [w][32] second contribution
-  double* stS = accB + w * 32;          // [nw][32] diagonal contribution of incidence k
-  double* stB = stS + nw * 32;          // [nw][32] load contribution
-  double* stL = stB + nw * 32;          // [nw][32] lifting contribution
-  double* prod = stL + nw * 32;         // [w][32] base*x products (RESID)
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  // shared memory: acc[wmax][kAsmBlock] doubles, then per-warp record ring [2][ring_w][32] int4
+  double* acc = sm;
+  int4* ring = reinterpret_cast<int4*>(sm + (size_t)P.wmax * kAsmBlock) + (size_t)wib * 2 * ring_w * 32;
+  const int gwarp = blockIdx.x * kAsmWarps + wib, nwarps = gridDim.x * kAsmWarps;
 
-  // ---- load stage 1: everything that does not depend on another load is issued up front -----------
-  // (the kernel is latency-bound: a CTA's life is [#dependent load stages] x [DRAM latency], so the
-  //  chain is kept at two stages: {records, own-node data, matrix slot} -> {neighbour data, x gather})
-  const int k_first = warp;                                  // incidence handled in pass 0
-  int4 rec = make_int4(-1, 0, 0, 0);
-  if (k_first < iw && live) rec = P.inc[ibase + k_first * 32 + lane];
-  const int rr = live ? row : 0;
-  const double2 q_own = P.xy[rr];
-  const bool rowD = live && P.isD[rr] != 0;
-  double own_g = 0.0, own_e3 = 0.0, own_u = 0.0, own_v = 0.0, own_eh = 0.0, own_ehi = 0.0;
-  if (MASS) own_g = P.gw[rr];
-  if (STIFF == STIFF_EXPV) own_e3 = P.E3[rr];
-  if (RHS == RHS_DDP || RHS == RHS_SRH) { own_u = P.fu[rr]; own_v = P.fv[rr]; own_eh = P.EH[rr]; own_ehi = P.EHi[rr]; }
-  if (RHS == RHS_SINH || RHS == RHS_POLY) own_eh = P.EH[rr];
-  double m_slot = 0.0;   // base matrix entry of the slot this warp writes first (slot = warp)
-  int c_slot = 0;
-  if (STIFF == STIFF_BASE && warp < w) {
-    m_slot = ld_stream(P.base_val + base + warp * 32 + lane);
-    if (RESID) c_slot = ld_stream(P.col + base + warp * 32 + lane);
-  }
-  double fin_lift = 0.0, fin_gd = 0.0, fin_nc = 0.0;
-  if (warp == 0 && RHS != RHS_NONE) {
-    if (STIFF == STIFF_BASE) fin_lift = P.lift_in[rr];
-    fin_gd = P.gD[rr];
-    if (P.nodal_const) fin_nc = P.nodal_const[rr];
-  }
-  for (int k = warp; k < 2 * w; k += nw) accA[k * 32 + lane] = 0.0;
-  if (warp == 0) { s_diag[lane] = 0; s_dsum[lane] = 0.0; s_bsum[lane] = 0.0; s_lsum[lane] = 0.0; }
-  // ---- load stage 2 (needs the column index) ----
-  double x_slot = 0.0;
-  if (STIFF == STIFF_BASE && RESID && warp < w) x_slot = P.xvec[c_slot];
-  __syncthreads();
-
-  for (int k0 = 0; k0 < iw; k0 += nw) {
-    const int k = k0 + warp;
-    if (k0 > 0) { rec = make_int4(-1, 0, 0, 0); if (k < iw && live) rec = P.inc[ibase + k * 32 + lane]; }
-    double c_self = 0.0, bv = 0.0, lv = 0.0;
-    if (rec.x >= 0) {
-      const int e = rec.x >> 2, a = rec.x & 3;
-      const int nb = rec.z, nc = rec.w;                      // next / previous corner (cyclic)
-      const double2 q_b = P.xy[nb], q_c = P.xy[nc];
-      // canonical corner order (1,2,3) of the triangle: corner a is this row
-      const double2 q1 = (a == 0) ? q_own : (a == 1) ? q_c : q_b;
-      const double2 q2 = (a == 0) ? q_b : (a == 1) ? q_own : q_c;
-      const double2 q3 = (a == 0) ? q_c : (a == 1) ? q_b : q_own;
-      // edge vectors and signed area, src:243-246
-      const double ux = q2.x - q3.x, uy = q2.y - q3.y;
-      const double vx = q3.x - q1.x, vy = q3.y - q1.y;
-      const double wx = q1.x - q2.x, wy = q1.y - q2.y;
-      const double ar = (ux * vy - uy * vx) * 0.5;
-      const int s_self = rec.y & 255, s_next = (rec.y >> 8) & 255, s_prev = (rec.y >> 16) & 255;
-      double c_next = 0.0, c_prev = 0.0;
-      if (STIFF != STIFF_BASE) {
-        double phx, phy;
-        if (STIFF == STIFF_COEF) { phx = P.phx[e]; phy = P.phy[e]; }
-        else {
-          // exp((V1+V2+V3)/3) as the product of the nodal factors in canonical corner order, src:469
-          const double eb = P.E3[nb], ec = P.E3[nc];
-          const double e1 = (a == 0) ? own_e3 : (a == 1) ? ec : eb;
-          const double e2 = (a == 0) ? eb : (a == 1) ? own_e3 : ec;
-          const double e3 = (a == 0) ? ec : (a == 1) ? eb : own_e3;
-          phx = P.phx[e] * (e1 * e2 * e3); phy = phx;
-        }
-        const double inv4 = 1.0 / fabs(ar * 4.0);  // src:257 (one division per triangle; <= 1 ulp vs x/ar4)
-        // canonical lower-triangle entries K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar|, i>=j
-        // (src:260-266); select the row of corner a: self, next, prev.
-        const double sx = (a == 0) ? ux : (a == 1) ? vx : wx, sy = (a == 0) ? uy : (a == 1) ? vy : wy;
-        const double nhx = (a == 0) ? vx : wx, nhy = (a == 0) ? vy : wy;   // (a,next): (2,1),(3,2),(3,1)
-        const double nlx = (a == 1) ? vx : ux, nly = (a == 1) ? vy : uy;
-        const double khx = (a == 1) ? vx : wx, khy = (a == 1) ? vy : wy;   // (a,prev): (3,1),(2,1),(3,2)
-        const double klx = (a == 2) ? vx : ux, kly = (a == 2) ? vy : uy;
-        const double k_self = (sx * phx * sx + sy * phy * sy) * inv4;
-        const double k_next = (nhx * phx * nlx + nhy * phy * nly) * inv4;
-        const double k_prev = (khx * phx * klx + khy * phy * kly) * inv4;
-        const bool nbD = P.isD[nb] != 0, ncD = P.isD[nc] != 0;
-        // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
-        c_self = rowD ? 0.0 : k_self;
-        c_next = (rowD || nbD) ? 0.0 : k_next;
-        c_prev = (rowD || ncD) ? 0.0 : k_prev;
-        // boundary lifting b -= K[:,D]*gD on rows outside D, src:362
-        if (!rowD) {
-          if (nbD) lv += k_next * P.gD[nb];
-          if (ncD) lv += k_prev * P.gD[nc];
-        }
-      }
-      if (MASS) {
-        // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never
-        // eliminated (Q3).  In the row's own frame: self = 3Wa+Wb+Wc, (a,b) = Wa+Wb+Wc/2.
-        const double ar30 = ar * (1.0 / 30.0);
-        const double Wa = own_g * ar30, Wb = P.gw[nb] * ar30, Wc = P.gw[nc] * ar30;
-        // canonical addition order of src:380-386 (W1,W2,W3 left to right)
-        const double W1 = (a == 0) ? Wa : (a == 1) ? Wc : Wb;
-        const double W2 = (a == 0) ? Wb : (a == 1) ? Wa : Wc;
-        const double W3 = (a == 0) ? Wc : (a == 1) ? Wb : Wa;
-        double m_self, m_next, m_prev;
-        if (a == 0) { m_self = 3.0 * W1 + W2 + W3; m_next = W1 + W2 + W3 * 0.5; m_prev = W1 + W2 * 0.5 + W3; }
-        else if (a == 1) { m_self = W1 + 3.0 * W2 + W3; m_next = W1 * 0.5 + W2 + W3; m_prev = W1 + W2 + W3 * 0.5; }
-        else { m_self = W1 + W2 + 3.0 * W3; m_next = W1 + W2 * 0.5 + W3; m_prev = W1 * 0.5 + W2 + W3; }
-        c_self -= m_self; c_next -= m_next; c_prev -= m_prev;
-      }
-      // lumped edge-midpoint load: corner a takes the midpoint between a and next (src:345-350, Q1)
-      if (RHS != RHS_NONE && RHS != RHS_ZERO) {
-        double f;
-        if (RHS == RHS_DDP) {   // src:341-343
-          const double ua = (own_u + P.fu[nb]) * 0.5, va = (own_v + P.fv[nb]) * 0.5;
-          const double eS = own_eh * P.EH[nb], eSi = own_ehi * P.EHi[nb];
-          f = P.par0 * (eSi * va - eS * ua) + P.mid[3 * e + a];
-        } else if (RHS == RHS_SRH) {  // src:517-519
-          const double ua = (own_u + P.fu[nb]) * 0.5, va = (own_v + P.fv[nb]) * 0.5;
-          const double eS = own_eh * P.EH[nb], eSi = own_ehi * P.EHi[nb];
-          f = 1.0 / (P.par0 * (eS * ua + 1.0) + P.par1 * (eSi * va + 1.0));
-        } else if (RHS == RHS_SINH) {  // registered functor, test:95
-          const double S = (own_eh + P.EH[nb]) * 0.5;
-          f = P.mid[3 * e + a] + P.par0 * sinh(P.par1 * S);
-        } else {  // RHS_POLY, README:107-108
-          const double S = (own_eh + P.EH[nb]) * 0.5;
-          const int deg = (int)P.par0;
-          f = P.mid_poly[deg][3 * e + a];
-          for (int d = deg - 1; d >= 0; --d) f = f * S + P.mid_poly[d][3 * e + a];
-        }
-        bv = f * (fabs(ar) * (1.0 / 3.0));  // src:349
-      }
-      if (STIFF != STIFF_BASE || MASS) {
-        // first / second contributor planes (ordinal bits resolved at setup)
-        double* pn = (rec.y & (1 << 24)) ? accB : accA;
-        double* pp = (rec.y & (1 << 25)) ? accB : accA;
-        pn[s_next * 32 + lane] = c_next;
-        pp[s_prev * 32 + lane] = c_prev;
-      }
-      s_diag[lane] = s_self;
+  auto prefetch = [&](int slice, int buf) {
+    if (slice < P.nslices) {
+      const int ibase = P.inc_slice_ptr[slice];
+      const int iw = min((P.inc_slice_ptr[slice + 1] - ibase) >> 5, ring_w);
+      for (int k = 0; k < iw; ++k)
+        __pipeline_memcpy_async(&ring[(buf * ring_w + k) * 32 + lane], &P.inc[ibase + k * 32 + lane], sizeof(int4));
     }
-    stS[warp * 32 + lane] = c_self;
-    stB[warp * 32 + lane] = bv;
-    stL[warp * 32 + lane] = lv;
-    __syncthreads();
-    if (warp == 0) {   // ordered sums of this pass (incidence order)
-      double ds = s_dsum[lane], bs = s_bsum[lane], ls = s_lsum[lane];
-      const int cnt = min(nw, iw - k0);
-      for (int kk = 0; kk < cnt; ++kk) { ds += stS[kk * 32 + lane]; bs += stB[kk * 32 + lane]; ls += stL[kk * 32 + lane]; }
-      s_dsum[lane] = ds; s_bsum[lane] = bs; s_lsum[lane] = ls;
-    }
-    __syncthreads();
-  }
+    __pipeline_commit();
+  };
 
-  // ---- write the slice: warp k streams slot k of all 32 rows ----
-  for (int k = warp; k < w; k += nw) {
-    const int idx = base + k * 32 + lane;
-    const bool isdiag = live && (k == s_diag[lane]);
-    double a_k = isdiag ? s_dsum[lane] : accA[k * 32 + lane] + accB[k * 32 + lane];
+  int buf = 0;
+  prefetch(gwarp, 0);
+  for (int slice = gwarp; slice < P.nslices; slice += nwarps, buf ^= 1) {
+    prefetch(slice + nwarps, buf ^ 1);          // records of the next slice: in flight during this one
+    const int row = slice * 32 + lane;
+    const bool live = row < P.nrows;
+    const int rr = live ? row : 0;
+    const int base = P.slice_ptr[slice];
+    const int w = (P.slice_ptr[slice + 1] - base) >> 5;
+    const int ibase = P.inc_slice_ptr[slice];
+    const int iw = (P.inc_slice_ptr[slice + 1] - ibase) >> 5;
+    // own-node data (coalesced; independent of the records)
+    const double2 q_own = P.xy[rr];
+    const bool rowD = live && P.isD[rr] != 0;
+    double own_g = 0.0, own_e3 = 0.0, own_u = 0.0, own_v = 0.0, own_eh = 0.0, own_ehi = 0.0;
+    if (MASS) own_g = P.gw[rr];
+    if (STIFF == STIFF_EXPV) own_e3 = P.E3[rr];
+    if (RHS == RHS_DDP || RHS == RHS_SRH) { own_u = P.fu[rr]; own_v = P.fv[rr]; own_eh = P.EH[rr]; own_ehi = P.EHi[rr]; }
+    if (RHS == RHS_SINH || RHS == RHS_POLY) own_eh = P.EH[rr];
+    for (int k = 0; k < w; ++k) acc[k * kAsmBlock + tid] = 0.0;
+    double bsum = 0.0, lift = 0.0;
+    int sdiag = 0;
+    __pipeline_wait_prior(1);                   // this slice's records have landed (the next slice's may be pending)
+    __syncwarp();
+
+    for (int k0 = 0; k0 < iw; k0 += kAsmBatch) {
+      int4 rec[kAsmBatch];
+      IncData d[kAsmBatch];
+      // ---- level 1: issue every gather of the batch ----
+#pragma unroll
+      for (int j = 0; j < kAsmBatch; ++j) {
+        const int k = k0 + j;
+        rec[j] = make_int4(-1, 0, 0, 0);
+        if (k < iw && live) rec[j] = (k < ring_w) ? ring[(buf * ring_w + k) * 32 + lane] : P.inc[ibase + k * 32 + lane];
+        if (rec[j].x >= 0) {
+          const int e = rec[j].x >> 2, a = rec[j].x & 3, nb = rec[j].z, nc = rec[j].w;
+          d[j].qb = P.xy[nb]; d[j].qc = P.xy[nc];
+          if (STIFF == STIFF_COEF) { d[j].phx = P.phx[e]; d[j].phy = P.phy[e]; }
+          if (STIFF == STIFF_EXPV) { d[j].phx = P.phx[e]; d[j].eb = P.E3[nb]; d[j].ec = P.E3[nc]; }
+          if (STIFF != STIFF_BASE) {
+            d[j].bD = P.isD[nb] != 0; d[j].cD = P.isD[nc] != 0;
+          }
+          if (MASS) { d[j].gb = P.gw[nb]; d[j].gc = P.gw[nc]; }
+          if (RHS == RHS_DDP || RHS == RHS_SRH) { d[j].ub = P.fu[nb]; d[j].vb = P.fv[nb]; d[j].ehb = P.EH[nb]; d[j].ehib = P.EHi[nb]; }
+          if (RHS == RHS_SINH || RHS == RHS_POLY) d[j].ehb = P.EH[nb];
+          if (RHS == RHS_DDP || RHS == RHS_SINH) d[j].mid = P.mid[3 * e + a];
+        }
+      }
+      // ---- compute, in incidence order ----
+#pragma unroll
+      for (int j = 0; j < kAsmBatch; ++j) {
+        if (rec[j].x < 0) continue;
+        const int e = rec[j].x >> 2, a = rec[j].x & 3;
+        const double2 q_b = d[j].qb, q_c = d[j].qc;
+        // canonical corner order (1,2,3) of the triangle: corner a is this row
+        const double2 q1 = (a == 0) ? q_own : (a == 1) ? q_c : q_b;
+        const double2 q2 = (a == 0) ? q_b : (a == 1) ? q_own : q_c;
+        const double2 q3 = (a == 0) ? q_c : (a == 1) ? q_b : q_own;
+        // edge vectors and signed area, src:243-246
+        const double ux = q2.x - q3.x, uy = q2.y - q3.y;
+        const double vx = q3.x - q1.x, vy = q3.y - q1.y;
+        const double wx = q1.x - q2.x, wy = q1.y - q2.y;
+        const double ar = (ux * vy - uy * vx) * 0.5;
+        const int s_self = rec[j].y & 255, s_next = (rec[j].y >> 8) & 255, s_prev = (rec[j].y >> 16) & 255;
+        sdiag = s_self;
+        double c_self = 0.0, c_next = 0.0, c_prev = 0.0;
+        if (STIFF != STIFF_BASE) {
+          double phx, phy;
+          if (STIFF == STIFF_COEF) { phx = d[j].phx; phy = d[j].phy; }
+          else {
+            // exp((V1+V2+V3)/3) as the product of the nodal factors in canonical corner order, src:469
+            const double eb = d[j].eb, ec = d[j].ec;
+            const double e1 = (a == 0) ? own_e3 : (a == 1) ? ec : eb;
+            const double e2 = (a == 0) ? eb : (a == 1) ? own_e3 : ec;
+            const double e3 = (a == 0) ? ec : (a == 1) ? eb : own_e3;
+            phx = d[j].phx * (e1 * e2 * e3); phy = phx;
+          }
+          const double inv4 = 1.0 / fabs(ar * 4.0);  // src:257 (one division per triangle; <= 1 ulp vs x/ar4)
+          // canonical lower-triangle entries K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar|, i>=j
+          // (src:260-266); select the row of corner a: self, next, prev.
+          const double sx = (a == 0) ? ux : (a == 1) ? vx : wx, sy = (a == 0) ? uy : (a == 1) ? vy : wy;
+          const double nhx = (a == 0) ? vx : wx, nhy = (a == 0) ? vy : wy;   // (a,next): (2,1),(3,2),(3,1)
+          const double nlx = (a == 1) ? vx : ux, nly = (a == 1) ? vy : uy;
+          const double khx = (a == 1) ? vx : wx, khy = (a == 1) ? vy : wy;   // (a,prev): (3,1),(2,1),(3,2)
+          const double klx = (a == 2) ? vx : ux, kly = (a == 2) ? vy : uy;
+          const double k_self = (sx * phx * sx + sy * phy * sy) * inv4;
+          const double k_next = (nhx * phx * nlx + nhy * phy * nly) * inv4;
+          const double k_prev = (khx * phx * klx + khy * phy * kly) * inv4;
+          // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
+          c_self = rowD ? 0.0 : k_self;
+          c_next = (rowD || d[j].bD) ? 0.0 : k_next;
+          c_prev = (rowD || d[j].cD) ? 0.0 : k_prev;
+          // boundary lifting b -= K[:,D]*gD on rows outside D, src:362
+          if (!rowD) {
+            if (d[j].bD) lift += k_next * P.gD[rec[j].z];   // rare (rows next to a contact): dependent load is fine
+            if (d[j].cD) lift += k_prev * P.gD[rec[j].w];
+          }
+        }
+        if (MASS) {
+          // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never
+          // eliminated (Q3)
+          const double ar30 = ar * (1.0 / 30.0);
+          const double Wa = own_g * ar30, Wb = d[j].gb * ar30, Wc = d[j].gc * ar30;
+          // canonical addition order of src:380-386 (W1,W2,W3 left to right)
+          const double W1 = (a == 0) ? Wa : (a == 1) ? Wc : Wb;
+          const double W2 = (a == 0) ? Wb : (a == 1) ? Wa : Wc;
+          const double W3 = (a == 0) ? Wc : (a == 1) ? Wb : Wa;
+          double m_self, m_next, m_prev;
+          if (a == 0) { m_self = 3.0 * W1 + W2 + W3; m_next = W1 + W2 + W3 * 0.5; m_prev = W1 + W2 * 0.5 + W3; }
+          else if (a == 1) { m_self = W1 + 3.0 * W2 + W3; m_next = W1 * 0.5 + W2 + W3; m_prev = W1 + W2 + W3 * 0.5; }
+          else { m_self = W1 + W2 + 3.0 * W3; m_next = W1 + W2 * 0.5 + W3; m_prev = W1 * 0.5 + W2 + W3; }
+          c_self -= m_self; c_next -= m_next; c_prev -= m_prev;
+        }
+        if (STIFF != STIFF_BASE || MASS) {
+          acc[s_self * kAsmBlock + tid] += c_self;
+          acc[s_next * kAsmBlock + tid] += c_next;
+          acc[s_prev * kAsmBlock + tid] += c_prev;
+        }
+        // lumped edge-midpoint load: corner a takes the midpoint between a and next (src:345-350, Q1)
+        if (RHS != RHS_NONE && RHS != RHS_ZERO) {
+          double f;
+          if (RHS == RHS_DDP) {   // src:341-343
+            const double ua = (own_u + d[j].ub) * 0.5, va = (own_v + d[j].vb) * 0.5;
+            const double eS = own_eh * d[j].ehb, eSi = own_ehi * d[j].ehib;
+            f = P.par0 * (eSi * va - eS * ua) + d[j].mid;
+          } else if (RHS == RHS_SRH) {  // src:517-519
+            const double ua = (own_u + d[j].ub) * 0.5, va = (own_v + d[j].vb) * 0.5;
+            const double eS = own_eh * d[j].ehb, eSi = own_ehi * d[j].ehib;
+            f = 1.0 / (P.par0 * (eS * ua + 1.0) + P.par1 * (eSi * va + 1.0));
+          } else if (RHS == RHS_SINH) {  // registered functor, test:95
+            const double S = (own_eh + d[j].ehb) * 0.5;
+            f = d[j].mid + P.par0 * sinh(P.par1 * S);
+          } else {  // RHS_POLY, README:107-108
+            const double S = (own_eh + d[j].ehb) * 0.5;
+            const int deg = (int)P.par0;
+            f = P.mid_poly[deg][3 * e + a];
+            for (int dd = deg - 1; dd >= 0; --dd) f = f * S + P.mid_poly[dd][3 * e + a];
+          }
+          bsum += f * (fabs(ar) * (1.0 / 3.0));  // src:349
+        }
+      }
+    }
+
+    // ---- write the slice (coalesced) ----
+    if (STIFF != STIFF_BASE && rowD) acc[sdiag * kAsmBlock + tid] += 1.0;  // src:279-281
+    double diag = 0.0, mv = 0.0;
     if (STIFF == STIFF_BASE) {
-      double m_k = m_slot, x_k = x_slot;
-      if (k != warp) {   // slots beyond the first nw (rows longer than the CTA's warp count)
-        m_k = ld_stream(P.base_val + idx);
-        if (RESID) x_k = P.xvec[ld_stream(P.col + idx)];
+      int k = 0;
+      for (; k + 4 <= w; k += 4) {   // level 2: columns + values first, then the x gather
+        const int idx = base + k * 32 + lane;
+        const double m0 = ld_stream(P.base_val + idx), m1 = ld_stream(P.base_val + idx + 32),
+                     m2 = ld_stream(P.base_val + idx + 64), m3 = ld_stream(P.base_val + idx + 96);
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+        if (RESID) {
+          const int c0 = ld_stream(P.col + idx), c1 = ld_stream(P.col + idx + 32), c2 = ld_stream(P.col + idx + 64),
+                    c3 = ld_stream(P.col + idx + 96);
+          x0 = P.xvec[c0]; x1 = P.xvec[c1]; x2 = P.xvec[c2]; x3 = P.xvec[c3];
+        }
+        const double a0 = acc[k * kAsmBlock + tid] + m0, a1 = acc[(k + 1) * kAsmBlock + tid] + m1,
+                     a2 = acc[(k + 2) * kAsmBlock + tid] + m2, a3 = acc[(k + 3) * kAsmBlock + tid] + m3;
+        if (RESID) { mv += m0 * x0; mv += m1 * x1; mv += m2 * x2; mv += m3 * x3; }
+        if (sdiag == k) diag = a0; if (sdiag == k + 1) diag = a1; if (sdiag == k + 2) diag = a2; if (sdiag == k + 3) diag = a3;
+        P.out_val[idx] = live ? a0 : 0.0; P.out_val[idx + 32] = live ? a1 : 0.0;
+        P.out_val[idx + 64] = live ? a2 : 0.0; P.out_val[idx + 96] = live ? a3 : 0.0;
       }
-      if (RESID) prod[k * 32 + lane] = live ? m_k * x_k : 0.0;
-      a_k += m_k;
-    } else if (isdiag && rowD) {
-      a_k += 1.0;   // src:279-281
-    }
-    if (!live) a_k = 0.0;
-    P.out_val[idx] = a_k;
-    if (isdiag) s_dval[lane] = a_k;
-  }
-  __syncthreads();
-  if (warp == 0 && live) {
-    if (P.dinv) P.dinv[row] = 1.0 / s_dval[lane];
-    double lift = s_lsum[lane];
-    if (STIFF != STIFF_BASE && P.lift_out) P.lift_out[row] = lift;
-    if (RHS != RHS_NONE) {
-      if (STIFF == STIFF_BASE) lift = fin_lift;
-      double bi = s_bsum[lane] + fin_nc;             // Neumann loads, src:994-996
-      bi -= lift;                                    // src:362
-      if (rowD) bi = fin_gd;                         // src:363
-      P.b[row] = bi;
-      if (RESID) {
-        double mv = 0.0;
-        for (int k = 0; k < w; ++k) mv += prod[k * 32 + lane];
-        P.resid[row] = mv - bi;                      // src:368
+      for (; k < w; ++k) {
+        const int idx = base + k * 32 + lane;
+        const double m_k = ld_stream(P.base_val + idx);
+        if (RESID) mv += m_k * P.xvec[ld_stream(P.col + idx)];
+        const double a_k = acc[k * kAsmBlock + tid] + m_k;
+        if (k == sdiag) diag = a_k;
+        P.out_val[idx] = live ? a_k : 0.0;
+      }
+    } else {
+      for (int k = 0; k < w; ++k) {
+        const double a_k = acc[k * kAsmBlock + tid];
+        if (k == sdiag) diag = a_k;
+        P.out_val[base + k * 32 + lane] = live ? a_k : 0.0;
       }
     }
+    if (live) {
+      if (P.dinv) P.dinv[row] = 1.0 / diag;
+      if (STIFF != STIFF_BASE && P.lift_out) P.lift_out[row] = lift;
+      if (RHS != RHS_NONE) {
+        if (STIFF == STIFF_BASE) lift = P.lift_in[row];
+        double bi = bsum;
+        if (P.nodal_const) bi += P.nodal_const[row];   // Neumann loads, src:994-996
+        bi -= lift;                                    // src:362
+        if (rowD) bi = P.gD[row];                      // src:363
+        P.b[row] = bi;
+        if (RESID) P.resid[row] = mv - bi;             // src:368
+      }
+    }
+    __syncwarp();
   }
+  __pipeline_wait_prior(0);
 }
 
 template <int STIFF, bool MASS, int RHS, bool RESID>
-static int launch_asm(Context* ctx, const AsmArgs& a) {
+static int launch_asm(Context* ctx, const AsmArgs& a_in) {
   const Pattern& P = ctx->pat;
   if (P.nslices == 0) return 0;
-  const int nw = std::max(1, std::min(8, P.max_inc));
-  size_t smem = (size_t)((RESID ? 3 : 2) * P.max_row_len + 3 * nw) * 32 * sizeof(double);
-  k_assemble<STIFF, MASS, RHS, RESID><<<P.nslices, 32 * nw, smem, ctx->stream>>>(a);
+  AsmArgs a = a_in;
+  a.wmax = P.max_row_len;
+  const int ring_w = std::min(P.max_inc, 8);
+  const size_t smem = (size_t)P.max_row_len * kAsmBlock * sizeof(double) + (size_t)kAsmWarps * 2 * ring_w * 32 * sizeof(int4);
+  auto kern = k_assemble<STIFF, MASS, RHS, RESID>;
+  static thread_local int blocks_per_sm_cache = 0;
+  static thread_local size_t smem_cache = (size_t)-1;
+  if (smem > 48 * 1024) DDPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem_cache != smem) {
+    DDPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_cache, kern, kAsmBlock, smem));
+    smem_cache = smem;
+  }
+  const int need = (P.nslices + kAsmWarps - 1) / kAsmWarps;
+  const int grid = std::max(1, std::min(need, ctx->num_sms * std::max(1, blocks_per_sm_cache)));
+  kern<<<grid, kAsmBlock, smem, ctx->stream>>>(a, ring_w);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
   return 0;
@@ -428,9 +575,17 @@ template <bool DOT>
 __global__ void __launch_bounds__(kVecBlock) k_spmv(int nrows, int nslices, const int* __restrict__ slice_ptr,
                                                     const int* __restrict__ col, const double* __restrict__ val,
                                                     const double* __restrict__ x, double* __restrict__ y,
-                                                    double* partials, PcgScalars* scal) {
+                                                    double* partials, PcgScalars* scal, const P2PDev pd) {
   __shared__ double sh_red[32];
   if (DOT && scal->done) return;
+  if (DOT && pd.nranks > 1) {   // the neighbours' halo pushes for this iteration must have landed
+    if (threadIdx.x < pd.nneigh) {
+      P2PWin* W = pd.win[pd.rank];
+      if (!spin_until(&W->halo_flag[pd.neigh[threadIdx.x]], pd.tag_halo)) W->error = 1;
+      __threadfence();
+    }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -465,7 +620,10 @@ __global__ void __launch_bounds__(kVecBlock) k_spmv(int nrows, int nslices, cons
   if (DOT) {
     double v[1] = {dot}, tot[1];
     if (grid_reduce<1, false>(v, partials, &scal->cnt[0], sh_red, tot)) {
-      if (threadIdx.x == 0) scal->sums[0] = tot[0];
+      if (threadIdx.x == 0) {
+        if (pd.nranks > 1) p2p_publish<1>(pd, 0, pd.tagA, tot);
+        else scal->sums[0] = tot[0];
+      }
     }
   }
 }
@@ -480,7 +638,8 @@ int launch_spmv(Context* ctx, const double* val, const double* x, double* y) {
   const Pattern& P = ctx->pat;
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
-  k_spmv<false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr);
+  P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
+  k_spmv<false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr, none);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
@@ -491,7 +650,8 @@ int launch_spmv_dot(Context* ctx, const double* val, const double* x, double* y)
   const Pattern& P = ctx->pat;
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
-  k_spmv<true><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal);
+  P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
+  k_spmv<true><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal, none);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
@@ -618,18 +778,27 @@ __global__ void k_pcg_start(PcgScalars* scal, double rtol, double atol_inf) {
   scal->done = (scal->sums[1] <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
 }
 
-// x += alpha p; r -= alpha q; local sums {r.D^-1 r, r.r}
+// x += alpha p; r -= alpha q; partial sums {r.D^-1 r, r.r, max|r|}
 __global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const double* __restrict__ p,
                                                           const double* __restrict__ q,
                                                           const double* __restrict__ dinv, double* __restrict__ x,
-                                                          double* __restrict__ r, double* partials, PcgScalars* scal) {
+                                                          double* __restrict__ r, double* partials, PcgScalars* scal,
+                                                          const P2PDev pd) {
   __shared__ double sh_red[32];
   if (scal->done) return;
-  const double pq = scal->sums[0];
+  double pq;
+  if (pd.nranks > 1) {
+    double t[1];
+    p2p_gather<1, 0u>(pd, 0, pd.tagA, t, sh_red);
+    pq = t[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal->sums[0] = pq;
+  } else {
+    pq = scal->sums[0];
+  }
   const double rz = scal->rz[par];
   if (!(pq > 0.0) || !(rz == rz)) {   // operator not SPD or NaN: stop
     if (blockIdx.x == 0 && threadIdx.x == 0) { scal->breakdown = 1; }
-    // every block takes this branch consistently; `done` is raised by k_pcg_direction
+    // every block (and every rank: pq is identical everywhere) takes this branch; `done` is raised by k_pcg_direction
     return;
   }
   const double alpha = rz / pq;
@@ -644,12 +813,12 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const 
     s_rr += ri * ri;
     s_max = fmax(s_max, fabs(ri));
   }
-  double v[2] = {s_rz, s_rr}, tot[2];
-  const bool last = grid_reduce<2, false>(v, partials, &scal->cnt[1], sh_red, tot);
-  if (last && threadIdx.x == 0) { scal->sums[1] = tot[0]; scal->sums[2] = tot[1]; }
-  double vm[1] = {s_max}, totm[1];
-  if (grid_reduce<1, true>(vm, partials + 2 * gridDim.x, &scal->cnt[2], sh_red, totm)) {
-    if (threadIdx.x == 0) scal->rmax = totm[0];
+  double v[3] = {s_rz, s_rr, s_max}, tot[3];
+  if (grid_reduce_mixed<3, 4u>(v, partials, &scal->cnt[1], sh_red, tot)) {
+    if (threadIdx.x == 0) {
+      if (pd.nranks > 1) p2p_publish<3>(pd, 1, pd.tagB, tot);
+      else { scal->sums[1] = tot[0]; scal->sums[2] = tot[1]; scal->rmax = tot[2]; }
+    }
   }
 }
 
@@ -657,17 +826,28 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const 
 __global__ void __launch_bounds__(kVecBlock) k_pcg_direction(int n, int par, int it, int max_it,
                                                              const double* __restrict__ r,
                                                              const double* __restrict__ dinv, double* __restrict__ p,
-                                                             PcgScalars* scal) {
+                                                             PcgScalars* scal, const P2PDev pd) {
+  __shared__ double sh_red[32];
   if (scal->done) return;
   if (scal->breakdown) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { scal->done = 1; scal->iters = it; }
     return;
   }
-  const double rz_new = scal->sums[1], rr = scal->sums[2];
+  double rz_new, rr, rmax;
+  bool comm_ok = true;
+  if (pd.nranks > 1) {
+    double t[3];
+    comm_ok = p2p_gather<3, 4u>(pd, 1, pd.tagB, t, sh_red);
+    rz_new = t[0]; rr = t[1]; rmax = t[2];
+  } else {
+    rz_new = scal->sums[1]; rr = scal->sums[2]; rmax = scal->rmax;
+  }
   const double rz_old = scal->rz[par];
-  const bool stop = (rr <= scal->thresh2) || (scal->rmax <= scal->thresh_inf) || (it + 1 >= max_it) || !(rr == rr);
+  const bool stop = (rr <= scal->thresh2) || (rmax <= scal->thresh_inf) || (it + 1 >= max_it) || !(rr == rr) || !comm_ok;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     scal->rz[par ^ 1] = rz_new;
+    scal->rmax = rmax;
+    if (!comm_ok) scal->breakdown = 2;
     scal->rr = rr;
     scal->iters = it + 1;
     if (stop) scal->done = 1;
@@ -683,16 +863,36 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
   const int n = ctx->n_own;
   const int par = it & 1;
   int rc;
-  if ((rc = halo_exchange(ctx, ctx->p))) return rc;
-  int g1 = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
-  k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
-                                                  ctx->partials, ctx->scal);
-  if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 1))) return rc;
-  int g2 = vec_grid(ctx, n, kVecBlock);
-  k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal);
-  if ((rc = allreduce_sum(ctx, &ctx->scal->sums[1], 2))) return rc;
-  if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
-  k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->r, dinv, ctx->p, ctx->scal);
+  const int g1 = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
+  const int g2 = vec_grid(ctx, n, kVecBlock);
+  P2PDev pd;
+  if (ctx->p2p.enabled) {
+    // Fused compute + collective over peer memory (NVLink): no NCCL call inside the PCG iteration.
+    P2PHost& H = ctx->p2p;
+    pd = H.dev;
+    pd.tag_halo = ++H.tag; pd.tagA = ++H.tag; pd.tagB = ++H.tag;
+    if (H.push.nneigh > 0) {
+      PushArgs pa = H.push;
+      pa.tag = pd.tag_halo;
+      k_halo_push<<<pa.nneigh, 1024, 0, ctx->stream>>>(pa, ctx->halo.send_idx, ctx->p, ctx->scal);
+      ctx->stats.kernel_launches++;
+    }
+    k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
+                                                    ctx->partials, ctx->scal, pd);
+    k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
+    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
+  } else {
+    memset(&pd, 0, sizeof(pd));
+    pd.nranks = 1;
+    if ((rc = halo_exchange(ctx, ctx->p))) return rc;
+    k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
+                                                    ctx->partials, ctx->scal, pd);
+    if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 1))) return rc;
+    k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
+    if ((rc = allreduce_sum(ctx, &ctx->scal->sums[1], 2))) return rc;
+    if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
+    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
+  }
   ctx->stats.kernel_launches += 3;
   ctx->stats.spmv_total++;
   return 0;
@@ -739,6 +939,10 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
   if (relres_out) *relres_out = (S.bb > 0) ? sqrt(S.rr / S.bb) : 0.0;
   ctx->stats.pcg_total += S.iters;
   ctx->hist_pcg.push_back((double)S.iters);
+  if (S.breakdown == 2) {
+    ctx->fail(DDPS_ERR_COMM, "peer-memory exchange timed out (a rank stopped participating)");
+    return DDPS_ERR_COMM;
+  }
   if (S.breakdown) {
     ctx->fail(DDPS_ERR_BREAKDOWN, "PCG breakdown: p.Ap <= 0 (operator not SPD; u or v negative? SURVEY H3)");
     return DDPS_ERR_BREAKDOWN;
