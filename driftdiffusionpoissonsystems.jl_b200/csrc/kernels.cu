@@ -572,10 +572,10 @@ int launch_prep_semlin(Context* ctx, const double* V) {
 // SpMV (SELL-32) with fused dot, persistent grid-stride over slices
 // ------------------------------------------------------------------------------------------------
 template <bool DOT>
-__global__ void __launch_bounds__(kVecBlock) k_spmv(int nrows, int nslices, const int* __restrict__ slice_ptr,
+__global__ void __launch_bounds__(kVecBlock, 8) k_spmv(int nrows, int nslices, const int* __restrict__ slice_ptr,
                                                     const int* __restrict__ col, const double* __restrict__ val,
                                                     const double* __restrict__ x, double* __restrict__ y,
-                                                    double* partials, PcgScalars* scal, const P2PDev pd) {
+                                                    double* partials, PcgScalars* scal, const P2PDev pd, const int rev) {
   __shared__ double sh_red[32];
   if (DOT && scal->done) return;
   if (DOT && pd.nranks > 1) {   // the neighbours' halo pushes for this iteration must have landed
@@ -590,12 +590,18 @@ __global__ void __launch_bounds__(kVecBlock) k_spmv(int nrows, int nslices, cons
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
   double dot = 0.0;
-  for (int slice = gw; slice < nslices; slice += nw) {
+  // `rev` alternates the traversal direction between consecutive PCG kernels: the vector tail the previous
+  // kernel wrote last is still in the 126 MB L2 and is consumed first.
+  for (int s0 = gw; s0 < nslices; s0 += nw) {
+    const int slice = rev ? nslices - 1 - s0 : s0;
     const int base = slice_ptr[slice];
     const int w = (slice_ptr[slice + 1] - base) >> 5;
     int idx = base + lane;
     double sum = 0.0;
     int k = 0;
+    // groups of 4 entries: 8 independent coalesced loads in flight per warp before the 4 gathers; measured
+    // faster than whole-row unrolling (which halves the occupancy) and than 16-bit column deltas (no gain:
+    // the kernel already keeps HBM ~72% busy = the practical read limit)
     for (; k + 4 <= w; k += 4) {
       const int c0 = ld_stream(col + idx), c1 = ld_stream(col + idx + 32), c2 = ld_stream(col + idx + 64),
                 c3 = ld_stream(col + idx + 96);
@@ -639,7 +645,7 @@ int launch_spmv(Context* ctx, const double* val, const double* x, double* y) {
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
-  k_spmv<false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr, none);
+  k_spmv<false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr, none, 0);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
@@ -651,7 +657,7 @@ int launch_spmv_dot(Context* ctx, const double* val, const double* x, double* y)
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
-  k_spmv<true><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal, none);
+  k_spmv<true><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal, none, 0);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
@@ -779,7 +785,7 @@ __global__ void k_pcg_start(PcgScalars* scal, double rtol, double atol_inf) {
 }
 
 // x += alpha p; r -= alpha q; partial sums {r.D^-1 r, r.r, max|r|}
-__global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const double* __restrict__ p,
+__global__ void __launch_bounds__(kVecBlock, 8) k_pcg_update(int n, int par, int rev, const double* __restrict__ p,
                                                           const double* __restrict__ q,
                                                           const double* __restrict__ dinv, double* __restrict__ x,
                                                           double* __restrict__ r, double* partials, PcgScalars* scal,
@@ -803,7 +809,8 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const 
   }
   const double alpha = rz / pq;
   double s_rz = 0.0, s_rr = 0.0, s_max = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const int i = rev ? n - 1 - i0 : i0;
     const double pi = p[i], qi = q[i];
     const double xi = x[i] + alpha * pi;
     const double ri = r[i] - alpha * qi;
@@ -823,7 +830,7 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_update(int n, int par, const 
 }
 
 // p = D^-1 r + beta p; convergence decision (identical in every block, written once by block 0)
-__global__ void __launch_bounds__(kVecBlock) k_pcg_direction(int n, int par, int it, int max_it,
+__global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, int rev, int it, int max_it,
                                                              const double* __restrict__ r,
                                                              const double* __restrict__ dinv, double* __restrict__ p,
                                                              PcgScalars* scal, const P2PDev pd) {
@@ -854,8 +861,10 @@ __global__ void __launch_bounds__(kVecBlock) k_pcg_direction(int n, int par, int
   }
   if (stop) return;
   const double beta = rz_new / rz_old;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const int i = rev ? n - 1 - i0 : i0;
     p[i] = dinv[i] * r[i] + beta * p[i];
+  }
 }
 
 int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it) {
@@ -865,6 +874,9 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
   int rc;
   const int g1 = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   const int g2 = vec_grid(ctx, n, kVecBlock);
+  // traversal directions: the three kernels of an iteration alternate (reserved[0] != 0 disables the trick)
+  const int r0 = ctx->opts.reserved[0] ? 0 : (it & 1);
+  const int r1 = ctx->opts.reserved[0] ? 0 : (r0 ^ 1);
   P2PDev pd;
   if (ctx->p2p.enabled) {
     // Fused compute + collective over peer memory (NVLink): no NCCL call inside the PCG iteration.
@@ -878,20 +890,20 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
       ctx->stats.kernel_launches++;
     }
     k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
-                                                    ctx->partials, ctx->scal, pd);
-    k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
-    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
+                                                    ctx->partials, ctx->scal, pd, r0);
+    k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r1, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
+    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
   } else {
     memset(&pd, 0, sizeof(pd));
     pd.nranks = 1;
     if ((rc = halo_exchange(ctx, ctx->p))) return rc;
     k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
-                                                    ctx->partials, ctx->scal, pd);
+                                                    ctx->partials, ctx->scal, pd, r0);
     if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 1))) return rc;
-    k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
+    k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r1, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
     if ((rc = allreduce_sum(ctx, &ctx->scal->sums[1], 2))) return rc;
     if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
-    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
+    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
   }
   ctx->stats.kernel_launches += 3;
   ctx->stats.spmv_total++;
