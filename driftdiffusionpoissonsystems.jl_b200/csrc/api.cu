@@ -188,6 +188,7 @@ AsmArgs base_args(Context* ctx) {
   const Pattern& P = ctx->pat;
   a.nrows = P.nrows; a.nslices = P.nslices; a.slice_ptr = P.slice_ptr; a.col = P.col;
   a.inc_slice_ptr = P.inc_slice_ptr; a.inc = P.inc; a.xy = ctx->xy; a.elem = ctx->elem; a.isD = ctx->isD;
+  a.diag_slot = P.diag_slot; a.bn_ptr = P.bn_ptr; a.bn_nodes = P.bn_nodes; a.lmax = P.max_bn; a.wmax = P.max_row_len;
   a.partial_max = ctx->partials; a.scal = ctx->scal;
   return a;
 }
@@ -290,7 +291,8 @@ struct EventTimer {
 int vsolve(Context* ctx) {
   int rc;
   const int n = ctx->n_own;
-  DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:311
+  if (!(ctx->opts.warm_start_v && ctx->stats.outer_iters > 0))   // opt-in warm start keeps the previous V
+    DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:311
   int newton = 0;
   const int cap = ctx->opts.max_newton > 0 ? ctx->opts.max_newton : 1000;
   while (true) {
@@ -954,7 +956,7 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
     switch (kernel) {
       case 0: return launch_spmv(ctx, ctx->val_op, ctx->p, ctx->q);
       case 1: return assemble_uv(ctx, DDPS_FIELD_U, ctx->rec_mode, ctx->tau_p, ctx->tau_n, ctx->V, ctx->U0, ctx->W0);
-      case 2: return pcg_iteration_launch(ctx, ctx->val_op, ctx->dinv, ctx->x, it, 1 << 30);
+      case 2: return pcg_iteration_launch(ctx, ctx->val_op, ctx->dinv, ctx->x, it, 1 << 30, it == 1);
       case 3: return assemble_newton(ctx, false, ctx->delta, ctx->V, ctx->U0, ctx->W0);
       case 4: return assemble_base(ctx, ctx->base_is_semlin);
       case 5: return launch_spmv_dot(ctx, ctx->val_op, ctx->p, ctx->q);
@@ -966,9 +968,9 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
   // FP64 values, int32 indices
   switch (kernel) {
     case 0: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq; break;                     // 14.86 B/nnz
-    case 1: bytes = 12.0 * nme + 16.0 * nq + 8.0 * nme + 6 * 8.0 * nq + 8.0 * nnz + 16.0 * nq; break;
+    case 1: bytes = 12.0 * nme + 16.0 * nq + 3 * 8.0 * nq + 8.0 * nme + 8.0 * nnz + 8.0 * nq; break;   // 72 B/triangle
     case 2: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq + 10 * 8.0 * nq; break;     // SURVEY 8d PCG iteration
-    case 3: bytes = 12.0 * nme + 16.0 * nq + 24.0 * nme + 6 * 8.0 * nq + 12.0 * nnz + 8.0 * nnz + 24.0 * nq; break;
+    case 3: bytes = 12.0 * nme + 16.0 * nq + 3 * 8.0 * nq + 24.0 * nme + 12.0 * nnz + 8.0 * nnz + 16.0 * nq; break;  // 134 B/triangle
     case 4: bytes = 12.0 * nme + 16.0 * nq + 8.0 * nme + 8.0 * nnz + 8.0 * nq; break;
     case 5: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq; break;
   }

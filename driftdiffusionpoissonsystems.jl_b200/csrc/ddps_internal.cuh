@@ -33,6 +33,7 @@ namespace ddps {
 
 constexpr int kSlice = 32;        // rows per slice = warp size
 constexpr int kAsmBlock = 128;    // threads per block of the row-major assembly kernels
+constexpr int kAsmRows = 128;     // rows per assembly block (= kAsmBlock: one thread per row)
 constexpr int kMaxRowLen = 40;    // shared-memory accumulator columns available per row
 constexpr int kVecBlock = 256;    // threads per block of SpMV / vector kernels
 constexpr int kMaxPoly = 5;       // polynomial functor: degree 0..4
@@ -61,7 +62,12 @@ struct Pattern {
   // incidence lists
   int64_t inc_entries = 0;
   int* inc_slice_ptr = nullptr;  // [nslices+1]
-  int4* inc = nullptr;           // [inc_entries] {tri*4+corner | -1, slot_self | slot_next<<8 | slot_prev<<16 | ord bits, next node, prev node}
+  int2* inc = nullptr;           // [inc_entries] {tri*4+corner | -1, slot_next | slot_prev<<5 | l_next<<10 | l_prev<<21}
+  unsigned char* diag_slot = nullptr;  // [nrows] slot of the diagonal entry
+  // row blocks of kAsmRows rows: sorted distinct nodes the block touches (staged in shared memory by k_assemble)
+  int nblocks = 0, max_bn = 0, bn_total = 0;
+  int* bn_ptr = nullptr;         // [nblocks+1]
+  int* bn_nodes = nullptr;       // [bn_total]
 };
 
 // device-side scalar block of one PCG solve (all control flow stays on the device)
@@ -214,7 +220,11 @@ struct AsmArgs {
   const int* slice_ptr;
   const int* col;
   const int* inc_slice_ptr;
-  const int4* inc;
+  const int2* inc;
+  const unsigned char* diag_slot;
+  const int* bn_ptr;
+  const int* bn_nodes;
+  int lmax;
   const double2* xy;
   const int4* elem;
   const unsigned char* isD;
@@ -266,7 +276,7 @@ int launch_max_abs_diff3(Context* ctx, const double* a0, const double* a1, const
 int launch_max_abs(Context* ctx, const double* a, int n, double* host_out);
 
 int fetch_resid_norm(Context* ctx, double* host_out);  // norm_inf written by the last RESID assembly
-int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it);
+int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it, bool first);
 // Jacobi-PCG: solve val*x = rhs; x holds the initial guess if x0_nonzero (else it is zeroed).
 int pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
               double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);

@@ -147,23 +147,37 @@ template <int NV, unsigned MAXMASK>
 __device__ __forceinline__ bool p2p_gather(const P2PDev& pd, int phase, unsigned long long tag, double (&out)[NV],
                                            double* sh) {
   __shared__ int s_ok;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {   // lane r waits for rank r (all flags polled concurrently), lane 0 combines in rank order
     P2PWin* W = pd.win[pd.rank];
+    const int r = threadIdx.x;
     bool ok = true;
-    double acc[NV];
+    double mine[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (int r = 0; r < pd.nranks; ++r) {
-      ok = ok && spin_until(phase == 0 ? &W->redA_flag[r] : &W->redB_flag[r], tag);
+    for (int i = 0; i < NV; ++i) mine[i] = 0.0;
+    if (r < pd.nranks) {
+      ok = spin_until(phase == 0 ? &W->redA_flag[r] : &W->redB_flag[r], tag);
       __threadfence();
       const volatile double* src = phase == 0 ? W->redA[r] : W->redB[r];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) acc[i] = ((MAXMASK >> i) & 1) ? fmax(acc[i], src[i]) : acc[i] + src[i];
+      for (int i = 0; i < NV; ++i) mine[i] = src[i];
     }
+    ok = __all_sync(0xffffffffu, ok);
+    double acc[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) sh[i] = acc[i];
-    s_ok = ok ? 1 : 0;
-    if (!ok) W->error = 1;
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (int q = 0; q < pd.nranks; ++q) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const double t = __shfl_sync(0xffffffffu, mine[i], q);
+        acc[i] = ((MAXMASK >> i) & 1) ? fmax(acc[i], t) : acc[i] + t;
+      }
+    }
+    if (r == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sh[i] = acc[i];
+      s_ok = ok ? 1 : 0;
+      if (!ok) W->error = 1;
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -190,273 +204,290 @@ __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p);
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 
 // ------------------------------------------------------------------------------------------------
-// Row-major fused assembly.
+// Row-major fused assembly with block-cooperative staging.
 //
-// One thread per matrix row, one warp per 32-row slice, persistent warps striding over the slices.
-// The kernel is latency-bound, not byte-bound (ncu: every data-dependent load level costs one DRAM
-// latency and nothing else is saturated), so it is organised around the number of DEPENDENT load
-// levels per slice and the number of slices in flight per SM:
-//   level 0  the slice's incidence records -- prefetched one slice ahead with cp.async into a
-//            per-warp shared-memory ring, so this level is off the critical path;
-//   level 1  for a batch of BATCH incidences at a time: every gather the batch needs (neighbour
-//            coordinates, nodal factors, per-triangle coefficients) is issued before any is used;
-//   level 2  (Newton systems only) columns+values of the base matrix, then the x gather.
-// Contributions are accumulated in incidence order into the thread's PRIVATE shared-memory column
-// (slots resolved at setup): no atomics, no staging buffer, bitwise reproducible, same summation
-// order as the reference's sparse() (increasing triangle id per entry).  All slice-
-// interleaved streams (records, values, columns) are fully coalesced 256/512-byte warp accesses.
+// One CTA per block of 128 consecutive rows, one thread per row.
+//   level 1 (coalesced):  the block's sorted node list (built at setup) and each row's packed 8-byte
+//                         incidence records;
+//   level 2 (gathers):    the nodal fields of every DISTINCT node the block touches are gathered ONCE
+//                         into shared memory (a 128-row block of a P1 mesh touches ~3x128 nodes but its
+//                         rows reference them ~13x128 times), plus the per-triangle coefficients;
+//   compute:              each thread walks its row's incident triangles in increasing triangle order,
+//                         reads the two other corners from shared memory through the block-local
+//                         indices packed in the record, and accumulates its row of every local 3x3
+//                         matrix into its PRIVATE shared-memory column (slots resolved at setup).
+// No atomics, no staging buffer in HBM, bitwise reproducible, same summation order as the reference's
+// sparse() (increasing triangle id per entry).  Dirichlet elimination (src:271-284), lifting
+// (src:362), the lumped edge-midpoint load (src:345-350) and, for the Newton systems, the residual
+// M*V-b (src:368) are fused into the same pass; all transcendentals live in the nodal prep kernels.
 // ------------------------------------------------------------------------------------------------
-constexpr int kAsmWarps = kAsmBlock / 32;
-#ifndef DDPS_ASM_BATCH
-#define DDPS_ASM_BATCH 2
-#endif
+constexpr int kMaxIncReg = 8;   // incidence records held in registers; longer rows take the tail loop
 #ifndef DDPS_ASM_MINBLOCKS
 #define DDPS_ASM_MINBLOCKS 1
 #endif
-constexpr int kAsmBatch = DDPS_ASM_BATCH;
-
-struct IncData {           // everything one incidence needs from memory (level-1 gathers)
-  double2 qb, qc;
-  double phx, phy, eb, ec, gb, gc, ub, vb, ehb, ehib, mid;
-  bool bD, cD;
-};
 
 template <int STIFF, bool MASS, int RHS, bool RESID>
-__global__ void __launch_bounds__(kAsmBlock, DDPS_ASM_MINBLOCKS) k_assemble(const AsmArgs P, const int ring_w) {
+__global__ void __launch_bounds__(kAsmBlock, DDPS_ASM_MINBLOCKS) k_assemble(const AsmArgs P) {
   extern __shared__ double sm[];
-  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  // shared memory: acc[wmax][kAsmBlock] doubles, then per-warp record ring [2][ring_w][32] int4
+  constexpr bool NEED_UV = (RHS == RHS_DDP || RHS == RHS_SRH);
+  constexpr bool NEED_EH = NEED_UV || RHS == RHS_SINH || RHS == RHS_POLY;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int lmax = P.lmax;
+  // shared memory: acc[wmax][128] | X | Y | E3 | GW | FU | FV | EH | EHI  (each [lmax]) | node ids | isD
   double* acc = sm;
-  int4* ring = reinterpret_cast<int4*>(sm + (size_t)P.wmax * kAsmBlock) + (size_t)wib * 2 * ring_w * 32;
-  const int gwarp = blockIdx.x * kAsmWarps + wib, nwarps = gridDim.x * kAsmWarps;
+  double* sX = acc + (size_t)P.wmax * kAsmBlock;
+  double* sY = sX + lmax;
+  double* sE3 = sY + lmax;
+  double* sGW = sE3 + (STIFF == STIFF_EXPV ? lmax : 0);
+  double* sFU = sGW + (MASS ? lmax : 0);
+  double* sFV = sFU + (NEED_UV ? lmax : 0);
+  double* sEH = sFV + (NEED_UV ? lmax : 0);
+  double* sEHI = sEH + (NEED_EH ? lmax : 0);
+  int* sNode = reinterpret_cast<int*>(sEHI + (NEED_UV ? lmax : 0));
+  unsigned char* sD = reinterpret_cast<unsigned char*>(sNode + lmax);
 
-  auto prefetch = [&](int slice, int buf) {
-    if (slice < P.nslices) {
-      const int ibase = P.inc_slice_ptr[slice];
-      const int iw = min((P.inc_slice_ptr[slice + 1] - ibase) >> 5, ring_w);
-      for (int k = 0; k < iw; ++k)
-        __pipeline_memcpy_async(&ring[(buf * ring_w + k) * 32 + lane], &P.inc[ibase + k * 32 + lane], sizeof(int4));
+  const int blk = blockIdx.x;
+  const int row = blk * kAsmRows + tid;
+  const bool live = row < P.nrows;
+  const int rr = live ? row : 0;
+  const int slice = row >> 5;
+  const bool in_pat = slice < P.nslices;
+  int base = 0, w = 0, ibase = 0, iw = 0;
+  if (in_pat) {
+    base = P.slice_ptr[slice]; w = (P.slice_ptr[slice + 1] - base) >> 5;
+    ibase = P.inc_slice_ptr[slice]; iw = (P.inc_slice_ptr[slice + 1] - ibase) >> 5;
+  }
+  // ---- level 1: incidence records (coalesced) ----
+  int2 rec[kMaxIncReg];
+#pragma unroll
+  for (int k = 0; k < kMaxIncReg; ++k) {
+    rec[k] = make_int2(-1, 0);
+    if (k < iw && live) rec[k] = P.inc[ibase + k * 32 + lane];
+  }
+  // ---- stage the block's distinct nodes (level 1: ids, level 2: fields) ----
+  const int nb0 = P.bn_ptr[blk], nn = P.bn_ptr[blk + 1] - nb0;
+  for (int i0 = tid; i0 < nn; i0 += 4 * kAsmBlock) {   // 4 list entries per thread per pass: ids first, then all gathers
+    int g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int i = i0 + j * kAsmBlock; g[j] = (i < nn) ? P.bn_nodes[nb0 + i] : -1; }
+    double2 q[4];
+    double f_e3[4], f_gw[4], f_u[4], f_v[4], f_eh[4], f_ehi[4];
+    unsigned char f_d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (g[j] < 0) continue;
+      q[j] = P.xy[g[j]];
+      if (STIFF == STIFF_EXPV) f_e3[j] = P.E3[g[j]];
+      if (STIFF != STIFF_BASE) f_d[j] = P.isD[g[j]];
+      if (MASS) f_gw[j] = P.gw[g[j]];
+      if (NEED_UV) { f_u[j] = P.fu[g[j]]; f_v[j] = P.fv[g[j]]; f_ehi[j] = P.EHi[g[j]]; }
+      if (NEED_EH) f_eh[j] = P.EH[g[j]];
     }
-    __pipeline_commit();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (g[j] < 0) continue;
+      const int i = i0 + j * kAsmBlock;
+      sX[i] = q[j].x; sY[i] = q[j].y;
+      sNode[i] = g[j];
+      if (STIFF == STIFF_EXPV) sE3[i] = f_e3[j];
+      if (STIFF != STIFF_BASE) sD[i] = f_d[j];
+      if (MASS) sGW[i] = f_gw[j];
+      if (NEED_UV) { sFU[i] = f_u[j]; sFV[i] = f_v[j]; sEHI[i] = f_ehi[j]; }
+      if (NEED_EH) sEH[i] = f_eh[j];
+    }
+  }
+  // ---- own-node data (coalesced) and per-triangle coefficients (level 2) ----
+  const double2 q_own = P.xy[rr];
+  const bool rowD = live && P.isD[rr] != 0;
+  double own_g = 0.0, own_e3 = 0.0, own_u = 0.0, own_v = 0.0, own_eh = 0.0, own_ehi = 0.0;
+  if (MASS) own_g = P.gw[rr];
+  if (STIFF == STIFF_EXPV) own_e3 = P.E3[rr];
+  if (NEED_UV) { own_u = P.fu[rr]; own_v = P.fv[rr]; own_ehi = P.EHi[rr]; }
+  if (NEED_EH) own_eh = P.EH[rr];
+  double cphx[kMaxIncReg], cphy[kMaxIncReg], cmid[kMaxIncReg];
+#pragma unroll
+  for (int k = 0; k < kMaxIncReg; ++k) {
+    cphx[k] = 0.0; cphy[k] = 0.0; cmid[k] = 0.0;
+    if (rec[k].x >= 0) {
+      const int e = rec[k].x >> 2, a = rec[k].x & 3;
+      if (STIFF != STIFF_BASE) cphx[k] = P.phx[e];
+      if (STIFF == STIFF_COEF) cphy[k] = P.phy[e];
+      if (RHS == RHS_DDP || RHS == RHS_SINH) cmid[k] = P.mid[3 * e + a];
+    }
+  }
+  for (int k = 0; k < w; ++k) acc[k * kAsmBlock + tid] = 0.0;
+  const int sdiag = live ? P.diag_slot[row] : 0;
+  // Newton systems: base*x for the residual -- all values + columns of the row first, then all x gathers
+  double mv = 0.0;
+  if (STIFF == STIFF_BASE && RESID && in_pat) {
+    for (int k0 = 0; k0 < w; k0 += 8) {
+      double m[8];
+      int c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        m[j] = 0.0; c[j] = rr;
+        if (k0 + j < w) { m[j] = ld_stream(P.base_val + base + (k0 + j) * 32 + lane); c[j] = ld_stream(P.col + base + (k0 + j) * 32 + lane); }
+      }
+      double xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] = (k0 + j < w) ? P.xvec[c[j]] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (k0 + j < w) mv += m[j] * xv[j];
+    }
+  }
+  __syncthreads();
+
+  double bsum = 0.0, lift = 0.0;
+  auto one = [&](const int2 r, const double phx_in, const double phy_in, const double mid_in) {
+    const int e = r.x >> 2, a = r.x & 3;
+    const unsigned y = (unsigned)r.y;
+    const int s_next = y & 31, s_prev = (y >> 5) & 31, lb = (y >> 10) & 2047, lc = y >> 21;
+    const double2 q_b = make_double2(sX[lb], sY[lb]), q_c = make_double2(sX[lc], sY[lc]);
+    // canonical corner order (1,2,3) of the triangle: corner a is this row
+    const double2 q1 = (a == 0) ? q_own : (a == 1) ? q_c : q_b;
+    const double2 q2 = (a == 0) ? q_b : (a == 1) ? q_own : q_c;
+    const double2 q3 = (a == 0) ? q_c : (a == 1) ? q_b : q_own;
+    // edge vectors and signed area, src:243-246
+    const double ux = q2.x - q3.x, uy = q2.y - q3.y;
+    const double vx = q3.x - q1.x, vy = q3.y - q1.y;
+    const double wx = q1.x - q2.x, wy = q1.y - q2.y;
+    const double ar = (ux * vy - uy * vx) * 0.5;
+    double c_self = 0.0, c_next = 0.0, c_prev = 0.0;
+    if (STIFF != STIFF_BASE) {
+      double phx = phx_in, phy = phy_in;
+      if (STIFF == STIFF_EXPV) {
+        // exp((V1+V2+V3)/3) as the product of the nodal factors in canonical corner order, src:469
+        const double eb = sE3[lb], ec = sE3[lc];
+        const double e1 = (a == 0) ? own_e3 : (a == 1) ? ec : eb;
+        const double e2 = (a == 0) ? eb : (a == 1) ? own_e3 : ec;
+        const double e3 = (a == 0) ? ec : (a == 1) ? eb : own_e3;
+        phx = phx_in * (e1 * e2 * e3); phy = phx;
+      }
+      const double inv4 = 1.0 / fabs(ar * 4.0);  // src:257 (one division per triangle; <= 1 ulp vs x/ar4)
+      // canonical lower-triangle entries K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar|, i>=j
+      // (src:260-266); select the row of corner a: self, next, prev.
+      const double sx = (a == 0) ? ux : (a == 1) ? vx : wx, sy = (a == 0) ? uy : (a == 1) ? vy : wy;
+      const double nhx = (a == 0) ? vx : wx, nhy = (a == 0) ? vy : wy;   // (a,next): (2,1),(3,2),(3,1)
+      const double nlx = (a == 1) ? vx : ux, nly = (a == 1) ? vy : uy;
+      const double khx = (a == 1) ? vx : wx, khy = (a == 1) ? vy : wy;   // (a,prev): (3,1),(2,1),(3,2)
+      const double klx = (a == 2) ? vx : ux, kly = (a == 2) ? vy : uy;
+      const double k_self = (sx * phx * sx + sy * phy * sy) * inv4;
+      const double k_next = (nhx * phx * nlx + nhy * phy * nly) * inv4;
+      const double k_prev = (khx * phx * klx + khy * phy * kly) * inv4;
+      const bool bD = sD[lb] != 0, cD = sD[lc] != 0;
+      // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
+      c_self = rowD ? 0.0 : k_self;
+      c_next = (rowD || bD) ? 0.0 : k_next;
+      c_prev = (rowD || cD) ? 0.0 : k_prev;
+      // boundary lifting b -= K[:,D]*gD on rows outside D, src:362 (rare: rows next to a contact)
+      if (!rowD) {
+        if (bD) lift += k_next * P.gD[sNode[lb]];
+        if (cD) lift += k_prev * P.gD[sNode[lc]];
+      }
+    }
+    if (MASS) {
+      // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never
+      // eliminated (Q3)
+      const double ar30 = ar * (1.0 / 30.0);
+      const double Wa = own_g * ar30, Wb = sGW[lb] * ar30, Wc = sGW[lc] * ar30;
+      // canonical addition order of src:380-386 (W1,W2,W3 left to right)
+      const double W1 = (a == 0) ? Wa : (a == 1) ? Wc : Wb;
+      const double W2 = (a == 0) ? Wb : (a == 1) ? Wa : Wc;
+      const double W3 = (a == 0) ? Wc : (a == 1) ? Wb : Wa;
+      double m_self, m_next, m_prev;
+      if (a == 0) { m_self = 3.0 * W1 + W2 + W3; m_next = W1 + W2 + W3 * 0.5; m_prev = W1 + W2 * 0.5 + W3; }
+      else if (a == 1) { m_self = W1 + 3.0 * W2 + W3; m_next = W1 * 0.5 + W2 + W3; m_prev = W1 + W2 + W3 * 0.5; }
+      else { m_self = W1 + W2 + 3.0 * W3; m_next = W1 + W2 * 0.5 + W3; m_prev = W1 * 0.5 + W2 + W3; }
+      c_self -= m_self; c_next -= m_next; c_prev -= m_prev;
+    }
+    if (STIFF != STIFF_BASE || MASS) {
+      acc[sdiag * kAsmBlock + tid] += c_self;
+      acc[s_next * kAsmBlock + tid] += c_next;
+      acc[s_prev * kAsmBlock + tid] += c_prev;
+    }
+    // lumped edge-midpoint load: corner a takes the midpoint between a and next (src:345-350, Q1)
+    if (RHS != RHS_NONE && RHS != RHS_ZERO) {
+      double f;
+      if (RHS == RHS_DDP) {   // src:341-343
+        const double ua = (own_u + sFU[lb]) * 0.5, va = (own_v + sFV[lb]) * 0.5;
+        const double eS = own_eh * sEH[lb], eSi = own_ehi * sEHI[lb];
+        f = P.par0 * (eSi * va - eS * ua) + mid_in;
+      } else if (RHS == RHS_SRH) {  // src:517-519
+        const double ua = (own_u + sFU[lb]) * 0.5, va = (own_v + sFV[lb]) * 0.5;
+        const double eS = own_eh * sEH[lb], eSi = own_ehi * sEHI[lb];
+        f = 1.0 / (P.par0 * (eS * ua + 1.0) + P.par1 * (eSi * va + 1.0));
+      } else if (RHS == RHS_SINH) {  // registered functor, test:95
+        const double S = (own_eh + sEH[lb]) * 0.5;
+        f = mid_in + P.par0 * sinh(P.par1 * S);
+      } else {  // RHS_POLY, README:107-108
+        const double S = (own_eh + sEH[lb]) * 0.5;
+        const int deg = (int)P.par0;
+        f = P.mid_poly[deg][3 * e + a];
+        for (int dd = deg - 1; dd >= 0; --dd) f = f * S + P.mid_poly[dd][3 * e + a];
+      }
+      bsum += f * (fabs(ar) * (1.0 / 3.0));  // src:349
+    }
   };
-
-  int buf = 0;
-  prefetch(gwarp, 0);
-  for (int slice = gwarp; slice < P.nslices; slice += nwarps, buf ^= 1) {
-    prefetch(slice + nwarps, buf ^ 1);          // records of the next slice: in flight during this one
-    const int row = slice * 32 + lane;
-    const bool live = row < P.nrows;
-    const int rr = live ? row : 0;
-    const int base = P.slice_ptr[slice];
-    const int w = (P.slice_ptr[slice + 1] - base) >> 5;
-    const int ibase = P.inc_slice_ptr[slice];
-    const int iw = (P.inc_slice_ptr[slice + 1] - ibase) >> 5;
-    // own-node data (coalesced; independent of the records)
-    const double2 q_own = P.xy[rr];
-    const bool rowD = live && P.isD[rr] != 0;
-    double own_g = 0.0, own_e3 = 0.0, own_u = 0.0, own_v = 0.0, own_eh = 0.0, own_ehi = 0.0;
-    if (MASS) own_g = P.gw[rr];
-    if (STIFF == STIFF_EXPV) own_e3 = P.E3[rr];
-    if (RHS == RHS_DDP || RHS == RHS_SRH) { own_u = P.fu[rr]; own_v = P.fv[rr]; own_eh = P.EH[rr]; own_ehi = P.EHi[rr]; }
-    if (RHS == RHS_SINH || RHS == RHS_POLY) own_eh = P.EH[rr];
-    for (int k = 0; k < w; ++k) acc[k * kAsmBlock + tid] = 0.0;
-    double bsum = 0.0, lift = 0.0;
-    int sdiag = 0;
-    __pipeline_wait_prior(1);                   // this slice's records have landed (the next slice's may be pending)
-    __syncwarp();
-
-    for (int k0 = 0; k0 < iw; k0 += kAsmBatch) {
-      int4 rec[kAsmBatch];
-      IncData d[kAsmBatch];
-      // ---- level 1: issue every gather of the batch ----
 #pragma unroll
-      for (int j = 0; j < kAsmBatch; ++j) {
-        const int k = k0 + j;
-        rec[j] = make_int4(-1, 0, 0, 0);
-        if (k < iw && live) rec[j] = (k < ring_w) ? ring[(buf * ring_w + k) * 32 + lane] : P.inc[ibase + k * 32 + lane];
-        if (rec[j].x >= 0) {
-          const int e = rec[j].x >> 2, a = rec[j].x & 3, nb = rec[j].z, nc = rec[j].w;
-          d[j].qb = P.xy[nb]; d[j].qc = P.xy[nc];
-          if (STIFF == STIFF_COEF) { d[j].phx = P.phx[e]; d[j].phy = P.phy[e]; }
-          if (STIFF == STIFF_EXPV) { d[j].phx = P.phx[e]; d[j].eb = P.E3[nb]; d[j].ec = P.E3[nc]; }
-          if (STIFF != STIFF_BASE) {
-            d[j].bD = P.isD[nb] != 0; d[j].cD = P.isD[nc] != 0;
-          }
-          if (MASS) { d[j].gb = P.gw[nb]; d[j].gc = P.gw[nc]; }
-          if (RHS == RHS_DDP || RHS == RHS_SRH) { d[j].ub = P.fu[nb]; d[j].vb = P.fv[nb]; d[j].ehb = P.EH[nb]; d[j].ehib = P.EHi[nb]; }
-          if (RHS == RHS_SINH || RHS == RHS_POLY) d[j].ehb = P.EH[nb];
-          if (RHS == RHS_DDP || RHS == RHS_SINH) d[j].mid = P.mid[3 * e + a];
-        }
-      }
-      // ---- compute, in incidence order ----
+  for (int k = 0; k < kMaxIncReg; ++k)
+    if (rec[k].x >= 0) one(rec[k], cphx[k], cphy[k], cmid[k]);
+  for (int k = kMaxIncReg; k < iw; ++k) {   // rows with more than kMaxIncReg triangles (rare)
+    if (!live) break;
+    const int2 r = P.inc[ibase + k * 32 + lane];
+    if (r.x < 0) continue;
+    const int e = r.x >> 2, a = r.x & 3;
+    one(r, STIFF != STIFF_BASE ? P.phx[e] : 0.0, STIFF == STIFF_COEF ? P.phy[e] : 0.0,
+        (RHS == RHS_DDP || RHS == RHS_SINH) ? P.mid[3 * e + a] : 0.0);
+  }
+
+  // ---- write the rows (coalesced per slice) ----
+  if (!in_pat) return;
+  if (STIFF != STIFF_BASE && rowD) acc[sdiag * kAsmBlock + tid] += 1.0;  // src:279-281
+  double diag = 0.0;
+  for (int k0 = 0; k0 < w; k0 += 8) {
+    double m[8];
 #pragma unroll
-      for (int j = 0; j < kAsmBatch; ++j) {
-        if (rec[j].x < 0) continue;
-        const int e = rec[j].x >> 2, a = rec[j].x & 3;
-        const double2 q_b = d[j].qb, q_c = d[j].qc;
-        // canonical corner order (1,2,3) of the triangle: corner a is this row
-        const double2 q1 = (a == 0) ? q_own : (a == 1) ? q_c : q_b;
-        const double2 q2 = (a == 0) ? q_b : (a == 1) ? q_own : q_c;
-        const double2 q3 = (a == 0) ? q_c : (a == 1) ? q_b : q_own;
-        // edge vectors and signed area, src:243-246
-        const double ux = q2.x - q3.x, uy = q2.y - q3.y;
-        const double vx = q3.x - q1.x, vy = q3.y - q1.y;
-        const double wx = q1.x - q2.x, wy = q1.y - q2.y;
-        const double ar = (ux * vy - uy * vx) * 0.5;
-        const int s_self = rec[j].y & 255, s_next = (rec[j].y >> 8) & 255, s_prev = (rec[j].y >> 16) & 255;
-        sdiag = s_self;
-        double c_self = 0.0, c_next = 0.0, c_prev = 0.0;
-        if (STIFF != STIFF_BASE) {
-          double phx, phy;
-          if (STIFF == STIFF_COEF) { phx = d[j].phx; phy = d[j].phy; }
-          else {
-            // exp((V1+V2+V3)/3) as the product of the nodal factors in canonical corner order, src:469
-            const double eb = d[j].eb, ec = d[j].ec;
-            const double e1 = (a == 0) ? own_e3 : (a == 1) ? ec : eb;
-            const double e2 = (a == 0) ? eb : (a == 1) ? own_e3 : ec;
-            const double e3 = (a == 0) ? ec : (a == 1) ? eb : own_e3;
-            phx = d[j].phx * (e1 * e2 * e3); phy = phx;
-          }
-          const double inv4 = 1.0 / fabs(ar * 4.0);  // src:257 (one division per triangle; <= 1 ulp vs x/ar4)
-          // canonical lower-triangle entries K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar|, i>=j
-          // (src:260-266); select the row of corner a: self, next, prev.
-          const double sx = (a == 0) ? ux : (a == 1) ? vx : wx, sy = (a == 0) ? uy : (a == 1) ? vy : wy;
-          const double nhx = (a == 0) ? vx : wx, nhy = (a == 0) ? vy : wy;   // (a,next): (2,1),(3,2),(3,1)
-          const double nlx = (a == 1) ? vx : ux, nly = (a == 1) ? vy : uy;
-          const double khx = (a == 1) ? vx : wx, khy = (a == 1) ? vy : wy;   // (a,prev): (3,1),(2,1),(3,2)
-          const double klx = (a == 2) ? vx : ux, kly = (a == 2) ? vy : uy;
-          const double k_self = (sx * phx * sx + sy * phy * sy) * inv4;
-          const double k_next = (nhx * phx * nlx + nhy * phy * nly) * inv4;
-          const double k_prev = (khx * phx * klx + khy * phy * kly) * inv4;
-          // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
-          c_self = rowD ? 0.0 : k_self;
-          c_next = (rowD || d[j].bD) ? 0.0 : k_next;
-          c_prev = (rowD || d[j].cD) ? 0.0 : k_prev;
-          // boundary lifting b -= K[:,D]*gD on rows outside D, src:362
-          if (!rowD) {
-            if (d[j].bD) lift += k_next * P.gD[rec[j].z];   // rare (rows next to a contact): dependent load is fine
-            if (d[j].cD) lift += k_prev * P.gD[rec[j].w];
-          }
-        }
-        if (MASS) {
-          // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never
-          // eliminated (Q3)
-          const double ar30 = ar * (1.0 / 30.0);
-          const double Wa = own_g * ar30, Wb = d[j].gb * ar30, Wc = d[j].gc * ar30;
-          // canonical addition order of src:380-386 (W1,W2,W3 left to right)
-          const double W1 = (a == 0) ? Wa : (a == 1) ? Wc : Wb;
-          const double W2 = (a == 0) ? Wb : (a == 1) ? Wa : Wc;
-          const double W3 = (a == 0) ? Wc : (a == 1) ? Wb : Wa;
-          double m_self, m_next, m_prev;
-          if (a == 0) { m_self = 3.0 * W1 + W2 + W3; m_next = W1 + W2 + W3 * 0.5; m_prev = W1 + W2 * 0.5 + W3; }
-          else if (a == 1) { m_self = W1 + 3.0 * W2 + W3; m_next = W1 * 0.5 + W2 + W3; m_prev = W1 + W2 + W3 * 0.5; }
-          else { m_self = W1 + W2 + 3.0 * W3; m_next = W1 + W2 * 0.5 + W3; m_prev = W1 * 0.5 + W2 + W3; }
-          c_self -= m_self; c_next -= m_next; c_prev -= m_prev;
-        }
-        if (STIFF != STIFF_BASE || MASS) {
-          acc[s_self * kAsmBlock + tid] += c_self;
-          acc[s_next * kAsmBlock + tid] += c_next;
-          acc[s_prev * kAsmBlock + tid] += c_prev;
-        }
-        // lumped edge-midpoint load: corner a takes the midpoint between a and next (src:345-350, Q1)
-        if (RHS != RHS_NONE && RHS != RHS_ZERO) {
-          double f;
-          if (RHS == RHS_DDP) {   // src:341-343
-            const double ua = (own_u + d[j].ub) * 0.5, va = (own_v + d[j].vb) * 0.5;
-            const double eS = own_eh * d[j].ehb, eSi = own_ehi * d[j].ehib;
-            f = P.par0 * (eSi * va - eS * ua) + d[j].mid;
-          } else if (RHS == RHS_SRH) {  // src:517-519
-            const double ua = (own_u + d[j].ub) * 0.5, va = (own_v + d[j].vb) * 0.5;
-            const double eS = own_eh * d[j].ehb, eSi = own_ehi * d[j].ehib;
-            f = 1.0 / (P.par0 * (eS * ua + 1.0) + P.par1 * (eSi * va + 1.0));
-          } else if (RHS == RHS_SINH) {  // registered functor, test:95
-            const double S = (own_eh + d[j].ehb) * 0.5;
-            f = d[j].mid + P.par0 * sinh(P.par1 * S);
-          } else {  // RHS_POLY, README:107-108
-            const double S = (own_eh + d[j].ehb) * 0.5;
-            const int deg = (int)P.par0;
-            f = P.mid_poly[deg][3 * e + a];
-            for (int dd = deg - 1; dd >= 0; --dd) f = f * S + P.mid_poly[dd][3 * e + a];
-          }
-          bsum += f * (fabs(ar) * (1.0 / 3.0));  // src:349
-        }
-      }
+    for (int j = 0; j < 8; ++j) {   // base values again (L2-resident from the pass above), all loads in flight together
+      m[j] = 0.0;
+      if (STIFF == STIFF_BASE && k0 + j < w) m[j] = P.base_val[base + (k0 + j) * 32 + lane];
     }
-
-    // ---- write the slice (coalesced) ----
-    if (STIFF != STIFF_BASE && rowD) acc[sdiag * kAsmBlock + tid] += 1.0;  // src:279-281
-    double diag = 0.0, mv = 0.0;
-    if (STIFF == STIFF_BASE) {
-      int k = 0;
-      for (; k + 4 <= w; k += 4) {   // level 2: columns + values first, then the x gather
-        const int idx = base + k * 32 + lane;
-        const double m0 = ld_stream(P.base_val + idx), m1 = ld_stream(P.base_val + idx + 32),
-                     m2 = ld_stream(P.base_val + idx + 64), m3 = ld_stream(P.base_val + idx + 96);
-        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-        if (RESID) {
-          const int c0 = ld_stream(P.col + idx), c1 = ld_stream(P.col + idx + 32), c2 = ld_stream(P.col + idx + 64),
-                    c3 = ld_stream(P.col + idx + 96);
-          x0 = P.xvec[c0]; x1 = P.xvec[c1]; x2 = P.xvec[c2]; x3 = P.xvec[c3];
-        }
-        const double a0 = acc[k * kAsmBlock + tid] + m0, a1 = acc[(k + 1) * kAsmBlock + tid] + m1,
-                     a2 = acc[(k + 2) * kAsmBlock + tid] + m2, a3 = acc[(k + 3) * kAsmBlock + tid] + m3;
-        if (RESID) { mv += m0 * x0; mv += m1 * x1; mv += m2 * x2; mv += m3 * x3; }
-        if (sdiag == k) diag = a0; if (sdiag == k + 1) diag = a1; if (sdiag == k + 2) diag = a2; if (sdiag == k + 3) diag = a3;
-        P.out_val[idx] = live ? a0 : 0.0; P.out_val[idx + 32] = live ? a1 : 0.0;
-        P.out_val[idx + 64] = live ? a2 : 0.0; P.out_val[idx + 96] = live ? a3 : 0.0;
-      }
-      for (; k < w; ++k) {
-        const int idx = base + k * 32 + lane;
-        const double m_k = ld_stream(P.base_val + idx);
-        if (RESID) mv += m_k * P.xvec[ld_stream(P.col + idx)];
-        const double a_k = acc[k * kAsmBlock + tid] + m_k;
-        if (k == sdiag) diag = a_k;
-        P.out_val[idx] = live ? a_k : 0.0;
-      }
-    } else {
-      for (int k = 0; k < w; ++k) {
-        const double a_k = acc[k * kAsmBlock + tid];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      if (k < w) {
+        const double a_k = acc[k * kAsmBlock + tid] + m[j];
         if (k == sdiag) diag = a_k;
         P.out_val[base + k * 32 + lane] = live ? a_k : 0.0;
       }
     }
-    if (live) {
-      if (P.dinv) P.dinv[row] = 1.0 / diag;
-      if (STIFF != STIFF_BASE && P.lift_out) P.lift_out[row] = lift;
-      if (RHS != RHS_NONE) {
-        if (STIFF == STIFF_BASE) lift = P.lift_in[row];
-        double bi = bsum;
-        if (P.nodal_const) bi += P.nodal_const[row];   // Neumann loads, src:994-996
-        bi -= lift;                                    // src:362
-        if (rowD) bi = P.gD[row];                      // src:363
-        P.b[row] = bi;
-        if (RESID) P.resid[row] = mv - bi;             // src:368
-      }
-    }
-    __syncwarp();
   }
-  __pipeline_wait_prior(0);
+  if (live) {
+    if (P.dinv) P.dinv[row] = 1.0 / diag;
+    if (STIFF != STIFF_BASE && P.lift_out) P.lift_out[row] = lift;
+    if (RHS != RHS_NONE) {
+      if (STIFF == STIFF_BASE) lift = P.lift_in[row];
+      double bi = bsum;
+      if (P.nodal_const) bi += P.nodal_const[row];   // Neumann loads, src:994-996
+      bi -= lift;                                    // src:362
+      if (rowD) bi = P.gD[row];                      // src:363
+      P.b[row] = bi;
+      if (RESID) P.resid[row] = mv - bi;             // src:368
+    }
+  }
 }
 
 template <int STIFF, bool MASS, int RHS, bool RESID>
-static int launch_asm(Context* ctx, const AsmArgs& a_in) {
+static int launch_asm(Context* ctx, const AsmArgs& a) {
   const Pattern& P = ctx->pat;
-  if (P.nslices == 0) return 0;
-  AsmArgs a = a_in;
-  a.wmax = P.max_row_len;
-  const int ring_w = std::min(P.max_inc, 8);
-  const size_t smem = (size_t)P.max_row_len * kAsmBlock * sizeof(double) + (size_t)kAsmWarps * 2 * ring_w * 32 * sizeof(int4);
+  if (P.nblocks == 0) return 0;
+  constexpr bool NEED_UV = (RHS == RHS_DDP || RHS == RHS_SRH);
+  constexpr bool NEED_EH = NEED_UV || RHS == RHS_SINH || RHS == RHS_POLY;
+  const int nf = 2 + (STIFF == STIFF_EXPV ? 1 : 0) + (MASS ? 1 : 0) + (NEED_UV ? 3 : 0) + (NEED_EH ? 1 : 0);
+  size_t smem = (size_t)P.max_row_len * kAsmBlock * sizeof(double) + (size_t)P.max_bn * (nf * sizeof(double) + sizeof(int) + 1);
+  smem = (smem + 15) & ~(size_t)15;
   auto kern = k_assemble<STIFF, MASS, RHS, RESID>;
-  static thread_local int blocks_per_sm_cache = 0;
-  static thread_local size_t smem_cache = (size_t)-1;
   if (smem > 48 * 1024) DDPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (smem_cache != smem) {
-    DDPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_cache, kern, kAsmBlock, smem));
-    smem_cache = smem;
-  }
-  const int need = (P.nslices + kAsmWarps - 1) / kAsmWarps;
-  const int grid = std::max(1, std::min(need, ctx->num_sms * std::max(1, blocks_per_sm_cache)));
-  kern<<<grid, kAsmBlock, smem, ctx->stream>>>(a, ring_w);
+  kern<<<P.nblocks, kAsmBlock, smem, ctx->stream>>>(a);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
   return 0;
@@ -833,8 +864,10 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_update(int n, int par, int
 __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, int rev, int it, int max_it,
                                                              const double* __restrict__ r,
                                                              const double* __restrict__ dinv, double* __restrict__ p,
-                                                             PcgScalars* scal, const P2PDev pd) {
+                                                             PcgScalars* scal, const P2PDev pd, const PushArgs push,
+                                                             const int* __restrict__ send_idx) {
   __shared__ double sh_red[32];
+  __shared__ bool s_last_dir;
   if (scal->done) return;
   if (scal->breakdown) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { scal->done = 1; scal->iters = it; }
@@ -865,34 +898,58 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, 
     const int i = rev ? n - 1 - i0 : i0;
     p[i] = dinv[i] * r[i] + beta * p[i];
   }
+  if (pd.nranks > 1 && push.nneigh > 0) {
+    // Fused halo push: the block that finishes last (all of p is final) writes this rank's boundary values
+    // straight into the neighbours' ghost blocks over NVLink and raises their flags for the NEXT iteration.
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned t = atomicInc(&scal->cnt[2], gridDim.x - 1);
+      s_last_dir = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last_dir) {
+      __threadfence();
+      for (int j = 0; j < push.nneigh; ++j) {
+        const int cnt = push.off[j + 1] - push.off[j];
+        double* dst = push.dst[j];
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = __ldcg(p + send_idx[push.off[j] + i]);
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < push.nneigh) *(volatile unsigned long long*)push.flag[threadIdx.x] = push.tag;
+    }
+  }
 }
 
-int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it) {
+int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it, bool first) {
   const Pattern& P = ctx->pat;
   const int n = ctx->n_own;
   const int par = it & 1;
   int rc;
   const int g1 = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   const int g2 = vec_grid(ctx, n, kVecBlock);
-  // traversal directions: the three kernels of an iteration alternate (reserved[0] != 0 disables the trick)
-  const int r0 = ctx->opts.reserved[0] ? 0 : (it & 1);
-  const int r1 = ctx->opts.reserved[0] ? 0 : (r0 ^ 1);
+  // traversal directions: the three kernels of an iteration alternate (opts.no_alt_traversal disables the trick)
+  const int r0 = ctx->opts.no_alt_traversal ? 0 : (it & 1);
+  const int r1 = ctx->opts.no_alt_traversal ? 0 : (r0 ^ 1);
   P2PDev pd;
   if (ctx->p2p.enabled) {
     // Fused compute + collective over peer memory (NVLink): no NCCL call inside the PCG iteration.
     P2PHost& H = ctx->p2p;
     pd = H.dev;
     pd.tag_halo = ++H.tag; pd.tagA = ++H.tag; pd.tagB = ++H.tag;
-    if (H.push.nneigh > 0) {
-      PushArgs pa = H.push;
+    PushArgs pa = H.push;
+    if (first && pa.nneigh > 0) {   // later iterations: the previous k_pcg_direction already pushed (fused)
       pa.tag = pd.tag_halo;
       k_halo_push<<<pa.nneigh, 1024, 0, ctx->stream>>>(pa, ctx->halo.send_idx, ctx->p, ctx->scal);
       ctx->stats.kernel_launches++;
     }
+    pa.tag = pd.tagB + 1;           // = tag_halo of the next iteration
     k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
                                                     ctx->partials, ctx->scal, pd, r0);
     k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r1, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
-    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
+    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd, pa,
+                                                       ctx->halo.send_idx);
   } else {
     memset(&pd, 0, sizeof(pd));
     pd.nranks = 1;
@@ -903,7 +960,9 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
     k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r1, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
     if ((rc = allreduce_sum(ctx, &ctx->scal->sums[1], 2))) return rc;
     if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
-    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd);
+    PushArgs none;
+    memset(&none, 0, sizeof(none));
+    k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd, none, nullptr);
   }
   ctx->stats.kernel_launches += 3;
   ctx->stats.spmv_total++;
@@ -942,7 +1001,7 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
     if (ctx->scal_host->done || it >= max_it) break;
     int nrun = (int)std::min<int64_t>(chunk, max_it - it);
     for (int j = 0; j < nrun; ++j, ++it)
-      if ((rc = pcg_iteration_launch(ctx, val, dinv, x, (int)it, (int)max_it))) return rc;
+      if ((rc = pcg_iteration_launch(ctx, val, dinv, x, (int)it, (int)max_it, it == 0))) return rc;
     DDPS_CUDA(cudaGetLastError());
     chunk = std::min(chunk * 2, chunk_max);
   }

@@ -100,42 +100,53 @@ __device__ __forceinline__ int find_slot(const int* __restrict__ cols, int len, 
   return lo;
 }
 
+// keys (row block << 32 | column) of every stored entry: sorted + uniqued they give, per block of
+// kAsmRows consecutive rows, the sorted list of distinct nodes the block's rows touch
+__global__ void k_make_block_keys(const int* __restrict__ rowptr, const int* __restrict__ csrcol, int nrows,
+                                  unsigned long long* __restrict__ keys) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const unsigned long long hi = (unsigned long long)(row / kAsmRows) << 32;
+  for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) keys[k] = hi | (unsigned)csrcol[k];
+}
+
+__global__ void k_block_maxlen(const int* __restrict__ bn_ptr, int nblk, int* __restrict__ out_max) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nblk) atomicMax(out_max, bn_ptr[b + 1] - bn_ptr[b]);
+}
+
+// Incidence record (8 bytes): x = triangle*4 + corner (or -1), y = slot_next | slot_prev<<5 | l_next<<10 | l_prev<<21
+// where l_* are the positions of the two other corners in the row block's node list.
 __global__ void k_fill_incidence(const int* __restrict__ inc_ptr, const int* __restrict__ inc_vals,
                                  const int4* __restrict__ elem, const int* __restrict__ rowptr,
                                  const int* __restrict__ csrcol, int nrows, int nslices,
-                                 const int* __restrict__ inc_slice_ptr, int4* __restrict__ inc, int* __restrict__ bad) {
+                                 const int* __restrict__ inc_slice_ptr, const int* __restrict__ bn_ptr,
+                                 const int* __restrict__ bn_nodes, int2* __restrict__ inc,
+                                 unsigned char* __restrict__ diag_slot) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   int slice = row >> 5, lane = row & 31;
   if (slice >= nslices) return;
   int base = inc_slice_ptr[slice];
   int w = (inc_slice_ptr[slice + 1] - base) >> 5;
-  int beg = 0, len = 0, rbeg = 0, rlen = 0;
+  int beg = 0, len = 0, rbeg = 0, rlen = 0, lb = 0, ll = 0;
   if (row < nrows) {
     beg = inc_ptr[row]; len = inc_ptr[row + 1] - beg;
     rbeg = rowptr[row]; rlen = rowptr[row + 1] - rbeg;
+    const int blk = row / kAsmRows;
+    lb = bn_ptr[blk]; ll = bn_ptr[blk + 1] - lb;
+    diag_slot[row] = (unsigned char)find_slot(csrcol + rbeg, rlen, row);
   }
   for (int k = 0; k < w; ++k) {
-    int4 rec = make_int4(-1, 0, 0, 0);
+    int2 rec = make_int2(-1, 0);
     if (k < len) {
       int packed = inc_vals[beg + k];
       int e = packed >> 2, a = packed & 3;
       int4 el = elem[e];
       int nb = (a == 0) ? el.y : (a == 1) ? el.z : el.x;   // next corner
       int nc = (a == 0) ? el.z : (a == 1) ? el.x : el.y;   // previous corner
-      int ss = find_slot(csrcol + rbeg, rlen, row);
-      int sb = find_slot(csrcol + rbeg, rlen, nb);
-      int sc = find_slot(csrcol + rbeg, rlen, nc);
-      // ordinal (0 = first, 1 = second contributor in increasing triangle order) of this triangle's
-      // contribution to the off-diagonal entries (row,nb) and (row,nc): count earlier incident
-      // triangles that contain the same neighbour.  An edge of a valid triangulation has <= 2 triangles.
-      int ob = 0, oc = 0;
-      for (int j = 0; j < k; ++j) {
-        int4 e2 = elem[inc_vals[beg + j] >> 2];
-        if (e2.x == nb || e2.y == nb || e2.z == nb) ++ob;
-        if (e2.x == nc || e2.y == nc || e2.z == nc) ++oc;
-      }
-      if (ob > 1 || oc > 1) atomicAdd(bad, 1);
-      rec = make_int4(packed, ss | (sb << 8) | (sc << 16) | ((ob & 1) << 24) | ((oc & 1) << 25), nb, nc);
+      unsigned sb = find_slot(csrcol + rbeg, rlen, nb), sc = find_slot(csrcol + rbeg, rlen, nc);
+      unsigned l1 = find_slot(bn_nodes + lb, ll, nb), l2 = find_slot(bn_nodes + lb, ll, nc);
+      rec = make_int2(packed, (int)(sb | (sc << 5) | (l1 << 10) | (l2 << 21)));
     }
     inc[base + k * 32 + lane] = rec;
   }
@@ -163,7 +174,7 @@ inline int bits_for(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) +
 void free_pattern(Context* ctx) {
   Pattern& P = ctx->pat;
   cudaFree(P.slice_ptr); cudaFree(P.col); cudaFree(P.rowptr); cudaFree(P.csrcol);
-  cudaFree(P.inc_slice_ptr); cudaFree(P.inc);
+  cudaFree(P.inc_slice_ptr); cudaFree(P.inc); cudaFree(P.bn_ptr); cudaFree(P.bn_nodes); cudaFree(P.diag_slot);
   P = Pattern();
 }
 
@@ -275,17 +286,45 @@ int build_pattern(Context* ctx) {
       return DDPS_ERR_ARG;
     }
   }
-  DDPS_CUDA(cudaMalloc(&P.inc, std::max<size_t>(P.inc_entries, 1) * sizeof(int4)));
-  DDPS_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
-  k_fill_incidence<<<(nsl * 32 + T - 1) / T, T, 0, st>>>(inc_ptr, iv_out, ctx->elem, P.rowptr, P.csrcol, n_own, nsl,
-                                                        P.inc_slice_ptr, P.inc, d_max);
-  int nbad = 0;
-  DDPS_CUDA(cudaMemcpyAsync(&nbad, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
-  DDPS_CUDA(cudaStreamSynchronize(st));
-  if (nbad) {
-    ctx->fail(DDPS_ERR_ARG, "mesh is not a valid triangulation: an edge is shared by more than two triangles");
-    return DDPS_ERR_ARG;
+  // ---- 5. per row block (kAsmRows rows): sorted list of the distinct nodes its rows touch ----------
+  const int nblk = (n_own + kAsmRows - 1) / kAsmRows;
+  P.nblocks = nblk;
+  {
+    unsigned long long *bk_in, *bk_out;
+    DDPS_CUDA(tmp.alloc(&bk_in, (size_t)nnz)); DDPS_CUDA(tmp.alloc(&bk_out, (size_t)nnz));
+    k_make_block_keys<<<(n_own + T - 1) / T, T, 0, st>>>(P.rowptr, P.csrcol, n_own, bk_in);
+    size_t bytes = 0;
+    const int endbit = 32 + bits_for((uint64_t)nblk + 1);
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, bk_in, bk_out, nnz, 0, endbit, st);
+    void* ws; DDPS_CUDA(tmp.alloc((char**)&ws, bytes));
+    DDPS_CUDA(cub::DeviceRadixSort::SortKeys(ws, bytes, bk_in, bk_out, nnz, 0, endbit, st));
+    size_t b2 = 0;
+    cub::DeviceSelect::Unique(nullptr, b2, bk_out, bk_in, d_num, nnz, st);
+    void* ws2; DDPS_CUDA(tmp.alloc((char**)&ws2, b2));
+    DDPS_CUDA(cub::DeviceSelect::Unique(ws2, b2, bk_out, bk_in, d_num, nnz, st));
+    int nlist = 0;
+    DDPS_CUDA(cudaMemcpyAsync(&nlist, d_num, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DDPS_CUDA(cudaStreamSynchronize(st));
+    DDPS_CUDA(cudaMalloc(&P.bn_ptr, ((size_t)nblk + 1) * sizeof(int)));
+    DDPS_CUDA(cudaMalloc(&P.bn_nodes, std::max<size_t>(nlist, 1) * sizeof(int)));
+    k_lower_bound<unsigned long long><<<(nblk + 1 + T - 1) / T, T, 0, st>>>(bk_in, nlist, nblk + 1, 32, P.bn_ptr);
+    k_low32<<<(unsigned)((nlist + T - 1) / T), T, 0, st>>>(bk_in, nlist, P.bn_nodes);
+    DDPS_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+    k_block_maxlen<<<(nblk + T - 1) / T, T, 0, st>>>(P.bn_ptr, nblk, d_max);
+    DDPS_CUDA(cudaMemcpyAsync(&P.max_bn, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DDPS_CUDA(cudaStreamSynchronize(st));
+    P.bn_total = nlist;
+    if (P.max_bn > 2047 || P.max_row_len > 32) {
+      ctx->fail(DDPS_ERR_ARG, "mesh connectivity too dense for the packed incidence records (a node with > 31 neighbours "
+                              "or a 128-row block touching > 2047 nodes)");
+      return DDPS_ERR_ARG;
+    }
   }
+  DDPS_CUDA(cudaMalloc(&P.inc, std::max<size_t>(P.inc_entries, 1) * sizeof(int2)));
+  DDPS_CUDA(cudaMalloc(&P.diag_slot, std::max<size_t>(n_own, 1)));
+  k_fill_incidence<<<(nsl * 32 + T - 1) / T, T, 0, st>>>(inc_ptr, iv_out, ctx->elem, P.rowptr, P.csrcol, n_own, nsl,
+                                                        P.inc_slice_ptr, P.bn_ptr, P.bn_nodes, P.inc, P.diag_slot);
+  DDPS_CUDA(cudaStreamSynchronize(st));
   DDPS_CUDA(cudaGetLastError());
   return 0;
 }

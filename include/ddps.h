@@ -89,7 +89,10 @@ typedef struct ddps_solver_opts {
   int32_t warm_start;   /* 1: continuity solves start PCG from the previous iterate (same solution) (default 1) */
   int32_t verbose;      /* 1: print "iteration k, tolerance: c" lines like src:655,1093 */
   int32_t lin_cap_ok;   /* 1: PCG / Newton solves that hit their caps are accepted instead of failing (profiling runs only) */
-  int32_t reserved[6];
+  int32_t no_alt_traversal; /* 1: disable the alternating traversal direction of the PCG kernels (A/B timing) */
+  int32_t warm_start_v; /* OPT-IN, changes the iteration history: Vsolve starts Newton from the previous Gummel iterate
+                           instead of V=0 (src:311) -- SURVEY section 8f rank 4.  Default 0 = reference behaviour */
+  int32_t reserved[4];
 } ddps_solver_opts;
 
 typedef struct ddps_stats {

@@ -186,6 +186,18 @@ def test_solve_ddpe_matches_golden(D, case):
     assert np.allclose(st["control_history"][:3], z["control"][:3], rtol=1e-4)
 
 
+def test_warm_start_v_opt_in_reaches_same_fixed_point(D):
+    """SURVEY 8f rank 4 (opt-in, default off): Vsolve started from the previous Gummel iterate instead of V=0
+    (src:311) converges to the same fixed point with fewer Newton iterations."""
+    mesh = gpu_mesh("F1")
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], C0=1.0, U=0.3)
+    z = golden("pn_F1")
+    with _ddpe_session(D, mesh, pr, warm_start_v=1) as s:
+        V, u, v, st = s.solve_ddpe(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+    assert rel_l2(V, z["V"]) <= 1e-7 and rel_l2(u, z["u"]) <= 1e-7 and rel_l2(v, z["v"]) <= 1e-7
+    assert st["newton_total"] < int(z["newton_counts"].sum())
+
+
 def test_last_uv_operator_matches_golden(D):
     """After the full solve the last assembled operator is the v-system of the last Gummel step."""
     mesh = gpu_mesh("F2")

@@ -8,7 +8,7 @@ mesh = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
 pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
 for flag, no16 in ((1, 1), (0, 1)):
     s = D.Session(0, lin_max_it=20, lin_cap_ok=1, max_newton=2)
-    o = s._opts; o.reserved[0] = flag; o.reserved[1] = no16; s.lib.ddps_set_opts(s.h, __import__("ctypes").byref(o))
+    o = s._opts; o.no_alt_traversal = flag; s.lib.ddps_set_opts(s.h, __import__("ctypes").byref(o))
     s.set_mesh(mesh)
     s.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
     s.ddpe_begin("shockley", 1.0, 1.0, 1.0, 1e-9)
