@@ -9,9 +9,12 @@
 //    column-major inside the slice, so lane l of a warp reads entry k of row 32*s+l at
 //    slice_ptr[s] + 32*k + l  -> perfectly coalesced value/column streams for both the row-major
 //    assembly (writes) and the SpMV (reads).  Padding entries carry value 0 and column = own row.
-//  * row -> incident triangle lists ("incidence"), also slice-interleaved; each record packs the
-//    triangle id, the row's local corner (0..2) and the three pre-computed slots of that
-//    triangle's row entries, so the scatter needs no search and no atomics.
+//  * row -> incident triangle lists ("incidence"), also slice-interleaved; each 8-byte record packs
+//    the triangle id, the row's local corner (0..2), the pre-computed slots of that triangle's
+//    off-diagonal row entries and the positions of its two other corners in the row block's
+//    node list, so the scatter needs no search and no atomics.
+//  * per block of 128 rows: the sorted list of distinct nodes its rows touch, staged once per
+//    block in shared memory by the assembly kernel.
 #pragma once
 
 #include <cuda_runtime.h>
