@@ -11,8 +11,10 @@ from .mesh import Mesh, read_mesh, construct_mesh4, construct_mesh8, construct_m
 from .functors import SinhRHS, PolyRHS
 from .api import (Session, DDPSError, solve_ddpe, solve_semlin_poisson, aquire_boundary, dirichlet_nodes,
                   neumann_edges)
+from .postprocess import aquire_boundary_separate_edges, get_gradients, calculate_current, current_from_fields
 from . import problems
 
 __all__ = ["Mesh", "read_mesh", "construct_mesh4", "construct_mesh8", "construct_mesh", "structured_mesh",
            "solve_ddpe", "solve_semlin_poisson", "aquire_boundary", "SinhRHS", "PolyRHS", "Session", "DDPSError",
-           "problems", "dirichlet_nodes", "neumann_edges"]
+           "problems", "dirichlet_nodes", "neumann_edges", "aquire_boundary_separate_edges", "get_gradients",
+           "calculate_current", "current_from_fields"]

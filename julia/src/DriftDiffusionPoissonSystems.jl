@@ -17,7 +17,7 @@ module DriftDiffusionPoissonSystems
 using DelimitedFiles
 
 export Mesh, read_mesh, construct_mesh, construct_mesh4, construct_mesh8, solve_ddpe, solve_semlin_poisson,
-       aquire_boundary, SinhRHS, PolyRHS, derivative
+       aquire_boundary, SinhRHS, PolyRHS, derivative, calculate_current, aquire_boundary_separate_edges, get_gradients
 
 const LIB = get(ENV, "DDPS_B200_LIB", joinpath(@__DIR__, "..", "..", "driftdiffusionpoissonsystems.jl_b200", "libddps_b200.so"))
 
@@ -193,6 +193,57 @@ function solve_semlin_poisson(mesh, A::Array, bddata::Array, f, g, tol = 10.0^(-
         chk(h, ccall((:ddps_solve_semlin, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Ref{Stats}), h, tol, V, st))
     end
     V
+end
+
+# ---------------------------------------------------------------- terminal current (host post-processing)
+function aquire_boundary_separate_edges(mesh::Mesh, Endpoints::Array, bddata::Array)
+    n1, n2, gD, n = aquire_boundary(mesh, bddata)
+    _, diri = split_bddata(bddata)
+    idx = reduce(vcat, [findall(==(bddata[1, j]), mesh.edges[4, :]) for j in diri]; init = Int[])
+    X(e, k) = mesh.nodes[1, mesh.edges[k, e]]; Y(e, k) = mesh.nodes[2, mesh.edges[k, e]]
+    xpar = [e for e in idx if isapprox(Y(e, 1) - Y(e, 2), 0)]
+    ypar = [e for e in idx if isapprox(X(e, 1) - X(e, 2), 0)]
+    length(xpar) + length(ypar) == length(idx) || error("Dirichlet edges must be parallel to the axes")
+    left = [e for e in ypar if isapprox(Endpoints[1, 1], X(e, 1))]; right = [e for e in ypar if isapprox(Endpoints[3, 1], X(e, 1))]
+    bottom = [e for e in xpar if isapprox(Endpoints[1, 2], Y(e, 1))]; top = [e for e in xpar if isapprox(Endpoints[3, 2], Y(e, 1))]
+    length(left) + length(right) + length(bottom) + length(top) == length(idx) || error("Dirichlet edges must lie on the rectangle")
+    n1, n2, gD, n, mesh.edges[:, left], mesh.edges[:, bottom], mesh.edges[:, right], mesh.edges[:, top]
+end
+
+function get_gradients(uu::Array{Float64,2}, vv::Array{Float64,2}, ww::Array{Float64,2}, ar::Array{Float64,1})
+    [0.5 .* uu[2, :] ./ ar 0.5 .* vv[2, :] ./ ar 0.5 .* ww[2, :] ./ ar], [-0.5 .* uu[1, :] ./ ar -0.5 .* vv[1, :] ./ ar -0.5 .* ww[1, :] ./ ar]
+end
+
+function calculate_current(mesh::Mesh, rec_mode::Symbol, Endpoints::Array, Vbddata::Array, ubddata::Array, vbddata::Array,
+                           lambda::Function, delta::Float64, tau_p::Float64, tau_n::Float64, mu_p::Function, mu_n::Function,
+                           C::Function, tol = 10.0^(-9); kwargs...)
+    V, u, v = solve_ddpe(mesh, rec_mode, Vbddata, ubddata, vbddata, lambda, delta, tau_p, tau_n, mu_p, mu_n, C, tol; kwargs...)
+    _, _, _, _, eL, eB, eR, eT = aquire_boundary_separate_edges(mesh, Endpoints, Vbddata)
+    q1, q2, q3 = corner(mesh, 1), corner(mesh, 2), corner(mesh, 3)
+    uu, vv, ww = q2 .- q3, q3 .- q1, q1 .- q2
+    ar = (uu[1, :] .* vv[2, :] .- uu[2, :] .* vv[1, :]) ./ 2
+    gradx, grady = get_gradients(uu, vv, ww, ar)
+    first = Dict{Tuple{Int64,Int64},Int}()                      # edge -> first triangle (replaces the O(ne*nme) findfirst)
+    for e in size(mesh.elements, 2):-1:1, (a, b) in ((1, 2), (2, 3), (1, 3))
+        p, q = minmax(mesh.elements[a, e], mesh.elements[b, e]); first[(p, q)] = e
+    end
+    gl = (-sqrt(3 / 5), 0.0, sqrt(3 / 5)); wt = (5 / 9, 8 / 9, 5 / 9)
+    I = 0.0
+    for (edges, fixed, alongx, g, sgn) in ((eL, Endpoints[1, 1], false, gradx, -1.0), (eB, Endpoints[1, 2], true, grady, -1.0),
+                                           (eR, Endpoints[3, 1], false, gradx, 1.0), (eT, Endpoints[3, 2], true, grady, 1.0))
+        for i in 1:size(edges, 2)
+            Vb = Vbddata[3, edges[4, i]]
+            c = mesh.nodes[alongx ? 1 : 2, edges[1:2, i]]; a, b = minimum(c), maximum(c)
+            ind = first[minmax(edges[1, i], edges[2, i])]
+            gu = sum(u[mesh.elements[1:3, ind]] .* g[ind, :]); gv = sum(v[mesh.elements[1:3, ind]] .* g[ind, :])
+            for (t, w) in zip(gl, wt)
+                s = (t + 1) * (b - a) / 2 + a
+                x, y = alongx ? (s, fixed) : (fixed, s)
+                I += sgn * w * (mu_n(x, y) * exp(Vb(x, y)) * gu - mu_p(x, y) * exp(-Vb(x, y)) * gv) * (b - a) / 2
+            end
+        end
+    end
+    I, V, u, v
 end
 
 # ---------------------------------------------------------------- mesh I/O (host only)

@@ -598,6 +598,71 @@ def semlin_newton_system(mesh, A, bddata, f, g, V):
 
 
 # --------------------------------------------------------------------------------------------
+# calculate_current (src:662-887) -- literal restatement incl. the O(ne*nme) findfirst
+# --------------------------------------------------------------------------------------------
+def _jl_isapprox(a, b):
+    return abs(a - b) <= np.sqrt(np.finfo(float).eps) * max(abs(a), abs(b))
+
+
+def aquire_boundary_separate_edges(mesh, Endpoints, bddata):
+    """src:662-727."""
+    E = np.asarray(Endpoints, dtype=float)
+    n1, n2, gD, n = aquire_boundary(mesh, bddata)
+    tags, fcts, _, diri = _bd_columns(bddata)
+    idx = []
+    for j in diri:
+        idx.extend(np.nonzero(mesh.edges[3, :] == tags[j])[0].tolist())          # src:690-691
+    X, Y = mesh.nodes
+    ed = mesh.edges
+    xpar = [k for k, e in enumerate(idx) if _jl_isapprox(Y[ed[0, e] - 1] - Y[ed[1, e] - 1], 0.0)]   # src:701
+    ypar = [k for k, e in enumerate(idx) if _jl_isapprox(X[ed[0, e] - 1] - X[ed[1, e] - 1], 0.0)]   # src:702
+    assert len(xpar) + len(ypar) == len(idx)
+    left = [k for k in ypar if _jl_isapprox(E[0, 0], X[ed[0, idx[k]] - 1])]                         # src:708
+    bottom = [k for k in xpar if _jl_isapprox(E[0, 1], Y[ed[0, idx[k]] - 1])]
+    right = [k for k in ypar if _jl_isapprox(E[2, 0], X[ed[0, idx[k]] - 1])]
+    top = [k for k in xpar if _jl_isapprox(E[2, 1], Y[ed[0, idx[k]] - 1])]
+    assert len(left) + len(bottom) + len(right) + len(top) == len(idx)
+    pick = lambda ks: ed[:, [idx[k] for k in ks]]
+    return n1, n2, gD, n, pick(left), pick(bottom), pick(right), pick(top)
+
+
+def calculate_current(mesh, rec_mode, Endpoints, Vbddata, ubddata, vbddata, lam, delta, tau_p, tau_n, mu_p, mu_n, C,
+                      tol=1e-9, linsolve="sparse", fields=None):
+    """src:753-887.  ``fields=(V,u,v)`` skips the Gummel loop (used to test the flux integrals alone)."""
+    E = np.asarray(Endpoints, dtype=float)
+    _, _, gD, n, eL, eB, eR, eT = aquire_boundary_separate_edges(mesh, E, Vbddata)
+    if fields is None:
+        V, u, v = solve_ddpe(mesh, rec_mode, Vbddata, ubddata, vbddata, lam, delta, tau_p, tau_n, mu_p, mu_n, C, tol, linsolve)
+    else:
+        V, u, v = fields
+    a1, a2, a3, uu, vv, ww, ar = _geometry(mesh)
+    gradx = np.stack([.5 * uu[1] / ar, .5 * vv[1] / ar, .5 * ww[1] / ar], axis=1)        # src:737-740
+    grady = np.stack([-.5 * uu[0] / ar, -.5 * vv[0] / ar, -.5 * ww[0] / ar], axis=1)     # src:743-746
+    gl_nodes = np.array([-np.sqrt(3 / 5), 0.0, np.sqrt(3 / 5)])                          # gausslegendre(3), src:792
+    gl_w = np.array([5 / 9, 8 / 9, 5 / 9])
+    tri = mesh.elements[0:3, :]
+    I = 0.0
+    for edges, fixed, along_x, gtab, sign in ((eL, E[0, 0], False, gradx, -1.0), (eB, E[0, 1], True, grady, -1.0),
+                                              (eR, E[2, 0], False, gradx, 1.0), (eT, E[2, 1], True, grady, 1.0)):
+        for i in range(edges.shape[1]):
+            Vb = Vbddata[2][int(edges[3, i]) - 1]                                        # src:801
+            c = mesh.nodes[0 if along_x else 1, edges[0:2, i] - 1]
+            a, b = c.min(), c.max()
+            ind = next(x for x in range(tri.shape[1]) if set(edges[0:2, i]) <= set(tri[:, x]))   # src:807
+            gradu = np.dot(u[tri[:, ind] - 1], gtab[ind])
+            gradv = np.dot(v[tri[:, ind] - 1], gtab[ind])
+            Ip = np.zeros(3)
+            In = np.zeros(3)
+            for q, t in enumerate(gl_nodes):
+                s = (t + 1) * (b - a) / 2 + a                                            # src:798
+                x, y = (s, fixed) if along_x else (fixed, s)
+                Ip[q] = float(mu_n(x, y)) * np.exp(float(Vb(x, y))) * gradu * (b - a) / 2      # src:802,814
+                In[q] = -float(mu_p(x, y)) * np.exp(-float(Vb(x, y))) * gradv * (b - a) / 2   # src:803,815
+            I += sign * np.dot(gl_w, Ip + In)                                            # src:817,839,861,883
+    return I, V, u, v
+
+
+# --------------------------------------------------------------------------------------------
 # Timing helper for bench.py's cpu_baseline leg
 # --------------------------------------------------------------------------------------------
 def timed_gummel_iterations(mesh, problem: dict, iters: int, linsolve="sparse"):

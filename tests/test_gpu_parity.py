@@ -318,3 +318,15 @@ def test_pcg_breakdown_is_reported(D):
         with pytest.raises(D.DDPSError) as ei:
             s.debug_pcg(np.ones(mesh.nq), rtol=1e-10, max_it=500)
         assert ei.value.code in (-5, -4)
+
+
+def test_calculate_current_reference_signature(D, O):
+    """calculate_current (src:753-887): GPU Gummel loop + host flux integrals vs the oracle."""
+    mesh, om = gpu_mesh("F1"), oracle_mesh("F1")
+    E = np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0]])
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], C0=1.0, U=0.3)
+    I, V, u, v = D.calculate_current(mesh, pr["rec_mode"], E, *[pr[k] for k in KEYS[1:]], verbose=False)
+    z = golden("pn_F1")
+    Iref = O.calculate_current(om, pr["rec_mode"], E, *[pr[k] for k in KEYS[1:]], fields=(z["V"], z["u"], z["v"]))[0]
+    assert rel_l2(u, z["u"]) <= FIELD_TOL
+    assert abs(I - Iref) <= 1e-7 * abs(Iref)

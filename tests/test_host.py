@@ -165,3 +165,29 @@ def test_partition_rcb(D):
     owner = np.zeros(mesh.nq, dtype=np.int32)
     lib.ddps_partition_nodes(_lib.dptr(nodes), mesh.nq, 2, owner.ctypes.data_as(_lib.c_int32_p))
     assert mesh.nodes[0, owner == 0].max() <= mesh.nodes[0, owner == 1].min() + 1e-12
+
+
+def test_terminal_current_postprocessing_matches_oracle(D, O):
+    """aquire_boundary_separate_edges / get_gradients / the flux integrals of calculate_current
+    (src:662-887) on the host, against the literal oracle restatement (same fields in, same current out)."""
+    mesh, om = gpu_mesh("F2"), oracle_mesh("F2")
+    E = np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0]])
+    pr = D.problems.pn_junction([3, 7], list(range(1, 9)), C0=1.0, U=0.3)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pn_F2.npz"))
+    got = D.aquire_boundary_separate_edges(mesh, E, pr["Vbddata"])
+    ref = O.aquire_boundary_separate_edges(om, E, pr["Vbddata"])
+    for a, b in zip(got, ref):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    assert got[4].shape[1] == 4 and got[6].shape[1] == 4 and got[5].shape[1] == 0      # contacts: 4 edges left, 4 right
+    I = D.current_from_fields(mesh, E, pr["Vbddata"], pr["mu_p"], pr["mu_n"], z["u"], z["v"])
+    Iref = O.calculate_current(om, pr["rec_mode"], E, pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["delta"],
+                               pr["tau_p"], pr["tau_n"], pr["mu_p"], pr["mu_n"], pr["C"], pr["tol"],
+                               fields=(z["V"], z["u"], z["v"]))[0]
+    assert abs(I - Iref) <= 1e-12 * max(1.0, abs(Iref)) and I != 0.0
+    # all-Dirichlet problem: every side contributes
+    pr1 = D.problems.ddpe1()
+    z1 = np.load(os.path.join(ROOT, "tests", "golden", "ddpe1_F2.npz"))
+    I1 = D.current_from_fields(mesh, E, pr1["Vbddata"], pr1["mu_p"], pr1["mu_n"], z1["u"], z1["v"])
+    I1ref = O.calculate_current(om, "zero", E, pr1["Vbddata"], pr1["ubddata"], pr1["vbddata"], pr1["lam"], 1.0, 0.0, 0.0,
+                                pr1["mu_p"], pr1["mu_n"], pr1["C"], 1e-12, fields=(z1["V"], z1["u"], z1["v"]))[0]
+    assert abs(I1 - I1ref) <= 1e-11 * max(1.0, abs(I1ref))
