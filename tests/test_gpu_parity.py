@@ -330,3 +330,49 @@ def test_calculate_current_reference_signature(D, O):
     Iref = O.calculate_current(om, pr["rec_mode"], E, *[pr[k] for k in KEYS[1:]], fields=(z["V"], z["u"], z["v"]))[0]
     assert rel_l2(u, z["u"]) <= FIELD_TOL
     assert abs(I - Iref) <= 1e-7 * abs(Iref)
+
+
+def test_full_size_16M_properties(D):
+    """BASELINE.json config 4 at FULL size (4096x2048 cells, 16,777,216 triangles) through size-independent
+    properties (the oracle cannot run at this size): symmetry of the assembled operator, constants in the null
+    space of the eliminated stiffness away from the contacts, identity Dirichlet rows, bitwise-reproducible
+    assembly, a PCG solve verified by an independent true-residual SpMV, and exact Dirichlet values of V after a
+    Gummel step."""
+    nx, ny = 4096, 2048
+    mesh = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
+    assert mesh.nme == 16777216 and mesh.nq == 8394753
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
+    rng = np.random.default_rng(4)
+    V, u, v = smooth_fields(mesh, 13)
+    with _ddpe_session(D, mesh, pr) as s:
+        n0 = s._ddpe_n - 1
+        isD = np.zeros(mesh.nq, bool)
+        isD[n0] = True
+        s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)
+        x, y = rng.standard_normal(mesh.nq), rng.standard_normal(mesh.nq)
+        Ax, Ay = s.debug_spmv(1, x), s.debug_spmv(1, y)
+        assert abs(y @ Ax - x @ Ay) <= 1e-10 * abs(y @ Ax)                      # symmetric operator (M - J0)
+        b1 = s.get_vector(0).copy()
+        s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)                   # assemble again: bitwise identical
+        assert np.array_equal(s.debug_spmv(1, x), Ax) and np.array_equal(s.get_vector(0), b1)
+        # a linear solve, checked with an independent SpMV
+        xs, it, rr = s.debug_pcg(b1, rtol=1e-9, max_it=40000)
+        assert rr <= 1e-9 and it > 100
+        res = b1 - s.debug_spmv(1, xs)
+        assert np.linalg.norm(res) <= 5e-9 * np.linalg.norm(b1)
+        # :zero mode = eliminated stiffness: A*1 vanishes on rows that do not touch a contact; Dirichlet rows are identity
+        s.debug_assemble_uv(1, "zero", 1.0, 1.0, V, u, v)
+        r = s.debug_spmv(1, np.ones(mesh.nq))
+        b = s.get_vector(0)
+        far = ~isD & (b == 0)
+        assert far.sum() > 0.99 * mesh.nq
+        assert np.max(np.abs(r[far])) <= 1e-9
+        assert np.all(r[isD] == 1.0)
+        # one full Gummel step (~23,000 PCG iterations): the Newton stop test max|MV*V-b| <= tol (src:368) bounds the
+        # Dirichlet error of V by tol because the Dirichlet rows of MV are identity rows (src:279-284,363)
+        s.ddpe_begin("shockley", 1.0, 1.0, 1.0, 1e-9)
+        s.ddpe_step(1)
+        Vg, ug, vg = s.ddpe_fetch()
+        gV = pr["Vbddata"][2][1](mesh.nodes[0, n0], mesh.nodes[1, n0])
+        assert np.allclose(Vg[n0], gV, rtol=0, atol=1e-9)
+        assert np.all(np.isfinite(ug)) and np.all(np.isfinite(vg))
