@@ -39,7 +39,8 @@ void free_mesh(Context* ctx) {
   dev_free(ctx->isD);
   for (int f = 0; f < 4; ++f) { dev_free(ctx->gD[f]); ctx->have_D[f] = false; }
   for (int s = 0; s < 64; ++s) { dev_free(ctx->coeff[s]); ctx->coeff_len[s] = 0; }
-  dev_free(ctx->val_base); dev_free(ctx->val_op); dev_free(ctx->lift);
+  dev_free(ctx->val_base); dev_free(ctx->val_op); dev_free(ctx->lift); dev_free(ctx->val_s); dev_free(ctx->sc); dev_free(ctx->bs);
+  ctx->last_val = nullptr; ctx->last_dinv = nullptr;
   dev_free(ctx->V); dev_free(ctx->U); dev_free(ctx->W); dev_free(ctx->V0); dev_free(ctx->U0); dev_free(ctx->W0);
   dev_free(ctx->Unew); dev_free(ctx->EH); dev_free(ctx->EHi); dev_free(ctx->E3); dev_free(ctx->gw);
   dev_free(ctx->b); dev_free(ctx->resid); dev_free(ctx->dinv); dev_free(ctx->x); dev_free(ctx->r); dev_free(ctx->q);
@@ -311,7 +312,7 @@ int vsolve(Context* ctx) {
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
     // Newton correction: the linear residual only has to be below the Newton tolerance (so that, like the
     // reference's direct solve, a linear problem converges in one step); newton_eta is a relative floor.
-    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * ctx->tol,
+    rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * ctx->tol,
                    ctx->opts.lin_max_it, nullptr, nullptr);
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
@@ -332,7 +333,7 @@ int uvsolve(Context* ctx, int which) {
   ta.stop();
   double* field = (which == DDPS_FIELD_U) ? ctx->U : ctx->W;
   EventTimer tp(ctx, ctx->ev2, ctx->ev3);
-  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, field, ctx->opts.warm_start != 0, ctx->opts.lin_rtol, 0.0,
+  rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->b, field, ctx->opts.warm_start != 0, ctx->opts.lin_rtol, 0.0,
                  ctx->opts.lin_max_it, nullptr, nullptr);                                     // src:588
   tp.stop();
   ctx->stats.t_pcg_ms += tp.ms();
@@ -566,6 +567,11 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
   }
   if ((rc = dev_alloc(ctx, &ctx->val_base, ne))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->val_op, ne))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->val_s, ne))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->sc, nl))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->bs, no))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(ctx->val_s, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
+  DDPS_CUDA(cudaMemsetAsync(ctx->sc, 0, std::max<size_t>(nl, 1) * sizeof(double), ctx->stream));
   DDPS_CUDA(cudaMemsetAsync(ctx->val_base, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
   DDPS_CUDA(cudaMemsetAsync(ctx->val_op, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
   int asm_blocks = (ctx->pat.nslices * 32 + kAsmBlock - 1) / kAsmBlock;
@@ -789,7 +795,7 @@ int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats
     if (!(res > tol)) break;                                                                  // src:1040
     if (count >= cap) { ctx->fail(DDPS_ERR_NOCONV, "semlin: Newton iteration cap reached"); rc = DDPS_ERR_NOCONV; break; }
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
-    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
+    rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
                    ctx->opts.lin_max_it, nullptr, nullptr);                                   // src:1063
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
@@ -937,7 +943,7 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
   if ((rc = require_mesh(ctx))) return rc;
   if (ctx->nranks != 1) { ctx->fail(DDPS_ERR_STATE, "debug exports are single-GPU"); return DDPS_ERR_STATE; }
   if ((rc = upload(ctx, ctx->b, rhs, (size_t)ctx->n_own)) || (rc = upload(ctx, ctx->x, x, (size_t)ctx->n_own))) return rc;
-  rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, true, rtol, 0.0, max_it, iters, relres);
+  rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, true, rtol, 0.0, max_it, iters, relres);
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   DDPS_CUDA(cudaMemcpy(x, ctx->x, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost));
   return rc;
@@ -954,12 +960,12 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
   double bytes = 0;
   auto run = [&](int it) -> int {
     switch (kernel) {
-      case 0: return launch_spmv(ctx, ctx->val_op, ctx->p, ctx->q);
+      case 0: return launch_spmv(ctx, ctx->last_val ? ctx->last_val : ctx->val_op, ctx->p, ctx->q);
       case 1: return assemble_uv(ctx, DDPS_FIELD_U, ctx->rec_mode, ctx->tau_p, ctx->tau_n, ctx->V, ctx->U0, ctx->W0);
-      case 2: return pcg_iteration_launch(ctx, ctx->val_op, ctx->dinv, ctx->x, it, 1 << 30, it == 1);
+      case 2: return pcg_iteration_launch(ctx, ctx->last_val ? ctx->last_val : ctx->val_op, ctx->last_val ? ctx->last_dinv : ctx->dinv, ctx->x, it, 1 << 30, it == 1);
       case 3: return assemble_newton(ctx, false, ctx->delta, ctx->V, ctx->U0, ctx->W0);
       case 4: return assemble_base(ctx, ctx->base_is_semlin);
-      case 5: return launch_spmv_dot(ctx, ctx->val_op, ctx->p, ctx->q);
+      case 5: return launch_spmv_dot(ctx, ctx->last_val ? ctx->last_val : ctx->val_op, ctx->p, ctx->q);
     }
     ctx->fail(DDPS_ERR_ARG, "unknown kernel id");
     return DDPS_ERR_ARG;
@@ -978,7 +984,8 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
   if (kernel == 2) {
     // fresh PCG state on the last assembled system; rtol 0 keeps the done flag down
     if ((rc = halo_exchange(ctx, ctx->p))) return rc;
-    rc = pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, false, 0.0, -1.0, 1, nullptr, nullptr);
+    rc = pcg_solve(ctx, ctx->last_val ? ctx->last_val : ctx->val_op, ctx->last_val ? ctx->last_dinv : ctx->dinv,
+                   ctx->last_val == ctx->val_s ? ctx->bs : ctx->b, ctx->x, false, 0.0, -1.0, 1, nullptr, nullptr);
     if (rc != DDPS_ERR_NOCONV && rc != 0) return rc;
     DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
   }

@@ -180,6 +180,11 @@ struct Context {
   // matrices (values in SELL order)
   double* val_base = nullptr;  // MV / semlin M
   double* val_op = nullptr;    // operator handed to the solver
+  double* val_s = nullptr;     // symmetrically Jacobi-scaled copy D^-1/2 A D^-1/2 the CG actually iterates on
+  double* sc = nullptr;        // [n_loc] scale factors D^-1/2
+  double* bs = nullptr;        // [n_own] scaled right-hand side
+  const double* last_val = nullptr;   // matrix / inverse diagonal of the last solve (kernel timing)
+  const double* last_dinv = nullptr;
   double* lift = nullptr;      // [n_own] K[:,D]*gD of the base stiffness
   bool base_ready = false;
   bool base_is_semlin = false;
@@ -281,6 +286,8 @@ int launch_max_abs(Context* ctx, const double* a, int n, double* host_out);
 int fetch_resid_norm(Context* ctx, double* host_out);  // norm_inf written by the last RESID assembly
 int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it, bool first);
 // Jacobi-PCG: solve val*x = rhs; x holds the initial guess if x0_nonzero (else it is zeroed).
+int solve_system(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
+                 double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);
 int pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
               double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);
 

@@ -788,7 +788,7 @@ __global__ void k_pcg_init(int n, const double* __restrict__ rhs, const double* 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double bi = rhs[i];
     const double ri = HAVE_Q ? bi - q[i] : bi;
-    const double zi = dinv[i] * ri;
+    const double zi = dinv ? dinv[i] * ri : ri;   // dinv == nullptr: symmetrically pre-scaled system, M = I
     r[i] = ri;
     p[i] = zi;
     s_rz += ri * zi; s_rr += ri * ri; s_bb += bi * bi;
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_update(int n, int par, int
     const double ri = r[i] - alpha * qi;
     x[i] = xi;
     r[i] = ri;
-    s_rz += ri * (dinv[i] * ri);
+    s_rz += dinv ? ri * (dinv[i] * ri) : ri * ri;
     s_rr += ri * ri;
     s_max = fmax(s_max, fabs(ri));
   }
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, 
   const double beta = rz_new / rz_old;
   for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const int i = rev ? n - 1 - i0 : i0;
-    p[i] = dinv[i] * r[i] + beta * p[i];
+    p[i] = (dinv ? dinv[i] * r[i] : r[i]) + beta * p[i];
   }
   if (pd.nranks > 1 && push.nneigh > 0) {
     // Fused halo push: the block that finishes last (all of p is final) writes this rank's boundary values
@@ -920,6 +920,83 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, 
       if (threadIdx.x < push.nneigh) *(volatile unsigned long long*)push.flag[threadIdx.x] = push.tag;
     }
   }
+}
+
+
+// ---- symmetric Jacobi scaling: A' = S A S, S = D^-1/2.  CG on A' is Jacobi-PCG on A (same Krylov iterates) without
+// the two per-iteration reads of D^-1: 11 instead of 13 vector passes per iteration.
+__global__ void k_make_scale(int n, const double* __restrict__ dinv, double* __restrict__ sc, double* partials,
+                             PcgScalars* scal) {
+  __shared__ double sh_red[32];
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double d = dinv[i];
+    sc[i] = sqrt(d);
+    m = fmax(m, 1.0 / d);   // largest diagonal entry -> smallest scale factor
+  }
+  double v[1] = {m}, tot[1];
+  if (grid_reduce<1, true>(v, partials, &scal->cnt[3], sh_red, tot)) {
+    if (threadIdx.x == 0) scal->norm_inf = tot[0];
+  }
+}
+
+__global__ void __launch_bounds__(kVecBlock) k_scale_matrix(int nslices, const int* __restrict__ slice_ptr,
+                                                            const int* __restrict__ col, const double* __restrict__ val,
+                                                            const double* __restrict__ sc, int nrows, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int slice = gw; slice < nslices; slice += nw) {
+    const int base = slice_ptr[slice];
+    const int w = (slice_ptr[slice + 1] - base) >> 5;
+    const int row = slice * 32 + lane;
+    const double sr = row < nrows ? sc[row] : 0.0;
+    for (int k = 0; k < w; ++k) {
+      const int idx = base + k * 32 + lane;
+      out[idx] = sr * ld_stream(val + idx) * __ldg(sc + ld_stream(col + idx));
+    }
+  }
+}
+
+__global__ void k_vec_mul(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] * b[i];
+}
+__global__ void k_vec_div(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] / b[i];
+}
+
+int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it, bool first);
+
+// Solve val*x = rhs (val, dinv = the last assembled operator and its inverse diagonal).
+int solve_system(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
+                 double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out) {
+  const int n = ctx->n_own;
+  ctx->last_val = val; ctx->last_dinv = dinv;
+  if (ctx->opts.no_sym_scaling || n == 0)
+    return pcg_solve(ctx, val, dinv, rhs, x, x0_nonzero, rtol, atol_inf, max_it, iters_out, relres_out);
+  const Pattern& P = ctx->pat;
+  int rc;
+  const int g = vec_grid(ctx, n, kVecBlock);
+  k_make_scale<<<g, kVecBlock, 0, ctx->stream>>>(n, dinv, ctx->sc, ctx->partials, ctx->scal);
+  if ((rc = halo_exchange(ctx, ctx->sc))) return rc;
+  k_scale_matrix<<<vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock), kVecBlock, 0, ctx->stream>>>(
+      P.nslices, P.slice_ptr, P.col, val, ctx->sc, P.nrows, ctx->val_s);
+  k_vec_mul<<<g, kVecBlock, 0, ctx->stream>>>(n, rhs, ctx->sc, ctx->bs);
+  if (x0_nonzero) k_vec_div<<<g, kVecBlock, 0, ctx->stream>>>(n, x, ctx->sc, x);
+  ctx->stats.kernel_launches += 3 + (x0_nonzero ? 1 : 0);
+  double maxdiag = 0.0;
+  if ((rc = allreduce_max(ctx, &ctx->scal->norm_inf, 1))) return rc;
+  DDPS_CUDA(cudaMemcpyAsync(&ctx->scal_host->norm_inf, &ctx->scal->norm_inf, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  maxdiag = ctx->scal_host->norm_inf;
+  // |r_i| = |r'_i| / s_i <= max|r'| * sqrt(max diag): scale the absolute threshold so that it still bounds the
+  // UNscaled residual (conservative)
+  const double atol_s = (atol_inf > 0 && maxdiag > 0) ? atol_inf / sqrt(maxdiag) : atol_inf;
+  ctx->last_val = ctx->val_s; ctx->last_dinv = nullptr;
+  rc = pcg_solve(ctx, ctx->val_s, nullptr, ctx->bs, x, x0_nonzero, rtol, atol_s, max_it, iters_out, relres_out);
+  k_vec_mul<<<g, kVecBlock, 0, ctx->stream>>>(n, x, ctx->sc, x);
+  ctx->stats.kernel_launches++;
+  DDPS_CUDA(cudaGetLastError());
+  return rc;
 }
 
 int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, double* x, int it, int max_it, bool first) {

@@ -92,7 +92,8 @@ typedef struct ddps_solver_opts {
   int32_t no_alt_traversal; /* 1: disable the alternating traversal direction of the PCG kernels (A/B timing) */
   int32_t warm_start_v; /* OPT-IN, changes the iteration history: Vsolve starts Newton from the previous Gummel iterate
                            instead of V=0 (src:311) -- SURVEY section 8f rank 4.  Default 0 = reference behaviour */
-  int32_t reserved[4];
+  int32_t no_sym_scaling; /* 1: classic Jacobi-PCG with explicit D^-1 reads instead of CG on D^-1/2 A D^-1/2 (same iterates) */
+  int32_t reserved[3];
 } ddps_solver_opts;
 
 typedef struct ddps_stats {
