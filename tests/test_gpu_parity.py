@@ -383,3 +383,77 @@ def test_full_size_16M_properties(D):
         gV = pr["Vbddata"][2][1](mesh.nodes[0, n0], mesh.nodes[1, n0])
         assert np.allclose(Vg[n0], gV, rtol=0, atol=1e-9)
         assert np.all(np.isfinite(ug)) and np.all(np.isfinite(vg))
+
+
+# ---------------------------------------------------------------- edge cases of the domain
+def _flip_some(mesh, D, seed=0, frac=0.3):
+    """Reverse the orientation of a random subset of triangles (signed area < 0 there: Q2 -- the reference uses
+    |ar| in the stiffness and the load but the SIGNED area in the mass weights, src:257,349 vs 375)."""
+    rng = np.random.default_rng(seed)
+    el = mesh.elements.copy()
+    pick = rng.random(el.shape[1]) < frac
+    el[1, pick], el[2, pick] = mesh.elements[2, pick], mesh.elements[1, pick]
+    return D.Mesh(mesh.nodes, mesh.edges, el), int(pick.sum())
+
+
+def test_clockwise_triangles_signed_area_quirk(D, O):
+    mesh, nflip = _flip_some(gpu_mesh("F1"), D, seed=2)
+    om = oracle_mesh(mesh)
+    pr = four_tag(D.problems.ddpe2())
+    V, u0, v0 = smooth_fields(mesh, 21)
+    _, _, gD, n = O.aquire_boundary(om, pr["Vbddata"])
+    A, b = O.uv_system(om, "shockley", V, pr["ubddata"], 0.8, 1.3, pr["mu_p"], n, u0, v0)
+    MV, bdMV, ar = O.MV_assemble(om, n, gD, pr["lam"])[:3]
+    An, bn, Fn = O.poisson_newton_system(om, V, u0, v0, 1.1, MV, bdMV, ar, n, gD, pr["C"])
+    with _ddpe_session(D, mesh, pr) as s:
+        assert s.stats()["n_negative_area"] == nflip > 100
+        s.debug_assemble_uv(1, "shockley", 0.8, 1.3, V, u0, v0)
+        assert csr_rel(s.get_csr(1), A.tocsr()) <= CSR_TOL and rel_max(s.get_vector(0), b) <= CSR_TOL
+        s.debug_assemble_base(False)
+        s.debug_assemble_newton(False, 1.1, V, u0, v0)
+        assert csr_rel(s.get_csr(1), An.tocsr()) <= CSR_TOL and rel_max(s.get_vector(0), bn) <= CSR_TOL
+        assert rel_max(s.get_vector(1), Fn) <= 1e-11
+
+
+def test_high_degree_node_mesh(D, O):
+    """A node with 14 incident triangles and 15-entry rows: exercises the kernels' long-row paths."""
+    from util import fan_mesh
+    mesh = fan_mesh(14, 3)
+    om = oracle_mesh(mesh)
+    assert np.all(O._geometry(om)[6] > 0)
+    f = D.SinhRHS(lambda x, y: 1.0 + x * y, alpha=-1.0, beta=1.0)
+    A = [lambda t: 1.0, lambda t: 0.0, lambda t: 0.0, lambda t: 2.0]
+    gd = lambda x, y: 0.2 * x - 0.1 * y
+    bd = [[1, 2], ["D", "N"], [gd, lambda x, y: 0.3 + 0 * x]]
+    with D.Session(0) as s:
+        s.set_mesh(mesh)
+        s.setup_semlin(A, bd, f, f.derivative())
+        s.debug_assemble_base(True)
+        Vt = 0.3 * np.cos(2 * mesh.nodes[0]) + 0.1 * mesh.nodes[1]
+        M, Aop, b, F = O.semlin_newton_system(om, A, bd, f, f.derivative(), Vt)
+        s.debug_assemble_newton(True, 0.0, Vt)
+        assert csr_rel(s.get_csr(0), M.tocsr()) <= CSR_TOL and csr_rel(s.get_csr(1), Aop.tocsr()) <= CSR_TOL
+        assert rel_max(s.get_vector(0), b) <= CSR_TOL and rel_max(s.get_vector(1), F) <= 1e-11
+        assert (np.diff(s.get_csr(0).indptr)).max() == 15
+        V, st = s.solve_semlin(1e-13)
+    Vo = O.solve_semlin_poisson(om, A, bd, f, f.derivative(), 1e-13)
+    assert rel_l2(V, Vo) <= FIELD_TOL
+
+
+def test_jittered_structured_mesh(D, O):
+    """SURVEY 8d config 4 perturbation: interior nodes jittered by 0.2h*U(-1,1), numpy default_rng(0)."""
+    nx, ny = 48, 24
+    mesh = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
+    h = 1.0 / ny
+    rng = np.random.default_rng(0)
+    nodes = mesh.nodes.copy()
+    X = nodes.reshape(2, ny + 1, nx + 1)
+    X[:, 1:-1, 1:-1] += 0.2 * h * rng.uniform(-1, 1, size=(2, ny - 1, nx - 1))
+    mesh = D.Mesh(nodes, mesh.edges, mesh.elements)
+    om = oracle_mesh(mesh)
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
+    V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], return_stats=True, verbose=False)
+    tr = {}
+    Vo, uo, vo = O.solve_ddpe(om, *[pr[k] for k in KEYS], trace=tr)
+    assert rel_l2(V, Vo) <= FIELD_TOL and rel_l2(u, uo) <= FIELD_TOL and rel_l2(v, vo) <= FIELD_TOL
+    assert st["outer_iters"] == len(tr["control"])

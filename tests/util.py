@@ -67,3 +67,43 @@ def smooth_fields(mesh, seed=0):
     u = np.exp(0.5 * np.sin(c[4] * 2 * x + y))
     v = np.exp(-0.4 * np.cos(c[5] * x - 2 * y))
     return V, u, v
+
+
+def fan_mesh(nfan=14, rings=3):
+    """Unstructured test mesh with a high-degree centre node (nfan triangles around it, > 8 so the kernels'
+    long-row / many-incidence paths run) surrounded by `rings` rings; boundary edges tagged 1 (lower half) / 2."""
+    import ddps_b200 as D
+    pts = [(0.0, 0.0)]
+    for r in range(1, rings + 1):
+        for k in range(nfan):
+            a = 2 * np.pi * (k + 0.5 * (r % 2)) / nfan
+            pts.append((r * np.cos(a) / rings, r * np.sin(a) / rings))
+    nodes = np.array(pts).T
+    idx = lambda r, k: 1 + (r - 1) * nfan + (k % nfan)          # 0-based id of ring r (1..), position k
+    tris = []
+    for k in range(nfan):
+        tris.append((0, idx(1, k), idx(1, k + 1)))
+    for r in range(1, rings):
+        for k in range(nfan):
+            a, b = idx(r, k), idx(r, k + 1)
+            if r % 2 == 1:      # outer ring shifted by half a step relative to the inner one
+                c, d = idx(r + 1, k), idx(r + 1, k + 1)
+                tris.append((a, c, b))
+                tris.append((b, c, d))
+            else:
+                c, d = idx(r + 1, k - 1), idx(r + 1, k)
+                tris.append((a, c, d))
+                tris.append((a, d, b))
+    el = np.zeros((5, len(tris)), dtype=np.int64)
+    for e, t in enumerate(tris):
+        q = nodes[:, list(t)]
+        area = (q[0, 1] - q[0, 2]) * (q[1, 2] - q[1, 0]) - (q[1, 1] - q[1, 2]) * (q[0, 2] - q[0, 0])
+        t = t if area > 0 else (t[0], t[2], t[1])
+        el[0:3, e] = np.array(t) + 1
+    el[3:] = 2
+    edges = []
+    for k in range(nfan):
+        a, b = idx(rings, k) + 1, idx(rings, k + 1) + 1
+        tag = 1 if k < nfan // 2 else 2
+        edges.append((a, b, 1, tag))
+    return D.Mesh(nodes, np.array(edges, dtype=np.int64).T.copy(), el)
