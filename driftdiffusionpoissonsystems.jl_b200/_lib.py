@@ -22,7 +22,7 @@ class SolverOpts(C.Structure):
     _fields_ = [("lin_rtol", C.c_double), ("newton_eta", C.c_double), ("lin_max_it", C.c_int64),
                 ("max_newton", C.c_int32), ("max_gummel", C.c_int32), ("check_every", C.c_int32),
                 ("warm_start", C.c_int32), ("verbose", C.c_int32), ("lin_cap_ok", C.c_int32), ("no_alt_traversal", C.c_int32), ("warm_start_v", C.c_int32),
-                ("no_sym_scaling", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Stats(C.Structure):

@@ -91,8 +91,11 @@ int upload_nodal(Context* ctx, double* dst, const double* src_global) {
   return 0;
 }
 
+int download_owned(Context* ctx, const double* src, double* dst_user);
+
 // Copy the owned part of a local field into a global [nq] host array (all ranks get the full field).
 int download_nodal(Context* ctx, const double* src_local, double* dst_global) {
+  if (ctx->nranks == 1 && !ctx->loc2glob.empty()) return download_owned(ctx, src_local, dst_global);
   if (ctx->nranks == 1) {
     DDPS_CUDA(cudaMemcpyAsync(dst_global, src_local, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -181,6 +184,53 @@ int build_local_mesh(const double* nodes, int64_t nq, const int64_t* elements, i
     L.elem[i] = make_int4(g2l[c[0] - 1], g2l[c[1] - 1], g2l[c[2] - 1], (int)c[4]);
   }
   return 0;
+}
+
+// Owned-row vectors in the caller's numbering (single-GPU debug exports; identity unless the mesh was renumbered)
+int upload_owned(Context* ctx, double* dst, const double* src_user) {
+  if (ctx->loc2glob.empty()) return upload(ctx, dst, src_user, (size_t)ctx->n_own);
+  std::vector<double> tmp(ctx->n_own);
+  for (int i = 0; i < ctx->n_own; ++i) tmp[i] = src_user[ctx->loc2glob[i]];
+  int rc = upload(ctx, dst, tmp.data(), tmp.size());
+  if (rc) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int download_owned(Context* ctx, const double* src, double* dst_user) {
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->loc2glob.empty()) {
+    DDPS_CUDA(cudaMemcpy(dst_user, src, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  std::vector<double> tmp(ctx->n_own);
+  DDPS_CUDA(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < ctx->n_own; ++i) dst_user[ctx->loc2glob[i]] = tmp[i];
+  return 0;
+}
+
+// Space-filling-curve (Morton / Z-order) renumbering of the nodes: internal id -> user id.  gmsh numbers nodes
+// in insertion order; rows that are neighbours in the mesh are then far apart in memory and the SpMV gathers
+// miss L1/L2.  Sorting the nodes along a Z-curve makes index-neighbours spatial neighbours.
+void morton_order(const double* nodes, int64_t nq, std::vector<int64_t>& user_of_int) {
+  double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+  for (int64_t i = 0; i < nq; ++i)
+    for (int d = 0; d < 2; ++d) { lo[d] = std::min(lo[d], nodes[2 * i + d]); hi[d] = std::max(hi[d], nodes[2 * i + d]); }
+  const double ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), 1e-300);
+  auto spread = [](uint32_t v) {
+    v &= 0xffff; v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+    return v;
+  };
+  std::vector<std::pair<uint32_t, int64_t>> keys(nq);
+  for (int64_t i = 0; i < nq; ++i) {
+    uint32_t xi = (uint32_t)std::min(65535.0, (nodes[2 * i] - lo[0]) / ext * 65535.0);
+    uint32_t yi = (uint32_t)std::min(65535.0, (nodes[2 * i + 1] - lo[1]) / ext * 65535.0);
+    keys[i] = {spread(xi) | (spread(yi) << 1), i};
+  }
+  std::sort(keys.begin(), keys.end());
+  user_of_int.resize(nq);
+  for (int64_t i = 0; i < nq; ++i) user_of_int[i] = keys[i].second;
 }
 
 AsmArgs base_args(Context* ctx) {
@@ -487,6 +537,28 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
   ctx->nq_global = nq; ctx->nme_global = nme;
   int rc;
   std::vector<int4> hel;
+  // optional internal renumbering (the caller keeps its own numbering at the ABI)
+  std::vector<int64_t> user_of_int;
+  std::vector<double> pnodes;
+  std::vector<int64_t> pelems;
+  if (ctx->opts.renumber) {
+    for (int64_t e = 0; e < nme; ++e)
+      for (int k = 0; k < 3; ++k)
+        if (elements[5 * e + k] < 1 || elements[5 * e + k] > nq) {
+          ctx->fail(DDPS_ERR_ARG, "element " + std::to_string(e + 1) + " references a node outside 1..nq");
+          return DDPS_ERR_ARG;
+        }
+    morton_order(nodes, nq, user_of_int);
+    std::vector<int64_t> int_of_user(nq);
+    for (int64_t i = 0; i < nq; ++i) int_of_user[user_of_int[i]] = i;
+    pnodes.resize((size_t)2 * nq);
+    for (int64_t i = 0; i < nq; ++i) { pnodes[2 * i] = nodes[2 * user_of_int[i]]; pnodes[2 * i + 1] = nodes[2 * user_of_int[i] + 1]; }
+    pelems.assign(elements, elements + (size_t)5 * nme);
+    for (int64_t e = 0; e < nme; ++e)
+      for (int k = 0; k < 3; ++k) pelems[5 * e + k] = int_of_user[elements[5 * e + k] - 1] + 1;
+    nodes = pnodes.data();
+    elements = pelems.data();
+  }
   if (ctx->nranks == 1) {
     ctx->n_own = ctx->n_loc = (int)nq;
     if (nme >= (1LL << 29)) { ctx->fail(DDPS_ERR_ARG, "too many triangles for one GPU"); return DDPS_ERR_ARG; }
@@ -503,6 +575,13 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     }
     if ((rc = dev_alloc(ctx, &ctx->xy, (size_t)nq))) return rc;
     if ((rc = upload(ctx, (double*)ctx->xy, nodes, (size_t)2 * nq))) return rc;
+    if (!user_of_int.empty()) {
+      ctx->loc2glob = user_of_int;
+      if ((rc = dev_alloc(ctx, &ctx->d_own_glob, (size_t)nq))) return rc;
+      std::vector<long long> og(user_of_int.begin(), user_of_int.end());
+      if ((rc = upload(ctx, ctx->d_own_glob, og.data(), og.size()))) return rc;
+      DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
   } else {
     LocalMesh L;
     std::string perr;
@@ -523,6 +602,8 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     for (int i = 0; i < ctx->n_loc; ++i) { hxy[2 * i] = nodes[2 * ctx->loc2glob[i]]; hxy[2 * i + 1] = nodes[2 * ctx->loc2glob[i] + 1]; }
     if ((rc = dev_alloc(ctx, &ctx->xy, (size_t)ctx->n_loc))) return rc;
     if ((rc = upload(ctx, (double*)ctx->xy, hxy.data(), hxy.size()))) return rc;
+    if (!user_of_int.empty())   // compose with the renumbering: local -> internal global -> caller's numbering
+      for (int i = 0; i < ctx->n_loc; ++i) ctx->loc2glob[i] = user_of_int[ctx->loc2glob[i]];
     if ((rc = dev_alloc(ctx, &ctx->d_own_glob, (size_t)ctx->n_own))) return rc;
     std::vector<long long> og(ctx->loc2glob.begin(), ctx->loc2glob.begin() + ctx->n_own);
     if ((rc = upload(ctx, ctx->d_own_glob, og.data(), og.size()))) return rc;
@@ -651,7 +732,8 @@ int ddps_coeff_set(ddps_ctx* ctx, int slot, const double* data, int64_t len) {
   size_t nloc = kind == 0 ? (size_t)ctx->nme : kind == 1 ? (size_t)3 * ctx->nme : (size_t)ctx->n_loc;
   if ((rc = dev_alloc(ctx, &ctx->coeff[slot], nloc))) return rc;
   ctx->coeff_len[slot] = (int64_t)nloc;
-  if (ctx->nranks == 1) {
+  const bool direct = (kind == 2) ? ctx->loc2glob.empty() : ctx->elem_glob.empty();
+  if (direct) {
     if ((rc = upload(ctx, ctx->coeff[slot], data, nloc))) return rc;
   } else {
     std::vector<double> tmp(nloc);
@@ -847,17 +929,38 @@ int ddps_get_csr(ddps_ctx* ctx, int which, int64_t* rowptr, int64_t* col, double
   DDPS_CUDA(cudaMemcpy(rp.data(), P.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
   DDPS_CUDA(cudaMemcpy(cc.data(), P.csrcol, cc.size() * sizeof(int), cudaMemcpyDeviceToHost));
   DDPS_CUDA(cudaMemcpy(sp.data(), P.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  if (rowptr) for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
-  if (col) for (size_t i = 0; i < cc.size(); ++i) col[i] = ctx->loc2glob.empty() ? cc[i] : ctx->loc2glob[cc[i]];
+  std::vector<double> vals;
   if (val) {
     const double* src = which == DDPS_MAT_BASE ? ctx->val_base : ctx->val_op;
     std::vector<double> sv(P.nentries);
     DDPS_CUDA(cudaMemcpy(sv.data(), src, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    vals.resize(P.nnz);
     for (int r = 0; r < P.nrows; ++r) {
       int base = sp[r >> 5], lane = r & 31;
-      for (int k = 0; k < rp[r + 1] - rp[r]; ++k) val[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
+      for (int k = 0; k < rp[r + 1] - rp[r]; ++k) vals[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
     }
   }
+  if (ctx->nranks == 1 && !ctx->loc2glob.empty()) {
+    // renumbered mesh: hand the matrix back in the CALLER's numbering (rows and columns permuted, columns re-sorted)
+    const int n = P.nrows;
+    std::vector<int> int_of_user(n);
+    for (int i = 0; i < n; ++i) int_of_user[ctx->loc2glob[i]] = i;
+    int64_t pos = 0;
+    std::vector<std::pair<int64_t, double>> rowbuf;
+    for (int ur = 0; ur < n; ++ur) {
+      const int r = int_of_user[ur];
+      if (rowptr) rowptr[ur] = pos;
+      rowbuf.clear();
+      for (int k = rp[r]; k < rp[r + 1]; ++k) rowbuf.emplace_back(ctx->loc2glob[cc[k]], val ? vals[k] : 0.0);
+      std::sort(rowbuf.begin(), rowbuf.end());
+      for (auto& e : rowbuf) { if (col) col[pos] = e.first; if (val) val[pos] = e.second; ++pos; }
+    }
+    if (rowptr) rowptr[n] = pos;
+    return DDPS_OK;
+  }
+  if (rowptr) for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
+  if (col) for (size_t i = 0; i < cc.size(); ++i) col[i] = ctx->loc2glob.empty() ? cc[i] : ctx->loc2glob[cc[i]];
+  if (val) for (int64_t i = 0; i < P.nnz; ++i) val[i] = vals[i];
   return DDPS_OK;
 }
 
@@ -877,6 +980,7 @@ int ddps_get_vector(ddps_ctx* ctx, int which, double* out, int64_t len) {
     default: ctx->fail(DDPS_ERR_ARG, "unknown vector"); return DDPS_ERR_ARG;
   }
   if (len != ctx->n_own) { ctx->fail(DDPS_ERR_ARG, "vector length must equal the number of owned rows"); return DDPS_ERR_ARG; }
+  if (ctx->nranks == 1) return download_owned(ctx, src, out);
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   DDPS_CUDA(cudaMemcpy(out, src, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost));
   return DDPS_OK;
@@ -931,6 +1035,7 @@ int ddps_debug_spmv(ddps_ctx* ctx, int which, const double* x, double* y) {
   if ((rc = require_mesh(ctx))) return rc;
   if ((rc = upload_nodal(ctx, ctx->p, x))) return rc;
   if ((rc = launch_spmv(ctx, which == DDPS_MAT_BASE ? ctx->val_base : ctx->val_op, ctx->p, ctx->q))) return rc;
+  if (ctx->nranks == 1) return download_owned(ctx, ctx->q, y);
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   DDPS_CUDA(cudaMemcpy(y, ctx->q, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost));
   return DDPS_OK;
@@ -942,11 +1047,10 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
   int rc;
   if ((rc = require_mesh(ctx))) return rc;
   if (ctx->nranks != 1) { ctx->fail(DDPS_ERR_STATE, "debug exports are single-GPU"); return DDPS_ERR_STATE; }
-  if ((rc = upload(ctx, ctx->b, rhs, (size_t)ctx->n_own)) || (rc = upload(ctx, ctx->x, x, (size_t)ctx->n_own))) return rc;
+  if ((rc = upload_owned(ctx, ctx->b, rhs)) || (rc = upload_owned(ctx, ctx->x, x))) return rc;
   rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, true, rtol, 0.0, max_it, iters, relres);
-  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
-  DDPS_CUDA(cudaMemcpy(x, ctx->x, (size_t)ctx->n_own * sizeof(double), cudaMemcpyDeviceToHost));
-  return rc;
+  int rc3 = download_owned(ctx, ctx->x, x);
+  return rc ? rc : rc3;
 }
 
 // ---- kernel timing on the library stream --------------------------------------------------------

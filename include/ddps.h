@@ -93,7 +93,10 @@ typedef struct ddps_solver_opts {
   int32_t warm_start_v; /* OPT-IN, changes the iteration history: Vsolve starts Newton from the previous Gummel iterate
                            instead of V=0 (src:311) -- SURVEY section 8f rank 4.  Default 0 = reference behaviour */
   int32_t no_sym_scaling; /* 1: classic Jacobi-PCG with explicit D^-1 reads instead of CG on D^-1/2 A D^-1/2 (same iterates) */
-  int32_t reserved[3];
+  int32_t renumber;     /* set BEFORE ddps_mesh_set.  1: renumber the nodes internally along a Morton (Z-order) curve so that
+                           mesh neighbours are index neighbours (gmsh numbering is insertion order); the ABI keeps the
+                           caller's numbering for every input and output.  Default 0 */
+  int32_t reserved[2];
 } ddps_solver_opts;
 
 typedef struct ddps_stats {

@@ -50,8 +50,8 @@ derivative(f::PolyRHS) = (x, y, u) -> sum((k - 1) * c(x, y) * u^(k - 2) for (k, 
 struct SolverOpts
     lin_rtol::Cdouble; newton_eta::Cdouble; lin_max_it::Int64
     max_newton::Int32; max_gummel::Int32; check_every::Int32; warm_start::Int32; verbose::Int32; lin_cap_ok::Int32
-    no_alt_traversal::Int32; warm_start_v::Int32; no_sym_scaling::Int32
-    reserved::NTuple{3,Int32}
+    no_alt_traversal::Int32; warm_start_v::Int32; no_sym_scaling::Int32; renumber::Int32
+    reserved::NTuple{2,Int32}
 end
 
 struct Stats
@@ -73,7 +73,7 @@ function with_ctx(f; device = 0, verbose = true)
         ccall((:ddps_default_opts, LIB), Cvoid, (Ref{SolverOpts},), o)
         v = o[]
         o[] = SolverOpts(v.lin_rtol, v.newton_eta, v.lin_max_it, v.max_newton, v.max_gummel, v.check_every, v.warm_start,
-                         Int32(verbose), v.lin_cap_ok, v.no_alt_traversal, v.warm_start_v, v.no_sym_scaling, v.reserved)
+                         Int32(verbose), v.lin_cap_ok, v.no_alt_traversal, v.warm_start_v, v.no_sym_scaling, v.renumber, v.reserved)
         chk(h, ccall((:ddps_set_opts, LIB), Cint, (Ptr{Cvoid}, Ref{SolverOpts}), h, o))
         return f(h)
     finally

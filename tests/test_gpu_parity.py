@@ -457,3 +457,47 @@ def test_jittered_structured_mesh(D, O):
     Vo, uo, vo = O.solve_ddpe(om, *[pr[k] for k in KEYS], trace=tr)
     assert rel_l2(V, Vo) <= FIELD_TOL and rel_l2(u, uo) <= FIELD_TOL and rel_l2(v, vo) <= FIELD_TOL
     assert st["outer_iters"] == len(tr["control"])
+
+
+# ---------------------------------------------------------------- numbering independence + internal renumbering
+def _permute_mesh(mesh, D, seed=0):
+    """Random renumbering of the nodes (what a gmsh-style insertion-order numbering looks like to the kernels)."""
+    rng = np.random.default_rng(seed)
+    p = rng.permutation(mesh.nq)               # p[old] = new (0-based)
+    nodes = np.empty_like(mesh.nodes)
+    nodes[:, p] = mesh.nodes
+    el = mesh.elements.copy()
+    el[0:3] = p[mesh.elements[0:3] - 1] + 1
+    ed = mesh.edges.copy()
+    ed[0:2] = p[mesh.edges[0:2] - 1] + 1
+    return D.Mesh(nodes, ed, el), p
+
+
+@pytest.mark.parametrize("renumber", [0, 1])
+def test_random_numbering_and_morton_renumbering(D, O, renumber):
+    """opts.renumber=1 reorders the nodes internally along a Z-curve; every input and output of
+    the ABI stays in the caller's numbering.  Fields, assembled CSR and vectors must not depend on it."""
+    base = gpu_mesh("F2")
+    mesh, p = _permute_mesh(base, D, seed=5)
+    om = oracle_mesh(mesh)
+    pr = D.problems.ddpe2()
+    z = golden("ddpe2_F2")
+    V0, u0, v0 = smooth_fields(mesh, 17)
+    _, _, gD, n = O.aquire_boundary(om, pr["Vbddata"])
+    A, b = O.uv_system(om, "shockley", V0, pr["ubddata"], 1.0, 1.0, pr["mu_p"], n, u0, v0)
+    with _ddpe_session(D, mesh, pr, renumber=renumber) as s:
+        s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V0, u0, v0)
+        assert csr_rel(s.get_csr(1), A.tocsr()) <= CSR_TOL
+        assert rel_max(s.get_vector(0), b) <= CSR_TOL
+        x = np.random.default_rng(1).standard_normal(mesh.nq)
+        assert rel_max(s.debug_spmv(1, x), A @ x) <= 1e-13
+        V, u, v, st = s.solve_ddpe(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+    assert rel_l2(V[p], z["V"]) <= FIELD_TOL and rel_l2(u[p], z["u"]) <= FIELD_TOL and rel_l2(v[p], z["v"]) <= FIELD_TOL
+    assert st["outer_iters"] == len(z["control"])
+    # semlin with Neumann loads (nodal coefficient arrays) through the same mapping
+    sp_ = D.problems.semlin_test(False)
+    with D.Session(0, renumber=renumber) as s:
+        s.set_mesh(mesh)
+        s.setup_semlin(sp_["A"], sp_["bddata"], sp_["f"], sp_["g"])
+        Vs, st2 = s.solve_semlin(sp_["tol"])
+    assert rel_l2(Vs[p], golden("semlin_F2")["V"]) <= FIELD_TOL and st2["outer_iters"] == 5
