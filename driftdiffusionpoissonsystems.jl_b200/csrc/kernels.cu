@@ -342,38 +342,24 @@ __global__ void __launch_bounds__(kAsmBlock, DDPS_ASM_MINBLOCKS) k_assemble(cons
     const int e = r.x >> 2, a = r.x & 3;
     const unsigned y = (unsigned)r.y;
     const int s_next = y & 31, s_prev = (y >> 5) & 31, lb = (y >> 10) & 2047, lc = y >> 21;
-    const double2 q_b = make_double2(sX[lb], sY[lb]), q_c = make_double2(sX[lc], sY[lc]);
-    // canonical corner order (1,2,3) of the triangle: corner a is this row
-    const double2 q1 = (a == 0) ? q_own : (a == 1) ? q_c : q_b;
-    const double2 q2 = (a == 0) ? q_b : (a == 1) ? q_own : q_c;
-    const double2 q3 = (a == 0) ? q_c : (a == 1) ? q_b : q_own;
-    // edge vectors and signed area, src:243-246
-    const double ux = q2.x - q3.x, uy = q2.y - q3.y;
-    const double vx = q3.x - q1.x, vy = q3.y - q1.y;
-    const double wx = q1.x - q2.x, wy = q1.y - q2.y;
-    const double ar = (ux * vy - uy * vx) * 0.5;
+    // Own frame of the row: A = this row's corner, B = next, C = previous corner (cyclic).  Edge vectors opposite
+    // each corner (src:243-245 up to the cyclic relabelling) and the signed area (src:246); every product is
+    // written so that entry (i,j) computed for row i and entry (j,i) computed for row j use the same operands
+    // in a commutative order (no 3-way selects on the corner index).
+    const double bx = sX[lb], by = sY[lb], cx = sX[lc], cy = sY[lc];
+    const double eax = bx - cx, eay = by - cy;            // e_A = q_B - q_C
+    const double ebx = cx - q_own.x, eby = cy - q_own.y;  // e_B = q_C - q_A
+    const double ecx = q_own.x - bx, ecy = q_own.y - by;  // e_C = q_A - q_B
+    const double ar = (eax * eby - eay * ebx) * 0.5;
     double c_self = 0.0, c_next = 0.0, c_prev = 0.0;
     if (STIFF != STIFF_BASE) {
       double phx = phx_in, phy = phy_in;
-      if (STIFF == STIFF_EXPV) {
-        // exp((V1+V2+V3)/3) as the product of the nodal factors in canonical corner order, src:469
-        const double eb = sE3[lb], ec = sE3[lc];
-        const double e1 = (a == 0) ? own_e3 : (a == 1) ? ec : eb;
-        const double e2 = (a == 0) ? eb : (a == 1) ? own_e3 : ec;
-        const double e3 = (a == 0) ? ec : (a == 1) ? eb : own_e3;
-        phx = phx_in * (e1 * e2 * e3); phy = phx;
-      }
+      if (STIFF == STIFF_EXPV) { phx = phx_in * (own_e3 * sE3[lb] * sE3[lc]); phy = phx; }   // src:469
       const double inv4 = 1.0 / fabs(ar * 4.0);  // src:257 (one division per triangle; <= 1 ulp vs x/ar4)
-      // canonical lower-triangle entries K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar|, i>=j
-      // (src:260-266); select the row of corner a: self, next, prev.
-      const double sx = (a == 0) ? ux : (a == 1) ? vx : wx, sy = (a == 0) ? uy : (a == 1) ? vy : wy;
-      const double nhx = (a == 0) ? vx : wx, nhy = (a == 0) ? vy : wy;   // (a,next): (2,1),(3,2),(3,1)
-      const double nlx = (a == 1) ? vx : ux, nly = (a == 1) ? vy : uy;
-      const double khx = (a == 1) ? vx : wx, khy = (a == 1) ? vy : wy;   // (a,prev): (3,1),(2,1),(3,2)
-      const double klx = (a == 2) ? vx : ux, kly = (a == 2) ? vy : uy;
-      const double k_self = (sx * phx * sx + sy * phy * sy) * inv4;
-      const double k_next = (nhx * phx * nlx + nhy * phy * nly) * inv4;
-      const double k_prev = (khx * phx * klx + khy * phy * kly) * inv4;
+      // K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar| (src:260-266)
+      const double k_self = (phx * (eax * eax) + phy * (eay * eay)) * inv4;
+      const double k_next = (phx * (eax * ebx) + phy * (eay * eby)) * inv4;
+      const double k_prev = (phx * (eax * ecx) + phy * (eay * ecy)) * inv4;
       const bool bD = sD[lb] != 0, cD = sD[lc] != 0;
       // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
       c_self = rowD ? 0.0 : k_self;
@@ -386,19 +372,13 @@ __global__ void __launch_bounds__(kAsmBlock, DDPS_ASM_MINBLOCKS) k_assemble(cons
       }
     }
     if (MASS) {
-      // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never
-      // eliminated (Q3)
+      // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never eliminated (Q3).
+      // diag = 3Wa+Wb+Wc, (a,b) = Wa+Wb+Wc/2: the pair sum first, so that (a,b) and (b,a) round identically
       const double ar30 = ar * (1.0 / 30.0);
       const double Wa = own_g * ar30, Wb = sGW[lb] * ar30, Wc = sGW[lc] * ar30;
-      // canonical addition order of src:380-386 (W1,W2,W3 left to right)
-      const double W1 = (a == 0) ? Wa : (a == 1) ? Wc : Wb;
-      const double W2 = (a == 0) ? Wb : (a == 1) ? Wa : Wc;
-      const double W3 = (a == 0) ? Wc : (a == 1) ? Wb : Wa;
-      double m_self, m_next, m_prev;
-      if (a == 0) { m_self = 3.0 * W1 + W2 + W3; m_next = W1 + W2 + W3 * 0.5; m_prev = W1 + W2 * 0.5 + W3; }
-      else if (a == 1) { m_self = W1 + 3.0 * W2 + W3; m_next = W1 * 0.5 + W2 + W3; m_prev = W1 + W2 + W3 * 0.5; }
-      else { m_self = W1 + W2 + 3.0 * W3; m_next = W1 + W2 * 0.5 + W3; m_prev = W1 * 0.5 + W2 + W3; }
-      c_self -= m_self; c_next -= m_next; c_prev -= m_prev;
+      c_self -= 3.0 * Wa + (Wb + Wc);
+      c_next -= (Wa + Wb) + Wc * 0.5;
+      c_prev -= (Wa + Wc) + Wb * 0.5;
     }
     if (STIFF != STIFF_BASE || MASS) {
       acc[sdiag * kAsmBlock + tid] += c_self;
