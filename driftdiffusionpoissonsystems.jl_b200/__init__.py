@@ -13,8 +13,9 @@ from .api import (Session, DDPSError, solve_ddpe, solve_semlin_poisson, aquire_b
                   neumann_edges)
 from .postprocess import aquire_boundary_separate_edges, get_gradients, calculate_current, current_from_fields
 from . import problems
+from . import amg
 
 __all__ = ["Mesh", "read_mesh", "construct_mesh4", "construct_mesh8", "construct_mesh", "structured_mesh",
            "solve_ddpe", "solve_semlin_poisson", "aquire_boundary", "SinhRHS", "PolyRHS", "Session", "DDPSError",
-           "problems", "dirichlet_nodes", "neumann_edges", "aquire_boundary_separate_edges", "get_gradients",
+           "problems", "amg", "dirichlet_nodes", "neumann_edges", "aquire_boundary_separate_edges", "get_gradients",
            "calculate_current", "current_from_fields"]

@@ -16,13 +16,16 @@ LIB_PATH = os.environ.get("DDPS_B200_LIB", os.path.join(_HERE, "libddps_b200.so"
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
 c_int32_p = C.POINTER(C.c_int32)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+PRECOND_JACOBI, PRECOND_AMG = 0, 1
 
 
 class SolverOpts(C.Structure):
     _fields_ = [("lin_rtol", C.c_double), ("newton_eta", C.c_double), ("lin_max_it", C.c_int64),
                 ("max_newton", C.c_int32), ("max_gummel", C.c_int32), ("check_every", C.c_int32),
                 ("warm_start", C.c_int32), ("verbose", C.c_int32), ("lin_cap_ok", C.c_int32), ("no_alt_traversal", C.c_int32), ("warm_start_v", C.c_int32),
-                ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("precond", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class Stats(C.Structure):
@@ -30,10 +33,11 @@ class Stats(C.Structure):
                 ("spmv_total", C.c_int64), ("kernel_launches", C.c_int64), ("control", C.c_double),
                 ("t_setup_ms", C.c_double), ("t_solve_ms", C.c_double), ("t_asm_ms", C.c_double),
                 ("t_pcg_ms", C.c_double), ("t_wall_ms", C.c_double), ("status", C.c_int32), ("n_negative_area", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("amg_levels", C.c_int32), ("reserved0", C.c_int32), ("t_amg_setup_ms", C.c_double),
+                ("reserved", C.c_int32 * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 # every symbol include/ddps.h declares: name -> (restype, argtypes)
@@ -72,6 +76,17 @@ SIGNATURES = {
     "ddps_debug_spmv": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
     "ddps_debug_pcg": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_int64, c_int64_p, c_double_p]),
     "ddps_time_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
+    "ddps_amg_host_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, c_int64_p, c_int64_p, c_double_p, c_uint8_p,
+                                       C.c_int, C.c_int]),
+    "ddps_amg_host_nlevels": (C.c_int, [C.c_void_p]),
+    "ddps_amg_host_level_sizes": (C.c_int, [C.c_void_p, C.c_int, c_int64_p]),
+    "ddps_amg_host_level_get": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_int64_p, c_double_p, c_int64_p, c_int64_p,
+                                          c_double_p, c_int64_p]),
+    "ddps_amg_host_free": (None, [C.c_void_p]),
+    "ddps_amg_levels": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),
+    "ddps_amg_numeric": (C.c_int, [C.c_void_p, C.c_int]),
+    "ddps_amg_get_values": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    "ddps_amg_apply": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
 }
 
 _lib = None

@@ -372,6 +372,29 @@ class Session:
         self._check(self.lib.ddps_debug_pcg(self.h, _lib.dptr(rhs), _lib.dptr(x), float(rtol), int(max_it), C.byref(it), C.byref(rr)))
         return x, it.value, rr.value
 
+    # -- multigrid preconditioner (opts.precond = 1) --
+    def amg_levels(self):
+        nl = C.c_int64(0)
+        sizes = np.zeros(16, dtype=np.int64)
+        self._check(self.lib.ddps_amg_levels(self.h, C.byref(nl), _lib.iptr(sizes)))
+        return [int(v) for v in sizes[:nl.value]]
+
+    def amg_numeric(self, which=MAT_OP):
+        self._check(self.lib.ddps_amg_numeric(self.h, int(which)))
+
+    def amg_get_values(self, level, nnz):
+        """CSR-ordered values (``nnz`` of them) and inverse diagonal of multigrid level ``level`` >= 1."""
+        n = self.amg_levels()[level]
+        val, dinv = np.zeros(int(nnz)), np.zeros(n)
+        self._check(self.lib.ddps_amg_get_values(self.h, int(level), _lib.dptr(val), _lib.dptr(dinv)))
+        return val, dinv
+
+    def amg_apply(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        z = np.zeros_like(r)
+        self._check(self.lib.ddps_amg_apply(self.h, _lib.dptr(r), _lib.dptr(z)))
+        return z
+
     def time_kernel(self, kernel, warm=3, reps=20):
         ms, by = C.c_double(0), C.c_double(0)
         self._check(self.lib.ddps_time_kernel(self.h, int(kernel), int(warm), int(reps), C.byref(ms), C.byref(by)))

@@ -1,0 +1,617 @@
+// Smoothed-aggregation multigrid preconditioner for the hand-written CG ("a better
+// preconditioner behind the same PCG interface", the replacement of the reference's `\`, src:394,588,1063).
+//
+// Split of the work:
+//   * once per base operator (host, amg_host.cu): aggregates, frozen smoothed prolongators P_l, R_l = P_l^T
+//     stored row-wise, and the coarse sparsity patterns;
+//   * once per operator A = M - J0 (device, k_amg_rap): the Galerkin products A_{l+1} = R_l A_l P_l on the frozen
+//     patterns -- one warp per coarse row, one lane per coarse entry, every lane walks the same
+//     (fine row, fine entry, prolongator entry) sequence and keeps the products of its own column, so every coarse
+//     entry is summed in a fixed order: no atomics, bitwise reproducible; then the dense inverse of the coarsest
+//     operator (Gauss-Jordan in one CTA);
+//   * per CG iteration (device): one V(1,1) cycle with damped-Jacobi smoothing; all matrices are SELL-32 like the
+//     fine operator, the smoother and the residual are fused into the SpMV epilogue, restriction/prolongation are
+//     deterministic row gathers.  The cycle is a fixed SPD linear operator, so plain (non-flexible) CG applies.
+// The PCG control flow (alpha, beta, stop test, iteration counter) stays on the device like in the Jacobi path;
+// every kernel of the cycle early-exits once the `done` flag is up.
+#include <chrono>
+
+#include "amg.h"
+#include "ddps_internal.cuh"
+#include "device_utils.cuh"
+
+namespace ddps {
+
+constexpr int kAmgMaxLevels = 12;
+constexpr int kAmgDenseMax = 512;
+
+struct AmgLevelDev {
+  int n = 0, nslices = 0, nc = 0;
+  int64_t nnz = 0, nentries = 0;
+  bool owns = false;                 // level 0 aliases the fine pattern of the context
+  int* slice_ptr = nullptr;
+  int* col = nullptr;
+  int* rowptr = nullptr;
+  double* val = nullptr;             // level >= 1: Galerkin values of the current operator (SELL order)
+  double* dinv = nullptr;            // level >= 1
+  const double* cur_val = nullptr;   // matrix / inverse diagonal used by the cycle (level 0: set per operator)
+  const double* cur_dinv = nullptr;
+  int *Pptr = nullptr, *Pcol = nullptr, *Rptr = nullptr, *Rrow = nullptr;
+  double *Pval = nullptr, *Rval = nullptr;
+  double *b = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
+};
+
+struct Amg {
+  bool ready = false;
+  int nlev = 0;
+  AmgLevelDev lv[kAmgMaxLevels];
+  double* dense = nullptr;   // [n_coarsest^2] inverse of the coarsest operator
+  double* z = nullptr;       // [n0] preconditioned residual of the CG
+  double omega = 2.0 / 3.0;
+  double setup_ms = 0.0;
+  std::vector<int> h_rowptr[kAmgMaxLevels], h_slice_ptr[kAmgMaxLevels];   // kept for the debug export (levels >= 1)
+};
+
+namespace {
+
+template <typename T>
+int amg_alloc(Context* ctx, T** p, size_t n) {
+  DDPS_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+template <typename T>
+int amg_upload(Context* ctx, T** p, const std::vector<T>& h) {
+  int rc = amg_alloc(ctx, p, h.size());
+  if (rc) return rc;
+  if (!h.empty()) DDPS_CUDA(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+template <typename T>
+void amg_release(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+inline int amg_grid(Context* ctx, int64_t work_items, int block) {
+  int64_t need = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)ctx->num_sms * (2048 / block);
+  return (int)std::max<int64_t>(1, std::min(need, cap));
+}
+
+double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------
+// SELL-32 SpMV with fused epilogue.  MODE 0: y = A x;  1: y = b - A x;  2: y = x + om * dinv * (b - A x)
+// (one damped-Jacobi sweep, out of place).  DOT (MODE 2, finest level): also sums b.y = r.z for the CG.
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(kVecBlock, 8) k_amg_spmv(int nrows, int nslices, const int* __restrict__ slice_ptr,
+                                                        const int* __restrict__ col, const double* __restrict__ val,
+                                                        const double* __restrict__ x, const double* __restrict__ b,
+                                                        const double* __restrict__ dinv, double om,
+                                                        double* __restrict__ y, double* partials, PcgScalars* scal) {
+  __shared__ double sh_red[32];
+  if (scal->done) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  for (int slice = gw; slice < nslices; slice += nw) {
+    const int base = slice_ptr[slice];
+    const int w = (slice_ptr[slice + 1] - base) >> 5;
+    int idx = base + lane;
+    double sum = 0.0;
+    int k = 0;
+    for (; k + 4 <= w; k += 4) {
+      const int c0 = ld_stream(col + idx), c1 = ld_stream(col + idx + 32), c2 = ld_stream(col + idx + 64),
+                c3 = ld_stream(col + idx + 96);
+      const double v0 = ld_stream(val + idx), v1 = ld_stream(val + idx + 32), v2 = ld_stream(val + idx + 64),
+                   v3 = ld_stream(val + idx + 96);
+      const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+      sum += v0 * x0; sum += v1 * x1; sum += v2 * x2; sum += v3 * x3;
+      idx += 128;
+    }
+    for (; k < w; ++k) {
+      const int c0 = ld_stream(col + idx);
+      const double v0 = ld_stream(val + idx);
+      sum += v0 * __ldg(x + c0);
+      idx += 32;
+    }
+    const int row = slice * 32 + lane;
+    if (row < nrows) {
+      double out;
+      if (MODE == 0) out = sum;
+      else if (MODE == 1) out = b[row] - sum;
+      else out = __ldg(x + row) + om * (dinv[row] * (b[row] - sum));
+      y[row] = out;
+      if (DOT) dot += b[row] * out;
+    }
+  }
+  if (DOT) {
+    double v[1] = {dot}, tot[1];
+    if (grid_reduce<1, false>(v, partials, &scal->cnt[0], sh_red, tot)) {
+      if (threadIdx.x == 0) scal->sums[1] = tot[0];
+    }
+  }
+}
+
+// x = om * dinv * b  (first damped-Jacobi sweep from the zero initial guess)
+__global__ void k_amg_jac0(int n, double om, const double* __restrict__ dinv, const double* __restrict__ b,
+                           double* __restrict__ x, const PcgScalars* scal) {
+  if (scal->done) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = om * (dinv[i] * b[i]);
+}
+
+// bc = R t   (R = P^T stored row-wise: a deterministic gather)
+__global__ void k_amg_restrict(int nc, const int* __restrict__ Rptr, const int* __restrict__ Rrow,
+                               const double* __restrict__ Rval, const double* __restrict__ t, double* __restrict__ bc,
+                               const PcgScalars* scal) {
+  if (scal->done) return;
+  for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    const int e = Rptr[I + 1];
+    for (int q = Rptr[I]; q < e; ++q) s += Rval[q] * __ldg(t + Rrow[q]);
+    bc[I] = s;
+  }
+}
+
+// x += P xc
+__global__ void k_amg_prolong(int n, const int* __restrict__ Pptr, const int* __restrict__ Pcol,
+                              const double* __restrict__ Pval, const double* __restrict__ xc, double* __restrict__ x,
+                              const PcgScalars* scal) {
+  if (scal->done) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    const int e = Pptr[i + 1];
+    for (int m = Pptr[i]; m < e; ++m) s += Pval[m] * __ldg(xc + Pcol[m]);
+    x[i] += s;
+  }
+}
+
+// Galerkin product on the frozen pattern: C = R A P.  One warp per coarse row I, lane t owns the coarse entry t of
+// that row; all lanes walk the same sequence (fine rows i of R(I,:), entries (i,j) of A, entries (j,J) of P) and
+// keep the products whose J is their own column.  Fixed summation order per entry -> bitwise reproducible.
+__global__ void __launch_bounds__(256) k_amg_rap(int nc, const int* __restrict__ f_slice_ptr, const int* __restrict__ f_col,
+                                                 const double* __restrict__ f_val, const int* __restrict__ Pptr,
+                                                 const int* __restrict__ Pcol, const double* __restrict__ Pval,
+                                                 const int* __restrict__ Rptr, const int* __restrict__ Rrow,
+                                                 const double* __restrict__ Rval, const int* __restrict__ c_rowptr,
+                                                 const int* __restrict__ c_slice_ptr, const int* __restrict__ c_col,
+                                                 double* __restrict__ c_val, double* __restrict__ c_dinv) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int I = gw; I < nc; I += nw) {
+    const int len = c_rowptr[I + 1] - c_rowptr[I];
+    const int cbase = c_slice_ptr[I >> 5] + (I & 31);
+    const int q0 = Rptr[I], q1 = Rptr[I + 1];
+    for (int t0 = 0; t0 < len; t0 += 32) {
+      const int t = t0 + lane;
+      const int myJ = t < len ? c_col[cbase + 32 * t] : -1;
+      double acc = 0.0;
+      for (int q = q0; q < q1; ++q) {
+        const int i = Rrow[q];
+        const double r = Rval[q];
+        const int fb = f_slice_ptr[i >> 5];
+        const int w = (f_slice_ptr[(i >> 5) + 1] - fb) >> 5;
+        int idx = fb + (i & 31);
+        for (int k = 0; k < w; ++k, idx += 32) {
+          const double a = f_val[idx];
+          if (a == 0.0) continue;   // padding and the exact zeros of right-angle meshes / eliminated entries
+          const int j = f_col[idx];
+          const double ra = r * a;
+          const int m1 = Pptr[j + 1];
+          for (int m = Pptr[j]; m < m1; ++m)
+            if (Pcol[m] == myJ) acc += ra * Pval[m];
+        }
+      }
+      if (t < len) {
+        c_val[cbase + 32 * t] = acc;
+        if (myJ == I) c_dinv[I] = 1.0 / acc;
+      }
+    }
+  }
+}
+
+// Dense inverse of the coarsest operator: in-place Gauss-Jordan without pivoting (the operator is SPD), one CTA.
+__global__ void __launch_bounds__(1024) k_amg_dense_inverse(int n, const int* __restrict__ rowptr,
+                                                            const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                                                            const double* __restrict__ val, double* __restrict__ Ainv) {
+  __shared__ double shrow[kAmgDenseMax], shcol[kAmgDenseMax];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int nn = n * n;
+  for (int e = tid; e < nn; e += nt) Ainv[e] = 0.0;
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) {
+    const int len = rowptr[i + 1] - rowptr[i];
+    const int base = slice_ptr[i >> 5] + (i & 31);
+    for (int k = 0; k < len; ++k) Ainv[i * n + col[base + 32 * k]] = val[base + 32 * k];
+  }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const double p = 1.0 / Ainv[k * n + k];
+    for (int j = tid; j < n; j += nt) {
+      shrow[j] = (j == k) ? p : Ainv[k * n + j] * p;
+      shcol[j] = Ainv[j * n + k];
+    }
+    __syncthreads();
+    for (int e = tid; e < nn; e += nt) {
+      const int i = e / n, j = e - i * n;
+      double v;
+      if (i == k) v = shrow[j];
+      else if (j == k) v = -(shcol[i] * p);
+      else v = Ainv[e] - shcol[i] * shrow[j];
+      Ainv[e] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// x = Ainv b on the coarsest level (one CTA; the inverse of a symmetric matrix is read column-wise = coalesced)
+__global__ void __launch_bounds__(kAmgDenseMax) k_amg_dense_apply(int n, const double* __restrict__ Ainv,
+                                                                const double* __restrict__ b, double* __restrict__ x,
+                                                                const PcgScalars* scal) {
+  __shared__ double shb[kAmgDenseMax];
+  if (scal->done) return;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) shb[j] = b[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += Ainv[j * n + i] * shb[j];
+    x[i] = s;
+  }
+}
+
+// ---- CG with a general preconditioner: control kernels -------------------------------------------------------
+// r = rhs - q (q = A x0) or r = rhs; sums {r.r, rhs.rhs}, max|r|
+template <bool HAVE_Q>
+__global__ void k_apcg_init(int n, const double* __restrict__ rhs, const double* __restrict__ q, double* __restrict__ r,
+                            double* partials, PcgScalars* scal) {
+  __shared__ double sh_red[32];
+  double s_rr = 0.0, s_bb = 0.0, s_max = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double bi = rhs[i];
+    const double ri = HAVE_Q ? bi - q[i] : bi;
+    r[i] = ri;
+    s_rr += ri * ri; s_bb += bi * bi;
+    s_max = fmax(s_max, fabs(ri));
+  }
+  double v[3] = {s_rr, s_bb, s_max}, tot[3];
+  if (grid_reduce_mixed<3, 4u>(v, partials, &scal->cnt[1], sh_red, tot)) {
+    if (threadIdx.x == 0) {
+      scal->rr = tot[0]; scal->bb = tot[1]; scal->rmax = tot[2];
+      scal->sums[2] = tot[0];
+    }
+  }
+}
+
+__global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf) {
+  scal->thresh2 = rtol * rtol * scal->bb;
+  scal->thresh_inf = atol_inf;
+  scal->iters = 0;
+  scal->breakdown = 0;
+  scal->done = (scal->rr <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
+}
+
+// x += alpha p; r -= alpha q; the block that finishes last takes the convergence decision, so that the cycle
+// kernels behind it exit immediately once the residual is small enough.
+__global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, int it, int max_it,
+                                                           const double* __restrict__ p, const double* __restrict__ q,
+                                                           double* __restrict__ x, double* __restrict__ r,
+                                                           double* partials, PcgScalars* scal) {
+  __shared__ double sh_red[32];
+  if (scal->done) return;
+  const double pq = scal->sums[0];
+  const double rz = scal->rz[par];
+  if (!(pq > 0.0) || !(rz == rz)) {   // operator (or preconditioner) not SPD, or NaN
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scal->breakdown = 1; scal->iters = it; }
+    // `done` is raised by the last block below so that no block can observe it before taking this branch
+    double v[1] = {0.0}, tot[1];
+    if (grid_reduce<1, false>(v, partials, &scal->cnt[1], sh_red, tot)) {
+      if (threadIdx.x == 0) scal->done = 1;
+    }
+    return;
+  }
+  const double alpha = rz / pq;
+  double s_rr = 0.0, s_max = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double xi = x[i] + alpha * p[i];
+    const double ri = r[i] - alpha * q[i];
+    x[i] = xi;
+    r[i] = ri;
+    s_rr += ri * ri;
+    s_max = fmax(s_max, fabs(ri));
+  }
+  double v[2] = {s_rr, s_max}, tot[2];
+  if (grid_reduce_mixed<2, 2u>(v, partials, &scal->cnt[1], sh_red, tot)) {
+    if (threadIdx.x == 0) {
+      scal->rr = tot[0];
+      scal->rmax = tot[1];
+      scal->iters = it + 1;
+      if (tot[0] <= scal->thresh2 || tot[1] <= scal->thresh_inf || it + 1 >= max_it || !(tot[0] == tot[0])) scal->done = 1;
+    }
+  }
+}
+
+// p = z + beta p  (first: p = z); r.z of this iteration was left in sums[1] by the last kernel of the cycle
+__global__ void __launch_bounds__(kVecBlock, 8) k_apcg_direction(int n, int par, int first, const double* __restrict__ z,
+                                                              double* __restrict__ p, PcgScalars* scal) {
+  if (scal->done) return;
+  const double rz_new = scal->sums[1];
+  const double beta = first ? 0.0 : rz_new / scal->rz[par];
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal->rz[first ? 0 : (par ^ 1)] = rz_new;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// setup / teardown
+// ------------------------------------------------------------------------------------------------------------
+bool amg_ready(const Context* ctx) { return ctx->amg && ctx->amg->ready; }
+
+void amg_free(Context* ctx) {
+  Amg* A = ctx->amg;
+  if (!A) return;
+  for (int l = 0; l < kAmgMaxLevels; ++l) {
+    AmgLevelDev& L = A->lv[l];
+    if (L.owns) { amg_release(L.slice_ptr); amg_release(L.col); amg_release(L.rowptr); }
+    amg_release(L.val); amg_release(L.dinv);
+    amg_release(L.Pptr); amg_release(L.Pcol); amg_release(L.Pval);
+    amg_release(L.Rptr); amg_release(L.Rrow); amg_release(L.Rval);
+    if (l > 0) { amg_release(L.b); amg_release(L.x2); }
+    amg_release(L.x); amg_release(L.t);
+  }
+  amg_release(A->dense);
+  amg_release(A->z);
+  delete A;
+  ctx->amg = nullptr;
+}
+
+int amg_setup(Context* ctx) {
+  amg_free(ctx);
+  if (ctx->nranks != 1 || !ctx->base_ready) return 0;   // multi-GPU: the Jacobi path stays in charge
+  const double t0 = wall_ms();
+  const Pattern& P = ctx->pat;
+  const int n = P.nrows;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  // fine pattern + base values -> host CSR
+  std::vector<int> rp(n + 1), cc(P.nnz), sp(P.nslices + 1);
+  std::vector<double> sv(P.nentries), vv(P.nnz);
+  std::vector<unsigned char> fixed(n);
+  DDPS_CUDA(cudaMemcpy(rp.data(), P.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(cc.data(), P.csrcol, cc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(sp.data(), P.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(sv.data(), ctx->val_base, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(fixed.data(), ctx->isD, fixed.size(), cudaMemcpyDeviceToHost));
+  for (int r = 0; r < n; ++r) {
+    const int base = sp[r >> 5], lane = r & 31;
+    for (int k = 0; k < rp[r + 1] - rp[r]; ++k) vv[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
+  }
+  sv.clear(); sv.shrink_to_fit();
+  AmgHost H;
+  AmgParams prm;
+  const int nlev = amg_host_build(H, n, std::move(rp), std::move(cc), std::move(vv), fixed.data(), prm);
+  if (nlev < 2 || nlev > kAmgMaxLevels || H.lv.back().n > kAmgDenseMax) return 0;   // no hierarchy: Jacobi-PCG stays
+
+  Amg* A = new Amg();
+  ctx->amg = A;
+  A->nlev = nlev;
+  A->omega = prm.omega;
+  int rc;
+  for (int l = 0; l < nlev; ++l) {
+    const AmgHostLevel& HL = H.lv[l];
+    AmgLevelDev& L = A->lv[l];
+    L.n = HL.n;
+    L.nnz = (int64_t)HL.col.size();
+    if (l == 0) {
+      L.nslices = P.nslices; L.nentries = P.nentries;
+      L.slice_ptr = P.slice_ptr; L.col = P.col; L.rowptr = P.rowptr; L.owns = false;
+    } else {
+      // SELL-32 layout of the coarse pattern (same convention as the fine pattern: padding = value 0, own column)
+      L.nslices = (HL.n + 31) / 32;
+      std::vector<int> hsp(L.nslices + 1, 0);
+      for (int s = 0; s < L.nslices; ++s) {
+        int w = 0;
+        for (int r = s * 32; r < std::min(HL.n, s * 32 + 32); ++r) w = std::max(w, HL.rowptr[r + 1] - HL.rowptr[r]);
+        hsp[s + 1] = hsp[s] + 32 * w;
+      }
+      L.nentries = hsp[L.nslices];
+      std::vector<int> hcol((size_t)L.nentries, 0);
+      for (int s = 0; s < L.nslices; ++s) {
+        const int w = (hsp[s + 1] - hsp[s]) / 32;
+        for (int lane = 0; lane < 32; ++lane) {
+          const int r = s * 32 + lane;
+          const int beg = r < HL.n ? HL.rowptr[r] : 0, len = r < HL.n ? HL.rowptr[r + 1] - beg : 0;
+          const int self = r < HL.n ? r : 0;
+          for (int k = 0; k < w; ++k) hcol[(size_t)hsp[s] + 32 * k + lane] = k < len ? HL.col[beg + k] : self;
+        }
+      }
+      L.owns = true;
+      if ((rc = amg_upload(ctx, &L.slice_ptr, hsp)) || (rc = amg_upload(ctx, &L.col, hcol)) ||
+          (rc = amg_upload(ctx, &L.rowptr, HL.rowptr)))
+        return rc;
+      if ((rc = amg_alloc(ctx, &L.val, (size_t)L.nentries)) || (rc = amg_alloc(ctx, &L.dinv, (size_t)L.n))) return rc;
+      DDPS_CUDA(cudaMemsetAsync(L.val, 0, std::max<size_t>((size_t)L.nentries, 1) * sizeof(double), ctx->stream));
+      DDPS_CUDA(cudaMemsetAsync(L.dinv, 0, std::max<size_t>((size_t)L.n, 1) * sizeof(double), ctx->stream));
+      if ((rc = amg_alloc(ctx, &L.b, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.x2, (size_t)L.n))) return rc;
+      A->h_rowptr[l] = HL.rowptr;
+      A->h_slice_ptr[l] = hsp;
+    }
+    if ((rc = amg_alloc(ctx, &L.x, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.t, (size_t)L.n))) return rc;
+    if (l + 1 < nlev) {
+      L.nc = HL.nc;
+      if ((rc = amg_upload(ctx, &L.Pptr, HL.Pptr)) || (rc = amg_upload(ctx, &L.Pcol, HL.Pcol)) ||
+          (rc = amg_upload(ctx, &L.Pval, HL.Pval)) || (rc = amg_upload(ctx, &L.Rptr, HL.Rptr)) ||
+          (rc = amg_upload(ctx, &L.Rrow, HL.Rrow)) || (rc = amg_upload(ctx, &L.Rval, HL.Rval)))
+        return rc;
+    }
+    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));   // the host vectors of this level go out of scope
+  }
+  const int nL = A->lv[nlev - 1].n;
+  if ((rc = amg_alloc(ctx, &A->dense, (size_t)nL * nL))) return rc;
+  if ((rc = amg_alloc(ctx, &A->z, (size_t)n))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  A->ready = true;
+  A->setup_ms = wall_ms() - t0;
+  return 0;
+}
+
+int amg_debug_levels(Context* ctx, int64_t* nlevels, int64_t* sizes, int cap) {
+  if (nlevels) *nlevels = amg_ready(ctx) ? ctx->amg->nlev : 0;
+  if (sizes && amg_ready(ctx))
+    for (int l = 0; l < ctx->amg->nlev && l < cap; ++l) sizes[l] = ctx->amg->lv[l].n;
+  return 0;
+}
+
+// values (CSR order of the level's pattern) and inverse diagonal of level >= 1 after the last amg_numeric
+int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv) {
+  if (!amg_ready(ctx) || level < 1 || level >= ctx->amg->nlev) { ctx->fail(DDPS_ERR_ARG, "no such multigrid level"); return DDPS_ERR_ARG; }
+  Amg& A = *ctx->amg;
+  const AmgLevelDev& L = A.lv[level];
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<double> sv((size_t)L.nentries);
+  DDPS_CUDA(cudaMemcpy(sv.data(), L.val, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const std::vector<int>& rp = A.h_rowptr[level];
+  const std::vector<int>& sp = A.h_slice_ptr[level];
+  if (val_csr)
+    for (int r = 0; r < L.n; ++r)
+      for (int k = 0; k < rp[r + 1] - rp[r]; ++k) val_csr[rp[r] + k] = sv[(size_t)sp[r >> 5] + 32 * k + (r & 31)];
+  if (dinv) DDPS_CUDA(cudaMemcpy(dinv, L.dinv, (size_t)L.n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-operator numeric phase and the V-cycle
+// ------------------------------------------------------------------------------------------------------------
+int amg_numeric(Context* ctx, const double* val, const double* dinv) {
+  Amg& A = *ctx->amg;
+  A.lv[0].cur_val = val;
+  A.lv[0].cur_dinv = dinv;
+  for (int l = 0; l + 1 < A.nlev; ++l) {
+    AmgLevelDev& F = A.lv[l];
+    AmgLevelDev& C = A.lv[l + 1];
+    const int grid = amg_grid(ctx, (int64_t)C.n * 32, 256);
+    k_amg_rap<<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr, F.Rrow,
+                                             F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+    C.cur_val = C.val;
+    C.cur_dinv = C.dinv;
+    ctx->stats.kernel_launches++;
+  }
+  const AmgLevelDev& L = A.lv[A.nlev - 1];
+  k_amg_dense_inverse<<<1, 1024, 0, ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, A.dense);
+  ctx->stats.kernel_launches++;
+  DDPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int MODE, bool DOT>
+static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x, const double* b, double om, double* y) {
+  const int grid = amg_grid(ctx, (int64_t)L.nslices * 32, kVecBlock);
+  k_amg_spmv<MODE, DOT><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur_val, x, b, L.cur_dinv,
+                                                            om, y, ctx->partials, ctx->scal);
+  ctx->stats.kernel_launches++;
+  ctx->stats.spmv_total++;
+}
+
+// z = B r: one V(1,1) cycle from the zero initial guess.  dot_rz: also leave r.z in scal->sums[1].
+int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz) {
+  Amg& A = *ctx->amg;
+  const double om = A.omega;
+  cudaStream_t st = ctx->stream;
+  A.lv[0].b = const_cast<double*>(r);
+  A.lv[0].x2 = z;
+  for (int l = 0; l + 1 < A.nlev; ++l) {
+    AmgLevelDev& L = A.lv[l];
+    k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);
+    launch_amg_spmv<1, false>(ctx, L, L.x, L.b, om, L.t);
+    k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rrow, L.Rval, L.t, A.lv[l + 1].b, ctx->scal);
+    ctx->stats.kernel_launches += 2;
+  }
+  {
+    AmgLevelDev& L = A.lv[A.nlev - 1];
+    k_amg_dense_apply<<<1, kAmgDenseMax, 0, st>>>(L.n, A.dense, L.b, L.x2, ctx->scal);
+    ctx->stats.kernel_launches++;
+  }
+  for (int l = A.nlev - 2; l >= 0; --l) {
+    AmgLevelDev& L = A.lv[l];
+    k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pcol, L.Pval, A.lv[l + 1].x2, L.x, ctx->scal);
+    ctx->stats.kernel_launches++;
+    if (l == 0 && dot_rz) launch_amg_spmv<2, true>(ctx, L, L.x, L.b, om, L.x2);
+    else launch_amg_spmv<2, false>(ctx, L, L.x, L.b, om, L.x2);
+  }
+  DDPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CG preconditioned with the V-cycle
+// ------------------------------------------------------------------------------------------------------------
+int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it) {
+  Amg& A = *ctx->amg;
+  const int n = ctx->n_own;
+  const int par = it & 1;
+  int rc;
+  const int g2 = amg_grid(ctx, n, kVecBlock);
+  if ((rc = launch_spmv_dot(ctx, A.lv[0].cur_val, ctx->p, ctx->q))) return rc;    // q = A p, p.q -> sums[0]
+  k_apcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, ctx->partials, ctx->scal);
+  if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;                        // z = B r, r.z -> sums[1]
+  k_apcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, 0, A.z, ctx->p, ctx->scal);
+  ctx->stats.kernel_launches += 2;
+  return 0;
+}
+
+int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
+                  double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out) {
+  Amg& A = *ctx->amg;
+  const int n = ctx->n_own;
+  int rc;
+  if (max_it <= 0) max_it = 200000;
+  if (max_it > 2000000000LL) max_it = 2000000000LL;
+  cudaStream_t st = ctx->stream;
+  if ((rc = amg_numeric(ctx, val, dinv))) return rc;
+  const int g = amg_grid(ctx, std::max(n, 1), kVecBlock);
+  if (x0_nonzero) {
+    DDPS_CUDA(cudaMemcpyAsync(ctx->p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_spmv(ctx, val, ctx->p, ctx->q))) return rc;
+    k_apcg_init<true><<<g, kVecBlock, 0, st>>>(n, rhs, ctx->q, ctx->r, ctx->partials, ctx->scal);
+  } else {
+    DDPS_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), st));
+    k_apcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, ctx->r, ctx->partials, ctx->scal);
+  }
+  k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf);
+  if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;
+  k_apcg_direction<<<g, kVecBlock, 0, st>>>(n, 0, 1, A.z, ctx->p, ctx->scal);
+  ctx->stats.kernel_launches += 3;
+  DDPS_CUDA(cudaGetLastError());
+
+  int64_t it = 0;
+  const int chunk = 4;   // iterations enqueued between two polls of the device-side done flag
+  while (true) {
+    DDPS_CUDA(cudaMemcpyAsync(ctx->scal_host, ctx->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    DDPS_CUDA(cudaStreamSynchronize(st));
+    if (ctx->scal_host->done || it >= max_it) break;
+    const int nrun = (int)std::min<int64_t>(chunk, max_it - it);
+    for (int j = 0; j < nrun; ++j, ++it)
+      if ((rc = amg_pcg_iteration_launch(ctx, x, (int)it, (int)max_it))) return rc;
+    DDPS_CUDA(cudaGetLastError());
+  }
+  const PcgScalars& S = *ctx->scal_host;
+  if (iters_out) *iters_out = S.iters;
+  if (relres_out) *relres_out = (S.bb > 0) ? sqrt(S.rr / S.bb) : 0.0;
+  ctx->stats.pcg_total += S.iters;
+  ctx->hist_pcg.push_back((double)S.iters);
+  if (S.breakdown) {
+    ctx->fail(DDPS_ERR_BREAKDOWN, "PCG breakdown: p.Ap <= 0 (operator not SPD; u or v negative? SURVEY H3)");
+    return DDPS_ERR_BREAKDOWN;
+  }
+  if (!(S.rr <= S.thresh2 || S.rmax <= S.thresh_inf) && !ctx->opts.lin_cap_ok) {
+    ctx->fail(DDPS_ERR_NOCONV, "AMG-PCG hit the iteration cap (" + std::to_string(S.iters) + " its, relres " +
+                                   std::to_string(S.bb > 0 ? sqrt(S.rr / S.bb) : 0.0) + ")");
+    return DDPS_ERR_NOCONV;
+  }
+  return 0;
+}
+
+}  // namespace ddps

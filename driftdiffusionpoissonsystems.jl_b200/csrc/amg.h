@@ -1,0 +1,40 @@
+// Smoothed-aggregation multigrid preconditioner: host-side hierarchy structures
+// shared by amg_host.cu (setup, no device code) and amg.cu (device kernels + the AMG-preconditioned CG).
+#pragma once
+
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/ddps.h"
+
+namespace ddps {
+
+struct AmgParams {
+  double theta = 0.25;      // strength threshold
+  double omega = 2.0 / 3.0; // prolongator smoothing + Jacobi smoother damping
+  int coarse_max = 400;     // stop coarsening at this size (dense inverse on the device, cap kAmgDenseMax)
+  int max_levels = 12;
+  int nthreads = 0;         // 0: min(16, hardware concurrency)
+};
+
+struct AmgHostLevel {
+  int n = 0;
+  std::vector<int> rowptr, col;   // CSR pattern, sorted columns (level 0: the fixed P1 pattern)
+  std::vector<double> val;        // BASE operator values at this level (strength + prolongator smoothing)
+  int nc = 0;                     // rows of the next level (0 on the coarsest level)
+  std::vector<int> agg;           // [n] aggregate id or -1
+  std::vector<int> Pptr, Pcol;    // prolongator [n x nc], CSR
+  std::vector<double> Pval;
+  std::vector<int> Rptr, Rrow;    // its transpose [nc x n], CSR, fine indices increasing inside a row
+  std::vector<double> Rval;
+};
+
+struct AmgHost {
+  std::vector<AmgHostLevel> lv;
+};
+
+int amg_host_build(AmgHost& H, int n, std::vector<int>&& rowptr, std::vector<int>&& col, std::vector<double>&& val,
+                   const unsigned char* fixed, const AmgParams& prm);
+
+}  // namespace ddps

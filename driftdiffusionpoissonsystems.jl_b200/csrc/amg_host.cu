@@ -1,0 +1,312 @@
+// Host-side setup of the smoothed-aggregation multigrid hierarchy (a better
+// preconditioner behind the same PCG interface, replacing the reference's `\` at src:394,588,1063).
+//
+// This file contains NO device code: it is the one-time, per-mesh symbolic/numeric setup that freezes the
+// transfer operators.  Per level it
+//   1. marks strong couplings of the BASE operator (the constant stiffness MV / semlin M, src:284,1028):
+//      -a_ij >= theta * max_k(-a_ik);
+//   2. aggregates the nodes greedily (root + all strong neighbours, leftovers join the strongest neighbouring
+//      aggregate) -- sequential, hence deterministic; Dirichlet rows ("fixed") are left out: their rows are
+//      identity rows (src:277-284) and are handled by the smoother alone;
+//   3. smooths the piecewise-constant tentative prolongator with one damped-Jacobi step of the base operator,
+//      P = (I - omega D^-1 A) T;
+//   4. stores R = P^T row-wise (so that restriction and the Galerkin product are deterministic gathers) and
+//      forms the coarse base operator R A P with a row-parallel marker-array product.
+// The per-operator work (Galerkin products of the CURRENT operator M - J0 on the frozen pattern, smoothing,
+// transfers, coarse solve) runs on the device (amg.cu).  Everything here is reachable WITHOUT a GPU through the
+// ddps_amg_host_* entry points so that the CPU test-suite can check it against scipy.
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <thread>
+#include <vector>
+
+#include "amg.h"
+
+namespace ddps {
+
+namespace {
+
+template <typename F>
+void parallel_ranges(int64_t n, int nthreads, F&& fn) {
+  nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, (n + 4095) / 4096));
+  if (nthreads <= 1) { fn(0, (int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    const int64_t lo = std::min<int64_t>(n, t * chunk), hi = std::min<int64_t>(n, lo + chunk);
+    th.emplace_back([&fn, t, lo, hi]() { fn(t, lo, hi); });
+  }
+  for (auto& x : th) x.join();
+}
+
+// strong[k] = 1 when entry k (row i, column j != i) is a strong negative coupling of row i
+void mark_strong(const AmgHostLevel& L, const unsigned char* fixed, double theta, int nthreads, std::vector<unsigned char>& strong) {
+  strong.assign(L.col.size(), 0);
+  parallel_ranges(L.n, nthreads, [&](int, int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      if (fixed && fixed[i]) continue;
+      double m = 0.0;
+      for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+        const int j = L.col[k];
+        if (j != i && !(fixed && fixed[j])) m = std::max(m, -L.val[k]);
+      }
+      if (!(m > 0.0)) continue;
+      const double cut = theta * m;
+      for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+        const int j = L.col[k];
+        if (j != i && !(fixed && fixed[j]) && -L.val[k] >= cut) strong[k] = 1;
+      }
+    }
+  });
+}
+
+// Greedy aggregation (sequential: the result is a pure function of the matrix).  Returns the number of aggregates.
+int aggregate(const AmgHostLevel& L, const std::vector<unsigned char>& strong, std::vector<int>& agg) {
+  const int n = L.n;
+  agg.assign(n, -1);
+  int nc = 0;
+  // pass 1: a node whose strong neighbourhood is still free becomes the root of a new aggregate
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    bool any = false, free_nb = true;
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+      if (!strong[k]) continue;
+      any = true;
+      if (agg[L.col[k]] >= 0) { free_nb = false; break; }
+    }
+    if (!any || !free_nb) continue;
+    agg[i] = nc;
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
+      if (strong[k]) agg[L.col[k]] = nc;
+    ++nc;
+  }
+  // pass 2: leftovers join the pass-1 aggregate they are most strongly coupled to (no chaining: decisions use
+  // the pass-1 state only)
+  std::vector<int> join(n, -1);
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    double best = 0.0;
+    int pick = -1;
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+      if (!strong[k]) continue;
+      const int a = agg[L.col[k]];
+      if (a >= 0 && -L.val[k] > best) { best = -L.val[k]; pick = a; }
+    }
+    join[i] = pick;
+  }
+  for (int i = 0; i < n; ++i)
+    if (agg[i] < 0 && join[i] >= 0) agg[i] = join[i];
+  // pass 3: what is still free (strongly coupled only to other leftovers) forms new aggregates
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    bool any = false;
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
+      if (strong[k]) { any = true; break; }
+    if (!any) continue;   // isolated row (diagonally dominant): smoother only
+    agg[i] = nc;
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
+      if (strong[k] && agg[L.col[k]] < 0) agg[L.col[k]] = nc;
+    ++nc;
+  }
+  return nc;
+}
+
+// P = (I - omega D^-1 A) T with T the piecewise-constant tentative prolongator; rows of fixed nodes stay empty
+void smooth_prolongator(AmgHostLevel& L, const unsigned char* fixed, double omega, int nthreads) {
+  const int n = L.n;
+  std::vector<int> len(n, 0);
+  const int nt = std::max(1, nthreads);
+  std::vector<std::vector<int>> tcol(nt);
+  std::vector<std::vector<double>> tval(nt);
+  std::vector<int64_t> tlo(nt, 0), thi(nt, 0);
+  parallel_ranges(n, nt, [&](int t, int64_t lo, int64_t hi) {
+    tlo[t] = lo; thi[t] = hi;
+    std::vector<std::pair<int, double>> row;
+    for (int64_t i = lo; i < hi; ++i) {
+      row.clear();
+      if (!(fixed && fixed[i])) {
+        double d = 0.0;
+        for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
+          if (L.col[k] == i) d = L.val[k];
+        if (L.agg[i] >= 0) row.emplace_back(L.agg[i], 1.0 - omega);
+        if (d != 0.0) {
+          for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+            const int j = L.col[k];
+            if (j == i || L.val[k] == 0.0 || L.agg[j] < 0) continue;
+            row.emplace_back(L.agg[j], -omega * L.val[k] / d);
+          }
+        }
+        std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+      }
+      int cnt = 0;
+      for (size_t q = 0; q < row.size();) {
+        double s = 0.0;
+        size_t e = q;
+        while (e < row.size() && row[e].first == row[q].first) s += row[e++].second;
+        tcol[t].push_back(row[q].first);
+        tval[t].push_back(s);
+        ++cnt;
+        q = e;
+      }
+      len[i] = cnt;
+    }
+  });
+  L.Pptr.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) L.Pptr[i + 1] = L.Pptr[i] + len[i];
+  L.Pcol.resize(L.Pptr[n]);
+  L.Pval.resize(L.Pptr[n]);
+  for (int t = 0; t < nt; ++t) {
+    if (thi[t] <= tlo[t]) continue;
+    std::copy(tcol[t].begin(), tcol[t].end(), L.Pcol.begin() + L.Pptr[tlo[t]]);
+    std::copy(tval[t].begin(), tval[t].end(), L.Pval.begin() + L.Pptr[tlo[t]]);
+  }
+}
+
+void transpose_prolongator(AmgHostLevel& L) {
+  const int n = L.n, nc = L.nc;
+  L.Rptr.assign(nc + 1, 0);
+  for (size_t k = 0; k < L.Pcol.size(); ++k) L.Rptr[L.Pcol[k] + 1]++;
+  for (int I = 0; I < nc; ++I) L.Rptr[I + 1] += L.Rptr[I];
+  L.Rrow.resize(L.Pcol.size());
+  L.Rval.resize(L.Pcol.size());
+  std::vector<int> fill(L.Rptr.begin(), L.Rptr.end() - 1);
+  for (int i = 0; i < n; ++i)
+    for (int k = L.Pptr[i]; k < L.Pptr[i + 1]; ++k) {
+      const int pos = fill[L.Pcol[k]]++;
+      L.Rrow[pos] = i;          // increasing fine index inside every coarse row
+      L.Rval[pos] = L.Pval[k];
+    }
+}
+
+// C = R A P, row-parallel, columns sorted.  Structural zeros of A are kept (the current operator M - J0 has
+// nonzeros where the base stiffness of a right-angle mesh has exact zeros).
+void galerkin(const AmgHostLevel& L, AmgHostLevel& C, int nthreads) {
+  const int nc = L.nc;
+  C.n = nc;
+  std::vector<int> len(nc, 0);
+  const int nt = std::max(1, nthreads);
+  std::vector<std::vector<int>> tcol(nt);
+  std::vector<std::vector<double>> tval(nt);
+  std::vector<int64_t> tlo(nt, 0), thi(nt, 0);
+  parallel_ranges(nc, nt, [&](int t, int64_t lo, int64_t hi) {
+    tlo[t] = lo; thi[t] = hi;
+    std::vector<int> marker(nc, -1), list;
+    std::vector<double> acc(nc, 0.0);
+    for (int64_t I = lo; I < hi; ++I) {
+      list.clear();
+      for (int q = L.Rptr[I]; q < L.Rptr[I + 1]; ++q) {
+        const int i = L.Rrow[q];
+        const double r = L.Rval[q];
+        for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+          const int j = L.col[k];
+          const double ra = r * L.val[k];
+          for (int m = L.Pptr[j]; m < L.Pptr[j + 1]; ++m) {
+            const int J = L.Pcol[m];
+            if (marker[J] != (int)I) { marker[J] = (int)I; acc[J] = 0.0; list.push_back(J); }
+            acc[J] += ra * L.Pval[m];
+          }
+        }
+      }
+      std::sort(list.begin(), list.end());
+      for (int J : list) { tcol[t].push_back(J); tval[t].push_back(acc[J]); }
+      len[I] = (int)list.size();
+    }
+  });
+  C.rowptr.assign(nc + 1, 0);
+  for (int I = 0; I < nc; ++I) C.rowptr[I + 1] = C.rowptr[I] + len[I];
+  C.col.resize(C.rowptr[nc]);
+  C.val.resize(C.rowptr[nc]);
+  for (int t = 0; t < nt; ++t) {
+    if (thi[t] <= tlo[t]) continue;
+    std::copy(tcol[t].begin(), tcol[t].end(), C.col.begin() + C.rowptr[tlo[t]]);
+    std::copy(tval[t].begin(), tval[t].end(), C.val.begin() + C.rowptr[tlo[t]]);
+  }
+}
+
+}  // namespace
+
+int amg_host_build(AmgHost& H, int n, std::vector<int>&& rowptr, std::vector<int>&& col, std::vector<double>&& val,
+                   const unsigned char* fixed, const AmgParams& prm) {
+  H.lv.clear();
+  H.lv.emplace_back();
+  H.lv[0].n = n;
+  H.lv[0].rowptr = std::move(rowptr);
+  H.lv[0].col = std::move(col);
+  H.lv[0].val = std::move(val);
+  int nthreads = prm.nthreads > 0 ? prm.nthreads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  while ((int)H.lv.size() < prm.max_levels) {
+    AmgHostLevel& L = H.lv.back();
+    if (L.n <= prm.coarse_max) break;
+    const unsigned char* fx = H.lv.size() == 1 ? fixed : nullptr;
+    std::vector<unsigned char> strong;
+    mark_strong(L, fx, prm.theta, nthreads, strong);
+    const int nc = aggregate(L, strong, L.agg);
+    if (nc <= 0 || nc > 0.7 * L.n) { L.agg.clear(); break; }   // coarsening stalled
+    L.nc = nc;
+    smooth_prolongator(L, fx, prm.omega, nthreads);
+    transpose_prolongator(L);
+    AmgHostLevel C;
+    galerkin(L, C, nthreads);
+    H.lv.push_back(std::move(C));
+  }
+  return (int)H.lv.size();
+}
+
+}  // namespace ddps
+
+// ------------------------------------------------------------------------------------------------------------
+// host-only C ABI (no CUDA context needed): used by the CPU tests to check the hierarchy against scipy
+// ------------------------------------------------------------------------------------------------------------
+struct ddps_amg_host : public ddps::AmgHost {};
+
+extern "C" {
+
+int ddps_amg_host_create(ddps_amg_host** out, int64_t n, const int64_t* rowptr, const int64_t* col, const double* val,
+                         const uint8_t* fixed, int nthreads, int coarse_max) {
+  if (!out || !rowptr || !col || !val || n <= 0 || n > 2000000000LL) return DDPS_ERR_ARG;
+  if (rowptr[n] > 2000000000LL) return DDPS_ERR_ARG;
+  ddps_amg_host* h = new ddps_amg_host();
+  std::vector<int> rp(n + 1), cc(rowptr[n]);
+  std::vector<double> vv(val, val + rowptr[n]);
+  for (int64_t i = 0; i <= n; ++i) rp[i] = (int)rowptr[i];
+  for (int64_t k = 0; k < rowptr[n]; ++k) cc[k] = (int)col[k];
+  ddps::AmgParams prm;
+  prm.nthreads = nthreads;
+  if (coarse_max > 0) prm.coarse_max = coarse_max;
+  ddps::amg_host_build(*h, (int)n, std::move(rp), std::move(cc), std::move(vv), fixed, prm);
+  *out = h;
+  return DDPS_OK;
+}
+
+int ddps_amg_host_nlevels(const ddps_amg_host* h) { return h ? (int)h->lv.size() : DDPS_ERR_ARG; }
+
+/* sizes = {n, nnz, nc (0 on the coarsest level), nnz(P)} */
+int ddps_amg_host_level_sizes(const ddps_amg_host* h, int level, int64_t sizes[4]) {
+  if (!h || level < 0 || level >= (int)h->lv.size() || !sizes) return DDPS_ERR_ARG;
+  const ddps::AmgHostLevel& L = h->lv[level];
+  sizes[0] = L.n;
+  sizes[1] = (int64_t)L.col.size();
+  sizes[2] = L.Pptr.empty() ? 0 : L.nc;
+  sizes[3] = (int64_t)L.Pcol.size();
+  return DDPS_OK;
+}
+
+int ddps_amg_host_level_get(const ddps_amg_host* h, int level, int64_t* rowptr, int64_t* col, double* val, int64_t* Pptr,
+                            int64_t* Pcol, double* Pval, int64_t* agg) {
+  if (!h || level < 0 || level >= (int)h->lv.size()) return DDPS_ERR_ARG;
+  const ddps::AmgHostLevel& L = h->lv[level];
+  if (rowptr) for (size_t i = 0; i < L.rowptr.size(); ++i) rowptr[i] = L.rowptr[i];
+  if (col) for (size_t i = 0; i < L.col.size(); ++i) col[i] = L.col[i];
+  if (val) for (size_t i = 0; i < L.val.size(); ++i) val[i] = L.val[i];
+  if (Pptr) for (size_t i = 0; i < L.Pptr.size(); ++i) Pptr[i] = L.Pptr[i];
+  if (Pcol) for (size_t i = 0; i < L.Pcol.size(); ++i) Pcol[i] = L.Pcol[i];
+  if (Pval) for (size_t i = 0; i < L.Pval.size(); ++i) Pval[i] = L.Pval[i];
+  if (agg) for (size_t i = 0; i < L.agg.size(); ++i) agg[i] = L.agg[i];
+  return DDPS_OK;
+}
+
+void ddps_amg_host_free(ddps_amg_host* h) { delete h; }
+
+}  // extern "C"

@@ -33,6 +33,7 @@ template <typename T>
 void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
 void free_mesh(Context* ctx) {
+  amg_free(ctx);
   p2p_teardown(ctx);
   free_pattern(ctx);
   dev_free(ctx->xy); dev_free(ctx->elem); dev_free(ctx->d_own_glob);
@@ -269,6 +270,19 @@ int assemble_base(Context* ctx, bool semlin) {
   if ((rc = launch_assemble_base(ctx, a))) return rc;
   ctx->base_ready = true;
   ctx->base_is_semlin = semlin;
+  return 0;
+}
+
+// Multigrid hierarchy of the freshly assembled base operator (opt-in, single GPU): SURVEY 8f rank 1
+int maybe_amg_setup(Context* ctx) {
+  ctx->stats.amg_levels = 0;
+  if (ctx->opts.precond != DDPS_PRECOND_AMG) { amg_free(ctx); return 0; }
+  if (ctx->nranks != 1) return 0;
+  int rc = amg_setup(ctx);
+  if (rc) return rc;
+  int64_t nl = 0;
+  amg_debug_levels(ctx, &nl, nullptr, 0);
+  ctx->stats.amg_levels = (int32_t)nl;
   return 0;
 }
 
@@ -781,6 +795,11 @@ int ddps_ddpe_begin(ddps_ctx* ctx, int rec_mode, double delta, double tau_p, dou
   ctx->rec_mode = rec_mode; ctx->delta = delta; ctx->tau_p = tau_p; ctx->tau_n = tau_n; ctx->tol = tol;
   reset_stats(ctx);
   if ((rc = assemble_base(ctx, false))) return rc;                              // src:643, once per solve
+  {
+    const double ta = now_ms();
+    if ((rc = maybe_amg_setup(ctx))) return rc;
+    ctx->stats.t_amg_setup_ms = now_ms() - ta;
+  }
   const size_t bytes = (size_t)ctx->n_loc * sizeof(double);
   DDPS_CUDA(cudaMemsetAsync(ctx->U, 0, bytes, ctx->stream));                     // src:635-637
   DDPS_CUDA(cudaMemsetAsync(ctx->W, 0, bytes, ctx->stream));
@@ -861,6 +880,11 @@ int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats
   ctx->ddpe_active = false;
   double t0 = now_ms();
   if ((rc = assemble_base(ctx, true))) return rc;                                            // src:924-1028
+  {
+    const double ta = now_ms();
+    if ((rc = maybe_amg_setup(ctx))) return rc;
+    ctx->stats.t_amg_setup_ms = now_ms() - ta;
+  }
   DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:948
   const int cap = ctx->opts.max_newton > 0 ? ctx->opts.max_newton : 1000;
   int count = 0;
@@ -993,7 +1017,7 @@ int ddps_debug_assemble_base(ddps_ctx* ctx, int use_semlin) {
   if ((rc = require_mesh(ctx))) return rc;
   if ((rc = assemble_base(ctx, use_semlin != 0))) return rc;
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
-  return DDPS_OK;
+  return maybe_amg_setup(ctx);
 }
 
 int ddps_debug_assemble_newton(ddps_ctx* ctx, int use_semlin, double delta, const double* V, const double* u,
@@ -1053,6 +1077,46 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
   return rc ? rc : rc3;
 }
 
+// ---- multigrid debug exports -----------------------------------------------------------------------
+int ddps_amg_levels(ddps_ctx* ctx, int64_t* nlevels, int64_t* sizes) {
+  if (!ctx || !nlevels) return DDPS_ERR_ARG;
+  return amg_debug_levels(ctx, nlevels, sizes, 16);
+}
+
+int ddps_amg_numeric(ddps_ctx* ctx, int which) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (!amg_ready(ctx)) { ctx->fail(DDPS_ERR_STATE, "no multigrid hierarchy (set opts.precond = DDPS_PRECOND_AMG before the base assembly)"); return DDPS_ERR_STATE; }
+  if (which == DDPS_MAT_BASE) {
+    // inverse diagonal of the base operator: the assembled dinv belongs to DDPS_MAT_OP, so take it from a unit solve
+    ctx->fail(DDPS_ERR_ARG, "numeric phase runs on DDPS_MAT_OP (assemble an operator first)");
+    return DDPS_ERR_ARG;
+  }
+  if ((rc = amg_numeric(ctx, ctx->val_op, ctx->dinv))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DDPS_OK;
+}
+
+int ddps_amg_get_values(ddps_ctx* ctx, int level, double* val, double* dinv) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return amg_debug_get_values(ctx, level, val, dinv);
+}
+
+int ddps_amg_apply(ddps_ctx* ctx, const double* r, double* z) {
+  if (!ctx || !r || !z) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (!amg_ready(ctx)) { ctx->fail(DDPS_ERR_STATE, "no multigrid hierarchy"); return DDPS_ERR_STATE; }
+  if ((rc = upload_owned(ctx, ctx->r, r))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
+  if ((rc = amg_vcycle(ctx, ctx->r, ctx->q, false))) return rc;
+  return download_owned(ctx, ctx->q, z);
+}
+
 // ---- kernel timing on the library stream --------------------------------------------------------
 int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_per_launch, double* algo_bytes) {
   if (!ctx || reps <= 0) return DDPS_ERR_ARG;
@@ -1070,6 +1134,9 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
       case 3: return assemble_newton(ctx, false, ctx->delta, ctx->V, ctx->U0, ctx->W0);
       case 4: return assemble_base(ctx, ctx->base_is_semlin);
       case 5: return launch_spmv_dot(ctx, ctx->last_val ? ctx->last_val : ctx->val_op, ctx->p, ctx->q);
+      case 6: return amg_pcg_iteration_launch(ctx, ctx->x, it, 1 << 30);
+      case 7: return amg_numeric(ctx, ctx->val_op, ctx->dinv);
+      case 8: return amg_vcycle(ctx, ctx->r, ctx->q, false);
     }
     ctx->fail(DDPS_ERR_ARG, "unknown kernel id");
     return DDPS_ERR_ARG;
@@ -1083,6 +1150,16 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
     case 3: bytes = 12.0 * nme + 16.0 * nq + 3 * 8.0 * nq + 24.0 * nme + 12.0 * nnz + 8.0 * nnz + 16.0 * nq; break;  // 134 B/triangle
     case 4: bytes = 12.0 * nme + 16.0 * nq + 8.0 * nme + 8.0 * nnz + 8.0 * nq; break;
     case 5: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq; break;
+  }
+  if (kernel >= 6 && kernel <= 8) {
+    if (!amg_ready(ctx)) { ctx->fail(DDPS_ERR_STATE, "no multigrid hierarchy (opts.precond = DDPS_PRECOND_AMG and a base assembly first)"); return DDPS_ERR_STATE; }
+    // fresh state on the last assembled system: one capped solve leaves r, p, z and the scalars consistent
+    const int32_t keep = ctx->opts.lin_cap_ok;
+    ctx->opts.lin_cap_ok = 1;
+    rc = amg_pcg_solve(ctx, ctx->val_op, ctx->dinv, ctx->b, ctx->x, false, 0.0, -1.0, 2, nullptr, nullptr);
+    ctx->opts.lin_cap_ok = keep;
+    if (rc) return rc;
+    DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
   }
   if (kernel == 5) DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
   if (kernel == 2) {

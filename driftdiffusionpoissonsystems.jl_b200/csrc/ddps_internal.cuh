@@ -136,6 +136,8 @@ struct HaloPlan {
   int nsend = 0;
 };
 
+struct Amg;   // amg.cu: device-side smoothed-aggregation hierarchy
+
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -209,6 +211,9 @@ struct Context {
   double delta = 1, tau_p = 1, tau_n = 1, tol = 1e-9;
 
   std::vector<double> hist_outer, hist_newton, hist_pcg;
+
+  // optional multigrid preconditioner (opts.precond == DDPS_PRECOND_AMG, single GPU)
+  Amg* amg = nullptr;
 
   void fail(int code, const std::string& msg) {
     err_code = code;
@@ -290,6 +295,19 @@ int solve_system(Context* ctx, const double* val, const double* dinv, const doub
                  double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);
 int pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
               double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);
+
+// ---- amg.cu ----
+int amg_setup(Context* ctx);      // build the hierarchy from the base operator (after assemble_base); host + uploads
+void amg_free(Context* ctx);
+bool amg_ready(const Context* ctx);
+// per-operator numeric phase: Galerkin products of `val` on the frozen pattern + coarsest-level inverse
+int amg_numeric(Context* ctx, const double* val, const double* dinv);
+int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz);
+int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
+                  double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);
+int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it);
+int amg_debug_levels(Context* ctx, int64_t* nlevels, int64_t* sizes, int cap);
+int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv);
 
 // ---- comm.cu ----
 int halo_exchange(Context* ctx, double* vec);            // fill ghost part of a [n_loc] vector

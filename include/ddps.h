@@ -96,8 +96,16 @@ typedef struct ddps_solver_opts {
   int32_t renumber;     /* set BEFORE ddps_mesh_set.  1: renumber the nodes internally along a Morton (Z-order) curve so that
                            mesh neighbours are index neighbours (gmsh numbering is insertion order); the ABI keeps the
                            caller's numbering for every input and output.  Default 0 */
-  int32_t reserved[2];
+  int32_t precond;      /* preconditioner of the hand-written CG.  DDPS_PRECOND_JACOBI (0, default):
+                           the Jacobi-PCG the north star names.  DDPS_PRECOND_AMG (1): smoothed-aggregation multigrid
+                           V(1,1) cycle (frozen prolongators from the base stiffness, Galerkin operators of every assembled
+                           M - J0 recomputed on the device); same stop rules, same solutions to solver tolerance.
+                           Single-GPU contexts only; with a communicator the Jacobi path stays in charge */
+  int32_t reserved[1];
 } ddps_solver_opts;
+
+#define DDPS_PRECOND_JACOBI 0
+#define DDPS_PRECOND_AMG 1
 
 typedef struct ddps_stats {
   int32_t outer_iters;     /* Gummel (ddpe) or Newton (semlin) iterations done */
@@ -113,7 +121,10 @@ typedef struct ddps_stats {
   double t_wall_ms;        /* host wall clock around the same region as t_solve_ms */
   int32_t status;          /* DDPS_OK / DDPS_ERR_NOCONV / DDPS_ERR_BREAKDOWN */
   int32_t n_negative_area; /* elements with signed area < 0 (Q2: mass uses signed ar, src:375) */
-  int32_t reserved[8];
+  int32_t amg_levels;      /* multigrid levels in use (0: Jacobi-PCG) */
+  int32_t reserved0;
+  double t_amg_setup_ms;   /* host wall: one-time hierarchy setup (aggregation, prolongators, coarse patterns, uploads) */
+  int32_t reserved[4];
 } ddps_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
@@ -201,10 +212,36 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
 /* ---- in-library kernel timing (CUDA events on the library's own stream) --------------------
  * kernel 0: SpMV on DDPS_MAT_OP; 1: continuity-system assembly (uvsolve A+b, src:433-588);
  * 2: one full PCG iteration; 3: Newton-system assembly (Vsolve, src:368-420); 4: base stiffness;
- * 5: the PCG's SpMV with the fused p.Ap dot.
+ * 5: the PCG's SpMV with the fused p.Ap dot; 6: one CG iteration preconditioned with the multigrid V-cycle
+ * (opts.precond = DDPS_PRECOND_AMG); 7: the per-operator multigrid numeric phase (Galerkin products on all levels +
+ * coarsest inverse); 8: one V-cycle alone.
  * Runs `reps` launches after `warm` untimed ones and returns the mean milliseconds per launch and
  * the algorithmic bytes of one launch (definition in DESIGN.md). */
 int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_per_launch, double* algo_bytes);
+
+/* ---- multigrid preconditioner (replaces `\` at src:394,588,1063 together with the CG) ----
+ * Host-only hierarchy setup, callable WITHOUT a GPU (the CPU tests check it against scipy): from a CSR matrix
+ * (0-based, sorted columns) and a per-row `fixed` flag (Dirichlet rows) build the smoothed-aggregation hierarchy
+ * the library uses internally.  level_sizes: {n, nnz, n_coarse (0 on the coarsest level), nnz(P)}.
+ * level_get: CSR of the level's (base) operator, CSR of the prolongator P [n x n_coarse], aggregate id per row
+ * (-1: none); any pointer may be NULL. */
+typedef struct ddps_amg_host ddps_amg_host;
+int ddps_amg_host_create(ddps_amg_host** out, int64_t n, const int64_t* rowptr, const int64_t* col, const double* val,
+                         const uint8_t* fixed, int nthreads, int coarse_max);
+int ddps_amg_host_nlevels(const ddps_amg_host* h);
+int ddps_amg_host_level_sizes(const ddps_amg_host* h, int level, int64_t sizes[4]);
+int ddps_amg_host_level_get(const ddps_amg_host* h, int level, int64_t* rowptr, int64_t* col, double* val, int64_t* Pptr,
+                            int64_t* Pcol, double* Pval, int64_t* agg);
+void ddps_amg_host_free(ddps_amg_host* h);
+/* Device-side parity/debug exports (single-GPU contexts, opts.precond = DDPS_PRECOND_AMG, after a base assembly):
+ * levels : number of levels and rows per level (sizes capacity 16);
+ * numeric: run the per-operator numeric phase on DDPS_MAT_OP / DDPS_MAT_BASE;
+ * values : CSR-ordered values + inverse diagonal of level >= 1 after the last numeric phase;
+ * apply  : z = one V(1,1) cycle applied to r (length nq each, caller's numbering). */
+int ddps_amg_levels(ddps_ctx* ctx, int64_t* nlevels, int64_t* sizes);
+int ddps_amg_numeric(ddps_ctx* ctx, int which);
+int ddps_amg_get_values(ddps_ctx* ctx, int level, double* val, double* dinv);
+int ddps_amg_apply(ddps_ctx* ctx, const double* r, double* z);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,58 @@
+"""numpy/scipy restatement of the multigrid preconditioner (test infrastructure): the V(1,1) cycle with damped-Jacobi
+smoothing, Galerkin operators of the current operator on the frozen prolongators, exact coarsest solve -- the
+device kernels of csrc/amg.cu are checked against this."""
+import numpy as np
+import scipy.sparse as sp
+
+
+def hierarchy_matrices(levels):
+    """scipy views of ddps_b200.amg.host_hierarchy(): list of (A_base, P or None)."""
+    out = []
+    for lev in levels:
+        n = lev["n"]
+        A = sp.csr_matrix((lev["val"], lev["col"], lev["rowptr"]), shape=(n, n))
+        P = sp.csr_matrix((lev["Pval"], lev["Pcol"], lev["Pptr"]), shape=(n, lev["nc"])) if lev["nc"] else None
+        out.append((A, P))
+    return out
+
+
+def operator_levels(A, levels):
+    """Galerkin hierarchy of the operator A on the frozen prolongators."""
+    mats = hierarchy_matrices(levels)
+    ops = [A.tocsr()]
+    for (_, P) in mats[:-1]:
+        ops.append((P.T @ ops[-1] @ P).tocsr())
+    return ops, [P for (_, P) in mats]
+
+
+def vcycle(ops, Ps, r, omega=2.0 / 3.0, level=0):
+    A = ops[level]
+    if Ps[level] is None:
+        return np.linalg.solve(A.toarray(), r)
+    dinv = 1.0 / A.diagonal()
+    x = omega * dinv * r
+    t = r - A @ x
+    xc = vcycle(ops, Ps, Ps[level].T @ t, omega, level + 1)
+    x = x + Ps[level] @ xc
+    return x + omega * dinv * (r - A @ x)
+
+
+def pcg(A, b, M, rtol=1e-13, maxit=2000):
+    x = np.zeros_like(b)
+    r = b.copy()
+    z = M(r)
+    p = z.copy()
+    rz = r @ z
+    bb = np.sqrt(b @ b)
+    for it in range(1, maxit + 1):
+        q = A @ p
+        al = rz / (p @ q)
+        x += al * p
+        r -= al * q
+        if np.sqrt(r @ r) <= rtol * bb:
+            return x, it
+        z = M(r)
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, maxit

@@ -1,0 +1,173 @@
+"""GPU tests of the multigrid-preconditioned CG (opts.precond = 1), through the C ABI:
+device Galerkin products / V-cycle against the numpy restatement (tests/amg_ref.py), solver parity with the CPU
+oracle's golden fixtures (same tolerances and iteration counts as the Jacobi path), determinism."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import amg_ref
+from util import KEYS, four_tag, golden, gpu_mesh, oracle_mesh, rel_l2, rel_max, smooth_fields
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def D():
+    import ddps_b200
+    return ddps_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    import ddps_oracle
+    return ddps_oracle
+
+
+def _session(D, mesh, pr, **opts):
+    s = D.Session(0, precond=1, **opts)
+    s.set_mesh(mesh)
+    s.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
+    return s
+
+
+def _fixed(D, mesh, pr):
+    n, _ = D.dirichlet_nodes(mesh, pr["Vbddata"])
+    f = np.zeros(mesh.nq, dtype=bool)
+    f[np.asarray(n) - 1] = True
+    return f
+
+
+MESHES = {
+    "F2": lambda D: (gpu_mesh("F2"), D.problems.pn_junction([3, 7], [1, 2, 3, 4, 5, 6, 7, 8], C0=1.0, U=0.3)),
+    "S": lambda D: (D.structured_mesh(160, 80, 0.0, 2.0, 0.0, 1.0),
+                    D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)),
+}
+
+
+@pytest.mark.parametrize("which", ["F2", "S"])
+def test_device_hierarchy_matches_restatement(D, which):
+    """Galerkin operators on every level (k_amg_rap), their inverse diagonals and one V-cycle (smoother, residual,
+    restriction, coarsest inverse, prolongation) against numpy on the same frozen prolongators."""
+    mesh, pr = MESHES[which](D)
+    V, u, v = smooth_fields(mesh, 5)
+    with _session(D, mesh, pr) as s:
+        s.debug_assemble_base(False)
+        sizes = s.amg_levels()
+        assert len(sizes) >= 2 and sizes[0] == mesh.nq
+        MV = s.get_csr(0)
+        levels = D.amg.host_hierarchy(MV.indptr, MV.indices, MV.data, _fixed(D, mesh, pr))
+        assert [lev["n"] for lev in levels] == sizes
+        s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)
+        A = s.get_csr(1)
+        s.amg_numeric()
+        ops, Ps = amg_ref.operator_levels(A, levels)
+        for l in range(1, len(levels)):
+            val, dinv = s.amg_get_values(l, levels[l]["col"].size)
+            dev = sp.csr_matrix((val, levels[l]["col"], levels[l]["rowptr"]), shape=(sizes[l], sizes[l]))
+            d = (dev - ops[l]).tocoo()
+            err = (np.max(np.abs(d.data)) if d.nnz else 0.0) / np.max(np.abs(ops[l].data))
+            assert err <= 1e-12, (l, err)
+            assert rel_max(dinv, 1.0 / ops[l].diagonal()) <= 1e-12
+        rng = np.random.default_rng(1)
+        r = rng.standard_normal(mesh.nq)
+        z = s.amg_apply(r)
+        zr = amg_ref.vcycle(ops, Ps, r)
+        assert rel_max(z, zr) <= 1e-10
+        # run to run bitwise identical
+        s.amg_numeric()
+        assert np.array_equal(s.amg_apply(r), z)
+
+
+@pytest.mark.parametrize("which", ["F2", "S"])
+def test_amg_pcg_against_direct_solve(D, which):
+    mesh, pr = MESHES[which](D)
+    V, u, v = smooth_fields(mesh, 7)
+    with _session(D, mesh, pr) as s:
+        s.debug_assemble_base(False)
+        s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)
+        A = s.get_csr(1)
+        b = s.get_vector(0)
+        x, it, rr = s.debug_pcg(b, rtol=1e-13)
+        xd = spla.spsolve(A.tocsc(), b)
+        assert rel_l2(x, xd) <= 1e-10
+        assert it <= 40, it
+        # warm start from the solution: converged at once
+        x2, it2, _ = s.debug_pcg(b, x0=x, rtol=1e-12)
+        assert it2 <= 1
+    with D.Session(0) as sj:   # the Jacobi path on the same system needs an order of magnitude more iterations
+        sj.set_mesh(mesh)
+        sj.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
+        sj.debug_assemble_base(False)
+        sj.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)
+        xj, itj, _ = sj.debug_pcg(b, rtol=1e-13)
+        assert rel_l2(x, xj) <= 1e-10
+        assert itj > 5 * it, (it, itj)
+
+
+CASES = {
+    "ddpe1_F2": ("F2", lambda P: P.ddpe1()),
+    "ddpe2_F2": ("F2", lambda P: P.ddpe2()),
+    "pn_F1": ("F1", lambda P: P.pn_junction([2, 4], [1, 2, 3, 4], C0=1.0, U=0.3)),
+    "pn_F2": ("F2", lambda P: P.pn_junction([3, 7], [1, 2, 3, 4, 5, 6, 7, 8], C0=1.0, U=0.3)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_solve_ddpe_with_amg_matches_golden(D, case):
+    """Same bar as the Jacobi path: fields <= 1e-8 rel-L2, Gummel and Newton iteration counts equal to the oracle's."""
+    mname, mk = CASES[case]
+    mesh = gpu_mesh(mname)
+    z = golden(case)
+    pr = mk(D.problems)
+    with D.Session(0, precond=1) as s:
+        V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+    assert st["amg_levels"] >= 2
+    for a, name in ((V, "V"), (u, "u"), (v, "v")):
+        assert rel_l2(a, z[name]) <= FIELD_TOL, (name, rel_l2(a, z[name]))
+    # same rule as tests/test_gpu_parity.py: counts equal unless the stop decision sits on the rounding floor
+    nref, ngpu = len(z["control"]), st["outer_iters"]
+    if ngpu != nref:
+        k = min(nref, ngpu) - 1
+        assert abs(ngpu - nref) == 1 and pr["tol"] / 4 <= z["control"][k] <= 4 * pr["tol"], (ngpu, nref, z["control"])
+    m = min(nref, ngpu)
+    assert np.array_equal(st["newton_per_vsolve"].astype(int)[:m], z["newton_counts"][:m])
+    assert np.allclose(st["control_history"][:3], z["control"][:3], rtol=1e-4)
+    assert max(st["pcg_per_solve"]) <= 40
+
+
+@pytest.mark.parametrize("tags4", [True, False])
+def test_solve_semlin_with_amg_matches_golden(D, tags4):
+    mesh = gpu_mesh("F1" if tags4 else "F2")
+    z = golden("semlin_F1" if tags4 else "semlin_F2")
+    pr = D.problems.semlin_test(tags4)
+    with D.Session(0, precond=1) as s:
+        V, st = D.solve_semlin_poisson(mesh, pr["A"], pr["bddata"], pr["f"], pr["g"], pr["tol"], session=s, return_stats=True,
+                                       verbose=False)
+    assert st["amg_levels"] >= 2
+    assert rel_l2(V, z["V"]) <= FIELD_TOL
+    assert st["outer_iters"] == int(z["newton"])
+
+
+def test_amg_and_jacobi_agree_on_a_structured_diode_and_renumbering(D):
+    mesh = D.structured_mesh(192, 96, 0.0, 2.0, 0.0, 1.0)
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
+    out = {}
+    for name, opts in (("jacobi", {}), ("amg", dict(precond=1)), ("amg_morton", dict(precond=1, renumber=1))):
+        with D.Session(0, **opts) as s:
+            V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+        out[name] = (V, u, v, st)
+    Vj, uj, vj, stj = out["jacobi"]
+    for name in ("amg", "amg_morton"):
+        Va, ua, va, sta = out[name]
+        assert sta["outer_iters"] == stj["outer_iters"]
+        assert [int(k) for k in sta["newton_per_vsolve"]] == [int(k) for k in stj["newton_per_vsolve"]]
+        for a, b in ((Va, Vj), (ua, uj), (va, vj)):
+            assert rel_l2(a, b) <= 1e-9
+        assert sta["pcg_total"] * 8 < stj["pcg_total"], (sta["pcg_total"], stj["pcg_total"])
+    # bitwise reproducible
+    with D.Session(0, precond=1) as s:
+        V2, u2, v2 = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, verbose=False)
+    assert np.array_equal(V2, out["amg"][0]) and np.array_equal(u2, out["amg"][1]) and np.array_equal(v2, out["amg"][2])
