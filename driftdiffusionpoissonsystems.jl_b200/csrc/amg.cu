@@ -15,6 +15,9 @@
 // The PCG control flow (alpha, beta, stop test, iteration counter) stays on the device like in the Jacobi path;
 // every kernel of the cycle early-exits once the `done` flag is up.
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
 
 #include "amg.h"
 #include "ddps_internal.cuh"
@@ -26,7 +29,7 @@ constexpr int kAmgMaxLevels = 12;
 constexpr int kAmgDenseMax = 512;
 
 struct AmgLevelDev {
-  int n = 0, nslices = 0, nc = 0;
+  int n = 0, nslices = 0, nc = 0, wmax = 0;   // wmax: longest row (= widest slice) of this level's matrix
   int64_t nnz = 0, nentries = 0;
   bool owns = false;                 // level 0 aliases the fine pattern of the context
   int* slice_ptr = nullptr;
@@ -215,6 +218,103 @@ __global__ void __launch_bounds__(256) k_amg_rap(int nc, const int* __restrict__
   }
 }
 
+// Same product, parallel over the lanes (the production path; k_amg_rap above is kept for coarse rows longer than
+// kRapSlots entries).  One warp per coarse row I.  The (fine row of R(I,:), fine entry) pairs are dealt round-robin
+// to the 32 lanes; every lane multiplies out its pairs with the prolongator rows and adds each product into its
+// PRIVATE accumulator row (shared memory, slot found by binary search in the staged sorted coarse row), so the
+// loads of the 32 lanes overlap instead of forming one dependent chain.  Then lane t sums column t of the 32
+// private rows in lane order.  The assignment of products to lanes and both summation orders are fixed functions
+// of the pattern: bitwise reproducible, no atomics.
+constexpr int kRapWarps = 4;
+constexpr int kRapSlots = 32;
+constexpr int kRapStride = 33;   // padded row stride of the private tables: equal slots of different lanes hit different banks
+
+__global__ void __launch_bounds__(kRapWarps * 32) k_amg_rap2(int nc, int wmax, const int* __restrict__ f_slice_ptr,
+                                                            const int* __restrict__ f_col, const double* __restrict__ f_val,
+                                                            const int* __restrict__ Pptr, const int* __restrict__ Pcol,
+                                                            const double* __restrict__ Pval, const int* __restrict__ Rptr,
+                                                            const int* __restrict__ Rrow, const double* __restrict__ Rval,
+                                                            const int* __restrict__ c_rowptr, const int* __restrict__ c_slice_ptr,
+                                                            const int* __restrict__ c_col, double* __restrict__ c_val,
+                                                            double* __restrict__ c_dinv) {
+  __shared__ double sh_tab[kRapWarps][32 * kRapStride];
+  __shared__ int sh_col[kRapWarps][kRapSlots];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* tab = sh_tab[wid];
+  int* ccols = sh_col[wid];
+  const int gw = blockIdx.x * kRapWarps + wid, nw = gridDim.x * kRapWarps;
+  for (int I = gw; I < nc; I += nw) {
+    const int len = c_rowptr[I + 1] - c_rowptr[I];
+    const int cbase = c_slice_ptr[I >> 5] + (I & 31);
+    const int q0 = Rptr[I], q1 = Rptr[I + 1];
+    if (len <= kRapSlots) {
+      if (lane < len) ccols[lane] = c_col[cbase + 32 * lane];
+      for (int t = 0; t < len; ++t) tab[lane * kRapStride + t] = 0.0;
+      __syncwarp();
+      const int npairs = (q1 - q0) * wmax;
+      for (int e = lane; e < npairs; e += 32) {
+        const int dq = e / wmax;
+        const int k = e - dq * wmax;
+        const int q = q0 + dq;
+        const int i = Rrow[q];
+        const int fb = f_slice_ptr[i >> 5];
+        const int w = (f_slice_ptr[(i >> 5) + 1] - fb) >> 5;
+        if (k >= w) continue;
+        const int idx = fb + 32 * k + (i & 31);
+        const double a = f_val[idx];
+        if (a == 0.0) continue;   // padding and the exact zeros of right-angle meshes / eliminated entries
+        const double ra = Rval[q] * a;
+        const int j = f_col[idx];
+        const int m1 = Pptr[j + 1];
+        for (int m = Pptr[j]; m < m1; ++m) {
+          const int J = Pcol[m];
+          int lo = 0, hi = len;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ccols[mid] < J) lo = mid + 1; else hi = mid;
+          }
+          tab[lane * kRapStride + lo] += ra * Pval[m];
+        }
+      }
+      __syncwarp();
+      if (lane < len) {
+        double s = 0.0;
+        for (int l = 0; l < 32; ++l) s += tab[l * kRapStride + lane];
+        c_val[cbase + 32 * lane] = s;
+        if (ccols[lane] == I) c_dinv[I] = 1.0 / s;
+      }
+      __syncwarp();
+    } else {
+      // long coarse row: every lane walks the whole product sequence and keeps its own column(s)
+      for (int t0 = 0; t0 < len; t0 += 32) {
+        const int t = t0 + lane;
+        const int myJ = t < len ? c_col[cbase + 32 * t] : -1;
+        double acc = 0.0;
+        for (int q = q0; q < q1; ++q) {
+          const int i = Rrow[q];
+          const double r = Rval[q];
+          const int fb = f_slice_ptr[i >> 5];
+          const int w = (f_slice_ptr[(i >> 5) + 1] - fb) >> 5;
+          int idx = fb + (i & 31);
+          for (int k = 0; k < w; ++k, idx += 32) {
+            const double a = f_val[idx];
+            if (a == 0.0) continue;
+            const int j = f_col[idx];
+            const double ra = r * a;
+            const int m1 = Pptr[j + 1];
+            for (int m = Pptr[j]; m < m1; ++m)
+              if (Pcol[m] == myJ) acc += ra * Pval[m];
+          }
+        }
+        if (t < len) {
+          c_val[cbase + 32 * t] = acc;
+          if (myJ == I) c_dinv[I] = 1.0 / acc;
+        }
+      }
+    }
+  }
+}
+
 // Dense inverse of the coarsest operator: in-place Gauss-Jordan without pivoting (the operator is SPD), one CTA.
 __global__ void __launch_bounds__(1024) k_amg_dense_inverse(int n, const int* __restrict__ rowptr,
                                                             const int* __restrict__ slice_ptr, const int* __restrict__ col,
@@ -265,34 +365,42 @@ __global__ void __launch_bounds__(kAmgDenseMax) k_amg_dense_apply(int n, const d
 }
 
 // ---- CG with a general preconditioner: control kernels -------------------------------------------------------
-// r = rhs - q (q = A x0) or r = rhs; sums {r.r, rhs.rhs}, max|r|
+// r = rhs - q (q = A x0) or r = rhs; sums {r.r, rhs.rhs, x0.rhs}, max|r|
 template <bool HAVE_Q>
-__global__ void k_apcg_init(int n, const double* __restrict__ rhs, const double* __restrict__ q, double* __restrict__ r,
-                            double* partials, PcgScalars* scal) {
+__global__ void k_apcg_init(int n, const double* __restrict__ rhs, const double* __restrict__ q, const double* __restrict__ x0,
+                            double* __restrict__ r, double* partials, PcgScalars* scal) {
   __shared__ double sh_red[32];
-  double s_rr = 0.0, s_bb = 0.0, s_max = 0.0;
+  double s_rr = 0.0, s_bb = 0.0, s_xb = 0.0, s_max = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double bi = rhs[i];
     const double ri = HAVE_Q ? bi - q[i] : bi;
     r[i] = ri;
     s_rr += ri * ri; s_bb += bi * bi;
+    if (HAVE_Q) s_xb += x0[i] * bi;
     s_max = fmax(s_max, fabs(ri));
   }
-  double v[3] = {s_rr, s_bb, s_max}, tot[3];
-  if (grid_reduce_mixed<3, 4u>(v, partials, &scal->cnt[1], sh_red, tot)) {
+  double v[4] = {s_rr, s_bb, s_xb, s_max}, tot[4];
+  if (grid_reduce_mixed<4, 8u>(v, partials, &scal->cnt[1], sh_red, tot)) {
     if (threadIdx.x == 0) {
-      scal->rr = tot[0]; scal->bb = tot[1]; scal->rmax = tot[2];
+      scal->rr = tot[0]; scal->bb = tot[1]; scal->xb = tot[2]; scal->rmax = tot[3];
       scal->sums[2] = tot[0];
     }
   }
 }
 
-__global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf) {
+// Stop rule: ||r||_2 <= rtol*||rhs||_2  OR  ||r||_inf <= atol_inf, like the Jacobi path.  A WARM-started solve must
+// in addition bring the energy norm of the error, estimated by r.z = r.Br ~ e.Ae, below rtol^2 * ||x||_A^2 (~ x0.rhs):
+// the residual of a smooth error (the Gummel update of the previous outer iteration) is far below rtol*||rhs|| long
+// before the error itself is, and a solve that returns its initial guess would end the Gummel loop early.
+__global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int warm) {
   scal->thresh2 = rtol * rtol * scal->bb;
   scal->thresh_inf = atol_inf;
+  scal->thresh_e = 0.0;
+  scal->warm = warm;
   scal->iters = 0;
   scal->breakdown = 0;
-  scal->done = (scal->rr <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
+  if (warm) scal->done = (scal->rr == 0.0) ? 1 : 0;
+  else scal->done = (scal->rr <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
 }
 
 // x += alpha p; r -= alpha q; the block that finishes last takes the convergence decision, so that the cycle
@@ -330,18 +438,25 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, in
       scal->rr = tot[0];
       scal->rmax = tot[1];
       scal->iters = it + 1;
-      if (tot[0] <= scal->thresh2 || tot[1] <= scal->thresh_inf || it + 1 >= max_it || !(tot[0] == tot[0])) scal->done = 1;
+      // rz = r.Br of the residual BEFORE this update bounds the energy of the error after it (CG decreases it)
+      const bool small_r = tot[0] <= scal->thresh2 || tot[1] <= scal->thresh_inf;
+      const bool small_e = !scal->warm || rz <= scal->thresh_e;
+      if ((small_r && small_e) || it + 1 >= max_it || !(tot[0] == tot[0])) scal->done = 1;
     }
   }
 }
 
 // p = z + beta p  (first: p = z); r.z of this iteration was left in sums[1] by the last kernel of the cycle
-__global__ void __launch_bounds__(kVecBlock, 8) k_apcg_direction(int n, int par, int first, const double* __restrict__ z,
-                                                              double* __restrict__ p, PcgScalars* scal) {
+__global__ void __launch_bounds__(kVecBlock, 8) k_apcg_direction(int n, int par, int first, double rtol,
+                                                              const double* __restrict__ z, double* __restrict__ p,
+                                                              PcgScalars* scal) {
   if (scal->done) return;
   const double rz_new = scal->sums[1];
   const double beta = first ? 0.0 : rz_new / scal->rz[par];
-  if (blockIdx.x == 0 && threadIdx.x == 0) scal->rz[first ? 0 : (par ^ 1)] = rz_new;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal->rz[first ? 0 : (par ^ 1)] = rz_new;
+    if (first) scal->thresh_e = rtol * rtol * fmax(fabs(scal->xb), rz_new);
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     p[i] = first ? z[i] : z[i] + beta * p[i];
 }
@@ -385,14 +500,26 @@ int amg_setup(Context* ctx) {
   DDPS_CUDA(cudaMemcpy(sp.data(), P.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
   DDPS_CUDA(cudaMemcpy(sv.data(), ctx->val_base, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
   DDPS_CUDA(cudaMemcpy(fixed.data(), ctx->isD, fixed.size(), cudaMemcpyDeviceToHost));
-  for (int r = 0; r < n; ++r) {
-    const int base = sp[r >> 5], lane = r & 31;
-    for (int k = 0; k < rp[r + 1] - rp[r]; ++k) vv[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
+  const double t1 = wall_ms();
+  {
+    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    const int chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        for (int r = t * chunk; r < std::min(n, (t + 1) * chunk); ++r) {
+          const int base = sp[r >> 5], lane = r & 31;
+          for (int k = 0; k < rp[r + 1] - rp[r]; ++k) vv[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
+        }
+      });
+    for (auto& x : th) x.join();
   }
   sv.clear(); sv.shrink_to_fit();
+  const double t2 = wall_ms();
   AmgHost H;
   AmgParams prm;
   const int nlev = amg_host_build(H, n, std::move(rp), std::move(cc), std::move(vv), fixed.data(), prm);
+  const double t3 = wall_ms();
   if (nlev < 2 || nlev > kAmgMaxLevels || H.lv.back().n > kAmgDenseMax) return 0;   // no hierarchy: Jacobi-PCG stays
 
   Amg* A = new Amg();
@@ -406,7 +533,7 @@ int amg_setup(Context* ctx) {
     L.n = HL.n;
     L.nnz = (int64_t)HL.col.size();
     if (l == 0) {
-      L.nslices = P.nslices; L.nentries = P.nentries;
+      L.nslices = P.nslices; L.nentries = P.nentries; L.wmax = P.max_row_len;
       L.slice_ptr = P.slice_ptr; L.col = P.col; L.rowptr = P.rowptr; L.owns = false;
     } else {
       // SELL-32 layout of the coarse pattern (same convention as the fine pattern: padding = value 0, own column)
@@ -416,6 +543,7 @@ int amg_setup(Context* ctx) {
         int w = 0;
         for (int r = s * 32; r < std::min(HL.n, s * 32 + 32); ++r) w = std::max(w, HL.rowptr[r + 1] - HL.rowptr[r]);
         hsp[s + 1] = hsp[s] + 32 * w;
+        L.wmax = std::max(L.wmax, w);
       }
       L.nentries = hsp[L.nslices];
       std::vector<int> hcol((size_t)L.nentries, 0);
@@ -455,6 +583,9 @@ int amg_setup(Context* ctx) {
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   A->ready = true;
   A->setup_ms = wall_ms() - t0;
+  if (getenv("DDPS_AMG_TIMING"))
+    fprintf(stderr, "[ddps amg] setup %.1f ms: D2H %.1f, SELL->CSR %.1f, host hierarchy %.1f, SELL build + uploads %.1f\n", A->setup_ms,
+            t1 - t0, t2 - t1, t3 - t2, wall_ms() - t3);
   return 0;
 }
 
@@ -492,9 +623,13 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv) {
   for (int l = 0; l + 1 < A.nlev; ++l) {
     AmgLevelDev& F = A.lv[l];
     AmgLevelDev& C = A.lv[l + 1];
-    const int grid = amg_grid(ctx, (int64_t)C.n * 32, 256);
-    k_amg_rap<<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr, F.Rrow,
-                                             F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + kRapWarps - 1) / kRapWarps, (int64_t)ctx->num_sms * 6));
+    if (ctx->opts.reserved[0] == 1)   // A/B switch (profiling): the serial-walk kernel
+      k_amg_rap<<<amg_grid(ctx, (int64_t)C.n * 32, 256), 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval,
+                                                                               F.Rptr, F.Rrow, F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+    else
+      k_amg_rap2<<<grid, kRapWarps * 32, 0, ctx->stream>>>(C.n, F.wmax, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr,
+                                                           F.Rrow, F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
     C.cur_val = C.val;
     C.cur_dinv = C.dinv;
     ctx->stats.kernel_launches++;
@@ -557,7 +692,7 @@ int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it) {
   if ((rc = launch_spmv_dot(ctx, A.lv[0].cur_val, ctx->p, ctx->q))) return rc;    // q = A p, p.q -> sums[0]
   k_apcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, ctx->partials, ctx->scal);
   if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;                        // z = B r, r.z -> sums[1]
-  k_apcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, 0, A.z, ctx->p, ctx->scal);
+  k_apcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, 0, 0.0, A.z, ctx->p, ctx->scal);
   ctx->stats.kernel_launches += 2;
   return 0;
 }
@@ -575,14 +710,14 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
   if (x0_nonzero) {
     DDPS_CUDA(cudaMemcpyAsync(ctx->p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = launch_spmv(ctx, val, ctx->p, ctx->q))) return rc;
-    k_apcg_init<true><<<g, kVecBlock, 0, st>>>(n, rhs, ctx->q, ctx->r, ctx->partials, ctx->scal);
+    k_apcg_init<true><<<g, kVecBlock, 0, st>>>(n, rhs, ctx->q, ctx->p, ctx->r, ctx->partials, ctx->scal);
   } else {
     DDPS_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), st));
-    k_apcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, ctx->r, ctx->partials, ctx->scal);
+    k_apcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, nullptr, ctx->r, ctx->partials, ctx->scal);
   }
-  k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf);
+  k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf, x0_nonzero ? 1 : 0);
   if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;
-  k_apcg_direction<<<g, kVecBlock, 0, st>>>(n, 0, 1, A.z, ctx->p, ctx->scal);
+  k_apcg_direction<<<g, kVecBlock, 0, st>>>(n, 0, 1, rtol, A.z, ctx->p, ctx->scal);
   ctx->stats.kernel_launches += 3;
   DDPS_CUDA(cudaGetLastError());
 

@@ -18,6 +18,9 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <thread>
 #include <vector>
@@ -113,71 +116,97 @@ int aggregate(const AmgHostLevel& L, const std::vector<unsigned char>& strong, s
   return nc;
 }
 
+// One row of P = (I - omega D^-1 A) T: distinct aggregates of the row's neighbourhood, sorted by aggregate id; the
+// contributions to one aggregate are added in entry order (own term first).  Returns the number of entries.
+inline int prolongator_row(const AmgHostLevel& L, const unsigned char* fixed, double omega, int i, int* ag, double* v) {
+  if (fixed && fixed[i]) return 0;
+  int cnt = 0;
+  double d = 0.0;
+  for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
+    if (L.col[k] == i) d = L.val[k];
+  if (L.agg[i] >= 0) { ag[0] = L.agg[i]; v[0] = 1.0 - omega; cnt = 1; }
+  if (d != 0.0) {
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+      const int j = L.col[k];
+      if (j == i || L.val[k] == 0.0 || L.agg[j] < 0) continue;
+      const int a = L.agg[j];
+      const double c = -omega * L.val[k] / d;
+      int pos = 0;
+      while (pos < cnt && ag[pos] != a) ++pos;
+      if (pos == cnt) { ag[cnt] = a; v[cnt] = c; ++cnt; }
+      else v[pos] += c;
+    }
+  }
+  for (int p = 1; p < cnt; ++p) {   // insertion sort by aggregate id (a handful of entries)
+    const int a = ag[p];
+    const double c = v[p];
+    int q = p - 1;
+    while (q >= 0 && ag[q] > a) { ag[q + 1] = ag[q]; v[q + 1] = v[q]; --q; }
+    ag[q + 1] = a; v[q + 1] = c;
+  }
+  return cnt;
+}
+
 // P = (I - omega D^-1 A) T with T the piecewise-constant tentative prolongator; rows of fixed nodes stay empty
 void smooth_prolongator(AmgHostLevel& L, const unsigned char* fixed, double omega, int nthreads) {
   const int n = L.n;
-  std::vector<int> len(n, 0);
-  const int nt = std::max(1, nthreads);
-  std::vector<std::vector<int>> tcol(nt);
-  std::vector<std::vector<double>> tval(nt);
-  std::vector<int64_t> tlo(nt, 0), thi(nt, 0);
-  parallel_ranges(n, nt, [&](int t, int64_t lo, int64_t hi) {
-    tlo[t] = lo; thi[t] = hi;
-    std::vector<std::pair<int, double>> row;
-    for (int64_t i = lo; i < hi; ++i) {
-      row.clear();
-      if (!(fixed && fixed[i])) {
-        double d = 0.0;
-        for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
-          if (L.col[k] == i) d = L.val[k];
-        if (L.agg[i] >= 0) row.emplace_back(L.agg[i], 1.0 - omega);
-        if (d != 0.0) {
-          for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
-            const int j = L.col[k];
-            if (j == i || L.val[k] == 0.0 || L.agg[j] < 0) continue;
-            row.emplace_back(L.agg[j], -omega * L.val[k] / d);
-          }
-        }
-        std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
-      }
-      int cnt = 0;
-      for (size_t q = 0; q < row.size();) {
-        double s = 0.0;
-        size_t e = q;
-        while (e < row.size() && row[e].first == row[q].first) s += row[e++].second;
-        tcol[t].push_back(row[q].first);
-        tval[t].push_back(s);
-        ++cnt;
-        q = e;
-      }
-      len[i] = cnt;
-    }
-  });
+  int maxlen = 1;
+  for (int i = 0; i < n; ++i) maxlen = std::max(maxlen, L.rowptr[i + 1] - L.rowptr[i] + 1);
   L.Pptr.assign(n + 1, 0);
-  for (int i = 0; i < n; ++i) L.Pptr[i + 1] = L.Pptr[i] + len[i];
+  parallel_ranges(n, nthreads, [&](int, int64_t lo, int64_t hi) {
+    std::vector<int> ag(maxlen);
+    std::vector<double> v(maxlen);
+    for (int64_t i = lo; i < hi; ++i) L.Pptr[i + 1] = prolongator_row(L, fixed, omega, (int)i, ag.data(), v.data());
+  });
+  for (int i = 0; i < n; ++i) L.Pptr[i + 1] += L.Pptr[i];
   L.Pcol.resize(L.Pptr[n]);
   L.Pval.resize(L.Pptr[n]);
-  for (int t = 0; t < nt; ++t) {
-    if (thi[t] <= tlo[t]) continue;
-    std::copy(tcol[t].begin(), tcol[t].end(), L.Pcol.begin() + L.Pptr[tlo[t]]);
-    std::copy(tval[t].begin(), tval[t].end(), L.Pval.begin() + L.Pptr[tlo[t]]);
-  }
+  parallel_ranges(n, nthreads, [&](int, int64_t lo, int64_t hi) {
+    std::vector<int> ag(maxlen);
+    std::vector<double> v(maxlen);
+    for (int64_t i = lo; i < hi; ++i) {
+      const int cnt = prolongator_row(L, fixed, omega, (int)i, ag.data(), v.data());
+      std::copy(ag.begin(), ag.begin() + cnt, L.Pcol.begin() + L.Pptr[i]);
+      std::copy(v.begin(), v.begin() + cnt, L.Pval.begin() + L.Pptr[i]);
+    }
+  });
 }
 
-void transpose_prolongator(AmgHostLevel& L) {
+// R = P^T row-wise, fine indices increasing inside every coarse row.  Parallel counting sort: thread t owns a
+// contiguous chunk of fine rows; per-thread column histograms give every (column, thread) its write offset.
+void transpose_prolongator(AmgHostLevel& L, int nthreads) {
   const int n = L.n, nc = L.nc;
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, ((int64_t)n + 65535) / 65536));
+  const int64_t chunk = ((int64_t)n + nt - 1) / nt;
+  std::vector<std::vector<int>> cnt(nt);
+  auto run = [&](auto&& fn) {
+    if (nt == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back([&fn, t]() { fn(t); });
+    for (auto& x : th) x.join();
+  };
+  run([&](int t) {
+    cnt[t].assign(nc, 0);
+    const int64_t lo = std::min<int64_t>(n, t * chunk), hi = std::min<int64_t>(n, lo + chunk);
+    for (int k = L.Pptr[lo]; k < L.Pptr[hi]; ++k) cnt[t][L.Pcol[k]]++;
+  });
   L.Rptr.assign(nc + 1, 0);
-  for (size_t k = 0; k < L.Pcol.size(); ++k) L.Rptr[L.Pcol[k] + 1]++;
-  for (int I = 0; I < nc; ++I) L.Rptr[I + 1] += L.Rptr[I];
+  for (int I = 0; I < nc; ++I) {
+    int s = L.Rptr[I];
+    for (int t = 0; t < nt; ++t) { const int c = cnt[t][I]; cnt[t][I] = s; s += c; }   // cnt becomes the write offset
+    L.Rptr[I + 1] = s;
+  }
   L.Rrow.resize(L.Pcol.size());
   L.Rval.resize(L.Pcol.size());
-  std::vector<int> fill(L.Rptr.begin(), L.Rptr.end() - 1);
-  for (int i = 0; i < n; ++i)
-    for (int k = L.Pptr[i]; k < L.Pptr[i + 1]; ++k) {
-      const int pos = fill[L.Pcol[k]]++;
-      L.Rrow[pos] = i;          // increasing fine index inside every coarse row
-      L.Rval[pos] = L.Pval[k];
-    }
+  run([&](int t) {
+    const int64_t lo = std::min<int64_t>(n, t * chunk), hi = std::min<int64_t>(n, lo + chunk);
+    for (int64_t i = lo; i < hi; ++i)
+      for (int k = L.Pptr[i]; k < L.Pptr[i + 1]; ++k) {
+        const int pos = cnt[t][L.Pcol[k]]++;
+        L.Rrow[pos] = (int)i;
+        L.Rval[pos] = L.Pval[k];
+      }
+  });
 }
 
 // C = R A P, row-parallel, columns sorted.  Structural zeros of A are kept (the current operator M - J0 has
@@ -236,19 +265,30 @@ int amg_host_build(AmgHost& H, int n, std::vector<int>&& rowptr, std::vector<int
   H.lv[0].col = std::move(col);
   H.lv[0].val = std::move(val);
   int nthreads = prm.nthreads > 0 ? prm.nthreads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  const bool timing = getenv("DDPS_AMG_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   while ((int)H.lv.size() < prm.max_levels) {
     AmgHostLevel& L = H.lv.back();
     if (L.n <= prm.coarse_max) break;
     const unsigned char* fx = H.lv.size() == 1 ? fixed : nullptr;
     std::vector<unsigned char> strong;
+    const double t0 = now();
     mark_strong(L, fx, prm.theta, nthreads, strong);
+    const double t1 = now();
     const int nc = aggregate(L, strong, L.agg);
+    const double t2 = now();
     if (nc <= 0 || nc > 0.7 * L.n) { L.agg.clear(); break; }   // coarsening stalled
     L.nc = nc;
     smooth_prolongator(L, fx, prm.omega, nthreads);
-    transpose_prolongator(L);
+    const double t3 = now();
+    transpose_prolongator(L, nthreads);
+    const double t4 = now();
     AmgHostLevel C;
     galerkin(L, C, nthreads);
+    const double t5 = now();
+    if (timing)
+      fprintf(stderr, "[ddps amg] level %d n=%d -> %d (%d threads): strong %.1f ms, aggregate %.1f, prolongator %.1f, transpose %.1f, galerkin %.1f\n",
+              (int)H.lv.size() - 1, L.n, nc, nthreads, t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4);
     H.lv.push_back(std::move(C));
   }
   return (int)H.lv.size();

@@ -90,6 +90,11 @@ struct PcgScalars {
   double rmax;      // ||r||_inf of the PCG residual
   double thresh_inf;
   double norm_aux2;
+  // multigrid-preconditioned CG (amg.cu): energy-norm stop rule of warm-started solves
+  double thresh_e;  // stop only when r.Br <= thresh_e
+  double xb;        // x0.rhs ~ ||x||_A^2
+  int warm;
+  int pad1;
 };
 
 // ---- peer-memory (NVLink P2P via CUDA IPC) windows for the fused halo push + scalar allreduce ----

@@ -151,22 +151,27 @@ def test_solve_semlin_with_amg_matches_golden(D, tags4):
     assert st["outer_iters"] == int(z["newton"])
 
 
-def test_amg_and_jacobi_agree_on_a_structured_diode_and_renumbering(D):
+def test_amg_and_jacobi_agree_on_a_structured_diode_and_renumbering(D, O):
+    """Structured pn-diode (the bench problem, 36,864 triangles): multigrid path (with and without the internal Morton
+    renumbering) against the CPU oracle at the north-star tolerance, same Gummel / Newton counts as the Jacobi path,
+    an order of magnitude fewer CG iterations, bitwise reproducible."""
     mesh = D.structured_mesh(192, 96, 0.0, 2.0, 0.0, 1.0)
     pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
+    ref = O.solve_ddpe(oracle_mesh(mesh), *[pr[k] for k in KEYS])
     out = {}
     for name, opts in (("jacobi", {}), ("amg", dict(precond=1)), ("amg_morton", dict(precond=1, renumber=1))):
         with D.Session(0, **opts) as s:
             V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
         out[name] = (V, u, v, st)
-    Vj, uj, vj, stj = out["jacobi"]
+        for a, b in zip((V, u, v), ref):
+            assert rel_l2(a, b) <= FIELD_TOL, (name, rel_l2(a, b))
+    stj = out["jacobi"][3]
     for name in ("amg", "amg_morton"):
-        Va, ua, va, sta = out[name]
+        sta = out[name][3]
         assert sta["outer_iters"] == stj["outer_iters"]
         assert [int(k) for k in sta["newton_per_vsolve"]] == [int(k) for k in stj["newton_per_vsolve"]]
-        for a, b in ((Va, Vj), (ua, uj), (va, vj)):
-            assert rel_l2(a, b) <= 1e-9
         assert sta["pcg_total"] * 8 < stj["pcg_total"], (sta["pcg_total"], stj["pcg_total"])
+    print("rel-L2 vs oracle:", {k: [rel_l2(a, b) for a, b in zip(out[k][:3], ref)] for k in out})
     # bitwise reproducible
     with D.Session(0, precond=1) as s:
         V2, u2, v2 = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, verbose=False)
