@@ -225,61 +225,83 @@ __global__ void __launch_bounds__(256) k_amg_rap(int nc, const int* __restrict__
 // loads of the 32 lanes overlap instead of forming one dependent chain.  Then lane t sums column t of the 32
 // private rows in lane order.  The assignment of products to lanes and both summation orders are fixed functions
 // of the pattern: bitwise reproducible, no atomics.
-constexpr int kRapWarps = 4;
-constexpr int kRapSlots = 32;
-constexpr int kRapStride = 33;   // padded row stride of the private tables: equal slots of different lanes hit different banks
+constexpr int kRapBatch = 4;   // pairs per lane whose loads are issued together (memory-level parallelism)
 
-__global__ void __launch_bounds__(kRapWarps * 32) k_amg_rap2(int nc, int wmax, const int* __restrict__ f_slice_ptr,
-                                                            const int* __restrict__ f_col, const double* __restrict__ f_val,
-                                                            const int* __restrict__ Pptr, const int* __restrict__ Pcol,
-                                                            const double* __restrict__ Pval, const int* __restrict__ Rptr,
-                                                            const int* __restrict__ Rrow, const double* __restrict__ Rval,
-                                                            const int* __restrict__ c_rowptr, const int* __restrict__ c_slice_ptr,
-                                                            const int* __restrict__ c_col, double* __restrict__ c_val,
-                                                            double* __restrict__ c_dinv) {
-  __shared__ double sh_tab[kRapWarps][32 * kRapStride];
-  __shared__ int sh_col[kRapWarps][kRapSlots];
+template <int SLOTS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, int wmax, const int* __restrict__ f_slice_ptr,
+                                                        const int* __restrict__ f_col, const double* __restrict__ f_val,
+                                                        const int* __restrict__ Pptr, const int* __restrict__ Pcol,
+                                                        const double* __restrict__ Pval, const int* __restrict__ Rptr,
+                                                        const int* __restrict__ Rrow, const double* __restrict__ Rval,
+                                                        const int* __restrict__ c_rowptr, const int* __restrict__ c_slice_ptr,
+                                                        const int* __restrict__ c_col, double* __restrict__ c_val,
+                                                        double* __restrict__ c_dinv) {
+  constexpr int STRIDE = SLOTS + 1;   // padded row stride of the private tables: equal slots of different lanes hit different banks
+  __shared__ double sh_tab[WARPS][32 * STRIDE];
+  __shared__ int sh_col[WARPS][SLOTS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* tab = sh_tab[wid];
   int* ccols = sh_col[wid];
-  const int gw = blockIdx.x * kRapWarps + wid, nw = gridDim.x * kRapWarps;
+  const int gw = blockIdx.x * WARPS + wid, nw = gridDim.x * WARPS;
   for (int I = gw; I < nc; I += nw) {
     const int len = c_rowptr[I + 1] - c_rowptr[I];
     const int cbase = c_slice_ptr[I >> 5] + (I & 31);
     const int q0 = Rptr[I], q1 = Rptr[I + 1];
-    if (len <= kRapSlots) {
+    if (len <= SLOTS) {
       if (lane < len) ccols[lane] = c_col[cbase + 32 * lane];
-      for (int t = 0; t < len; ++t) tab[lane * kRapStride + t] = 0.0;
+      for (int t = 0; t < len; ++t) tab[lane * STRIDE + t] = 0.0;
       __syncwarp();
       const int npairs = (q1 - q0) * wmax;
-      for (int e = lane; e < npairs; e += 32) {
-        const int dq = e / wmax;
-        const int k = e - dq * wmax;
-        const int q = q0 + dq;
-        const int i = Rrow[q];
-        const int fb = f_slice_ptr[i >> 5];
-        const int w = (f_slice_ptr[(i >> 5) + 1] - fb) >> 5;
-        if (k >= w) continue;
-        const int idx = fb + 32 * k + (i & 31);
-        const double a = f_val[idx];
-        if (a == 0.0) continue;   // padding and the exact zeros of right-angle meshes / eliminated entries
-        const double ra = Rval[q] * a;
-        const int j = f_col[idx];
-        const int m1 = Pptr[j + 1];
-        for (int m = Pptr[j]; m < m1; ++m) {
-          const int J = Pcol[m];
-          int lo = 0, hi = len;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (ccols[mid] < J) lo = mid + 1; else hi = mid;
+      for (int e0 = lane; e0 < npairs; e0 += 32 * kRapBatch) {
+        int fi[kRapBatch], kk[kRapBatch], idx[kRapBatch], jj[kRapBatch], m0[kRapBatch], m1[kRapBatch];
+        double rv[kRapBatch], av[kRapBatch];
+#pragma unroll
+        for (int u = 0; u < kRapBatch; ++u) {
+          const int e = e0 + 32 * u;
+          const int dq = e / wmax;
+          kk[u] = e - dq * wmax;
+          const bool ok = e < npairs;
+          fi[u] = ok ? Rrow[q0 + dq] : -1;
+          rv[u] = ok ? Rval[q0 + dq] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRapBatch; ++u) {
+          idx[u] = -1;
+          if (fi[u] >= 0) {
+            const int fb = f_slice_ptr[fi[u] >> 5];
+            const int w = (f_slice_ptr[(fi[u] >> 5) + 1] - fb) >> 5;
+            if (kk[u] < w) idx[u] = fb + 32 * kk[u] + (fi[u] & 31);
           }
-          tab[lane * kRapStride + lo] += ra * Pval[m];
+        }
+#pragma unroll
+        for (int u = 0; u < kRapBatch; ++u) {
+          av[u] = idx[u] >= 0 ? f_val[idx[u]] : 0.0;
+          jj[u] = idx[u] >= 0 ? f_col[idx[u]] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRapBatch; ++u) {
+          // padding and the exact zeros of right-angle meshes / eliminated entries contribute nothing
+          m0[u] = Pptr[jj[u]];
+          m1[u] = av[u] != 0.0 ? Pptr[jj[u] + 1] : m0[u];
+        }
+#pragma unroll
+        for (int u = 0; u < kRapBatch; ++u) {
+          const double ra = rv[u] * av[u];
+          for (int m = m0[u]; m < m1[u]; ++m) {
+            const int J = Pcol[m];
+            int lo = 0, hi = len;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (ccols[mid] < J) lo = mid + 1; else hi = mid;
+            }
+            tab[lane * STRIDE + lo] += ra * Pval[m];
+          }
         }
       }
       __syncwarp();
       if (lane < len) {
         double s = 0.0;
-        for (int l = 0; l < 32; ++l) s += tab[l * kRapStride + lane];
+        for (int l = 0; l < 32; ++l) s += tab[l * STRIDE + lane];
         c_val[cbase + 32 * lane] = s;
         if (ccols[lane] == I) c_dinv[I] = 1.0 / s;
       }
@@ -623,13 +645,18 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv) {
   for (int l = 0; l + 1 < A.nlev; ++l) {
     AmgLevelDev& F = A.lv[l];
     AmgLevelDev& C = A.lv[l + 1];
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + kRapWarps - 1) / kRapWarps, (int64_t)ctx->num_sms * 6));
-    if (ctx->opts.reserved[0] == 1)   // A/B switch (profiling): the serial-walk kernel
+    if (ctx->opts.reserved[0] == 1) {   // A/B switch (profiling): the serial-walk kernel
       k_amg_rap<<<amg_grid(ctx, (int64_t)C.n * 32, 256), 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval,
                                                                                F.Rptr, F.Rrow, F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
-    else
-      k_amg_rap2<<<grid, kRapWarps * 32, 0, ctx->stream>>>(C.n, F.wmax, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr,
-                                                           F.Rrow, F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+    } else if (C.wmax <= 16) {          // short coarse rows: small private tables, 48 resident warps per SM
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 6));
+      k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.wmax, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr, F.Rrow,
+                                                       F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+    } else {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 3) / 4, (int64_t)ctx->num_sms * 6));
+      k_amg_rap2<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.wmax, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr, F.Rrow,
+                                                       F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+    }
     C.cur_val = C.val;
     C.cur_dinv = C.dinv;
     ctx->stats.kernel_launches++;
