@@ -4,11 +4,10 @@
 // Split of the work:
 //   * once per base operator (host, amg_host.cu): aggregates, frozen smoothed prolongators P_l, R_l = P_l^T
 //     stored row-wise, and the coarse sparsity patterns;
-//   * once per operator A = M - J0 (device, k_amg_rap): the Galerkin products A_{l+1} = R_l A_l P_l on the frozen
-//     patterns -- one warp per coarse row, one lane per coarse entry, every lane walks the same
-//     (fine row, fine entry, prolongator entry) sequence and keeps the products of its own column, so every coarse
-//     entry is summed in a fixed order: no atomics, bitwise reproducible; then the dense inverse of the coarsest
-//     operator (Gauss-Jordan in one CTA);
+//   * once per operator A = M - J0 (device, k_amg_rap2): the Galerkin products A_{l+1} = R_l A_l P_l on the frozen
+//     patterns -- one warp per coarse row, the (fine row, fine entry) pairs dealt to the lanes, lane-private
+//     accumulator rows in shared memory, fixed-order reduction: no atomics, bitwise reproducible; then the dense
+//     inverse of the coarsest operator (Gauss-Jordan in one CTA, in shared memory);
 //   * per CG iteration (device): one V(1,1) cycle with damped-Jacobi smoothing; all matrices are SELL-32 like the
 //     fine operator, the smoother and the residual are fused into the SpMV epilogue, restriction/prolongation are
 //     deterministic row gathers.  The cycle is a fixed SPD linear operator, so plain (non-flexible) CG applies.
@@ -39,8 +38,10 @@ struct AmgLevelDev {
   double* dinv = nullptr;            // level >= 1
   const double* cur_val = nullptr;   // matrix / inverse diagonal used by the cycle (level 0: set per operator)
   const double* cur_dinv = nullptr;
-  int *Pptr = nullptr, *Pcol = nullptr, *Rptr = nullptr, *Rrow = nullptr;
-  double *Pval = nullptr, *Rval = nullptr;
+  // transfers to the next level, CSR with packed 8-byte entries {index, float value}: the prolongator values are
+  // rounded to fp32 at setup (P, R = P^T and the Galerkin products all use the same rounded numbers)
+  int *Pptr = nullptr, *Rptr = nullptr;
+  int2 *Pent = nullptr, *Rent = nullptr;
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
 };
 
@@ -148,91 +149,50 @@ __global__ void k_amg_jac0(int n, double om, const double* __restrict__ dinv, co
 }
 
 // bc = R t   (R = P^T stored row-wise: a deterministic gather)
-__global__ void k_amg_restrict(int nc, const int* __restrict__ Rptr, const int* __restrict__ Rrow,
-                               const double* __restrict__ Rval, const double* __restrict__ t, double* __restrict__ bc,
-                               const PcgScalars* scal) {
+__global__ void k_amg_restrict(int nc, const int* __restrict__ Rptr, const int2* __restrict__ Rent,
+                               const double* __restrict__ t, double* __restrict__ bc, const PcgScalars* scal) {
   if (scal->done) return;
   for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += gridDim.x * blockDim.x) {
     double s = 0.0;
     const int e = Rptr[I + 1];
-    for (int q = Rptr[I]; q < e; ++q) s += Rval[q] * __ldg(t + Rrow[q]);
+    for (int q = Rptr[I]; q < e; ++q) {
+      const int2 en = Rent[q];
+      s += (double)__int_as_float(en.y) * __ldg(t + en.x);
+    }
     bc[I] = s;
   }
 }
 
 // x += P xc
-__global__ void k_amg_prolong(int n, const int* __restrict__ Pptr, const int* __restrict__ Pcol,
-                              const double* __restrict__ Pval, const double* __restrict__ xc, double* __restrict__ x,
-                              const PcgScalars* scal) {
+__global__ void k_amg_prolong(int n, const int* __restrict__ Pptr, const int2* __restrict__ Pent,
+                              const double* __restrict__ xc, double* __restrict__ x, const PcgScalars* scal) {
   if (scal->done) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double s = 0.0;
     const int e = Pptr[i + 1];
-    for (int m = Pptr[i]; m < e; ++m) s += Pval[m] * __ldg(xc + Pcol[m]);
+    for (int m = Pptr[i]; m < e; ++m) {
+      const int2 en = Pent[m];
+      s += (double)__int_as_float(en.y) * __ldg(xc + en.x);
+    }
     x[i] += s;
   }
 }
 
-// Galerkin product on the frozen pattern: C = R A P.  One warp per coarse row I, lane t owns the coarse entry t of
-// that row; all lanes walk the same sequence (fine rows i of R(I,:), entries (i,j) of A, entries (j,J) of P) and
-// keep the products whose J is their own column.  Fixed summation order per entry -> bitwise reproducible.
-__global__ void __launch_bounds__(256) k_amg_rap(int nc, const int* __restrict__ f_slice_ptr, const int* __restrict__ f_col,
-                                                 const double* __restrict__ f_val, const int* __restrict__ Pptr,
-                                                 const int* __restrict__ Pcol, const double* __restrict__ Pval,
-                                                 const int* __restrict__ Rptr, const int* __restrict__ Rrow,
-                                                 const double* __restrict__ Rval, const int* __restrict__ c_rowptr,
-                                                 const int* __restrict__ c_slice_ptr, const int* __restrict__ c_col,
-                                                 double* __restrict__ c_val, double* __restrict__ c_dinv) {
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int I = gw; I < nc; I += nw) {
-    const int len = c_rowptr[I + 1] - c_rowptr[I];
-    const int cbase = c_slice_ptr[I >> 5] + (I & 31);
-    const int q0 = Rptr[I], q1 = Rptr[I + 1];
-    for (int t0 = 0; t0 < len; t0 += 32) {
-      const int t = t0 + lane;
-      const int myJ = t < len ? c_col[cbase + 32 * t] : -1;
-      double acc = 0.0;
-      for (int q = q0; q < q1; ++q) {
-        const int i = Rrow[q];
-        const double r = Rval[q];
-        const int fb = f_slice_ptr[i >> 5];
-        const int w = (f_slice_ptr[(i >> 5) + 1] - fb) >> 5;
-        int idx = fb + (i & 31);
-        for (int k = 0; k < w; ++k, idx += 32) {
-          const double a = f_val[idx];
-          if (a == 0.0) continue;   // padding and the exact zeros of right-angle meshes / eliminated entries
-          const int j = f_col[idx];
-          const double ra = r * a;
-          const int m1 = Pptr[j + 1];
-          for (int m = Pptr[j]; m < m1; ++m)
-            if (Pcol[m] == myJ) acc += ra * Pval[m];
-        }
-      }
-      if (t < len) {
-        c_val[cbase + 32 * t] = acc;
-        if (myJ == I) c_dinv[I] = 1.0 / acc;
-      }
-    }
-  }
-}
-
-// Same product, parallel over the lanes (the production path; k_amg_rap above is kept for coarse rows longer than
-// kRapSlots entries).  One warp per coarse row I.  The (fine row of R(I,:), fine entry) pairs are dealt round-robin
-// to the 32 lanes; every lane multiplies out its pairs with the prolongator rows and adds each product into its
-// PRIVATE accumulator row (shared memory, slot found by binary search in the staged sorted coarse row), so the
-// loads of the 32 lanes overlap instead of forming one dependent chain.  Then lane t sums column t of the 32
-// private rows in lane order.  The assignment of products to lanes and both summation orders are fixed functions
-// of the pattern: bitwise reproducible, no atomics.
-constexpr int kRapBatch = 4;   // pairs per lane whose loads are issued together (memory-level parallelism)
+// Galerkin product on the frozen pattern: C = R A P.  One warp per coarse row I.  The (fine row i of R(I,:), entry k
+// of fine row i) pairs are dealt to the 32 lanes entry-major (consecutive lanes = consecutive fine rows at the same
+// entry position: aggregates are index-local, so their SELL entries and the prolongator rows of their neighbours
+// share sectors); kRapBatch pairs per lane are loaded together (memory-level parallelism).  Every lane multiplies
+// its pairs out with the prolongator rows and adds each product into its PRIVATE accumulator row (shared memory,
+// slot found by binary search in the staged sorted coarse row); then lane t sums column t of the 32 private rows
+// in lane order.  The assignment of products to lanes and both summation orders are fixed functions of the
+// pattern: no atomics, bitwise reproducible.  Coarse rows longer than SLOTS entries take the serial walk at the end.
+constexpr int kRapBatch = 4;
 
 template <int SLOTS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, int wmax, const int* __restrict__ f_slice_ptr,
+__global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, const int* __restrict__ f_slice_ptr,
                                                         const int* __restrict__ f_col, const double* __restrict__ f_val,
-                                                        const int* __restrict__ Pptr, const int* __restrict__ Pcol,
-                                                        const double* __restrict__ Pval, const int* __restrict__ Rptr,
-                                                        const int* __restrict__ Rrow, const double* __restrict__ Rval,
+                                                        const int* __restrict__ Pptr, const int2* __restrict__ Pent,
+                                                        const int* __restrict__ Rptr, const int2* __restrict__ Rent,
                                                         const int* __restrict__ c_rowptr, const int* __restrict__ c_slice_ptr,
                                                         const int* __restrict__ c_col, double* __restrict__ c_val,
                                                         double* __restrict__ c_dinv) {
@@ -246,31 +206,39 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, int wmax, const
   for (int I = gw; I < nc; I += nw) {
     const int len = c_rowptr[I + 1] - c_rowptr[I];
     const int cbase = c_slice_ptr[I >> 5] + (I & 31);
-    const int q0 = Rptr[I], q1 = Rptr[I + 1];
+    const int q0 = Rptr[I], nq = Rptr[I + 1] - q0;
     if (len <= SLOTS) {
       if (lane < len) ccols[lane] = c_col[cbase + 32 * lane];
       for (int t = 0; t < len; ++t) tab[lane * STRIDE + t] = 0.0;
       __syncwarp();
-      const int npairs = (q1 - q0) * wmax;
+      // widest fine row among the rows of R(I,:) (lanes beyond it have nothing to do)
+      int wloc = 0;
+      for (int q = lane; q < nq; q += 32) {
+        const int i = Rent[q0 + q].x;
+        wloc = max(wloc, (f_slice_ptr[(i >> 5) + 1] - f_slice_ptr[i >> 5]) >> 5);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) wloc = max(wloc, __shfl_xor_sync(0xffffffffu, wloc, o));
+      const int npairs = nq * wloc;
       for (int e0 = lane; e0 < npairs; e0 += 32 * kRapBatch) {
-        int fi[kRapBatch], kk[kRapBatch], idx[kRapBatch], jj[kRapBatch], m0[kRapBatch], m1[kRapBatch];
-        double rv[kRapBatch], av[kRapBatch];
+        int idx[kRapBatch], jj[kRapBatch], m0[kRapBatch], m1[kRapBatch];
+        int2 re[kRapBatch];
+        double av[kRapBatch];
 #pragma unroll
         for (int u = 0; u < kRapBatch; ++u) {
           const int e = e0 + 32 * u;
-          const int dq = e / wmax;
-          kk[u] = e - dq * wmax;
-          const bool ok = e < npairs;
-          fi[u] = ok ? Rrow[q0 + dq] : -1;
-          rv[u] = ok ? Rval[q0 + dq] : 0.0;
+          const int k = e / nq;
+          idx[u] = k;                                  // entry position for now
+          re[u] = e < npairs ? Rent[q0 + (e - k * nq)] : make_int2(-1, 0);
         }
 #pragma unroll
         for (int u = 0; u < kRapBatch; ++u) {
+          const int i = re[u].x, k = idx[u];
           idx[u] = -1;
-          if (fi[u] >= 0) {
-            const int fb = f_slice_ptr[fi[u] >> 5];
-            const int w = (f_slice_ptr[(fi[u] >> 5) + 1] - fb) >> 5;
-            if (kk[u] < w) idx[u] = fb + 32 * kk[u] + (fi[u] & 31);
+          if (i >= 0) {
+            const int fb = f_slice_ptr[i >> 5];
+            const int w = (f_slice_ptr[(i >> 5) + 1] - fb) >> 5;
+            if (k < w) idx[u] = fb + 32 * k + (i & 31);
           }
         }
 #pragma unroll
@@ -286,15 +254,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, int wmax, const
         }
 #pragma unroll
         for (int u = 0; u < kRapBatch; ++u) {
-          const double ra = rv[u] * av[u];
+          const double ra = (double)__int_as_float(re[u].y) * av[u];
           for (int m = m0[u]; m < m1[u]; ++m) {
-            const int J = Pcol[m];
+            const int2 pe = Pent[m];
             int lo = 0, hi = len;
             while (lo < hi) {
               const int mid = (lo + hi) >> 1;
-              if (ccols[mid] < J) lo = mid + 1; else hi = mid;
+              if (ccols[mid] < pe.x) lo = mid + 1; else hi = mid;
             }
-            tab[lane * STRIDE + lo] += ra * Pval[m];
+            tab[lane * STRIDE + lo] += ra * (double)__int_as_float(pe.y);
           }
         }
       }
@@ -312,9 +280,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, int wmax, const
         const int t = t0 + lane;
         const int myJ = t < len ? c_col[cbase + 32 * t] : -1;
         double acc = 0.0;
-        for (int q = q0; q < q1; ++q) {
-          const int i = Rrow[q];
-          const double r = Rval[q];
+        for (int q = q0; q < q0 + nq; ++q) {
+          const int2 en = Rent[q];
+          const int i = en.x;
+          const double r = (double)__int_as_float(en.y);
           const int fb = f_slice_ptr[i >> 5];
           const int w = (f_slice_ptr[(i >> 5) + 1] - fb) >> 5;
           int idx = fb + (i & 31);
@@ -324,8 +293,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, int wmax, const
             const int j = f_col[idx];
             const double ra = r * a;
             const int m1 = Pptr[j + 1];
-            for (int m = Pptr[j]; m < m1; ++m)
-              if (Pcol[m] == myJ) acc += ra * Pval[m];
+            for (int m = Pptr[j]; m < m1; ++m) {
+              const int2 pe = Pent[m];
+              if (pe.x == myJ) acc += ra * (double)__int_as_float(pe.y);
+            }
           }
         }
         if (t < len) {
@@ -338,25 +309,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, int wmax, const
 }
 
 // Dense inverse of the coarsest operator: in-place Gauss-Jordan without pivoting (the operator is SPD), one CTA.
+// IN_SHARED: the n x n matrix lives in dynamic shared memory (n <= kAmgDenseShared) and is written out at the end;
+// otherwise it is eliminated in global memory (fallback for hierarchies whose coarsening stalled early).
+constexpr int kAmgDenseShared = 128;
+
+template <bool IN_SHARED>
 __global__ void __launch_bounds__(1024) k_amg_dense_inverse(int n, const int* __restrict__ rowptr,
                                                             const int* __restrict__ slice_ptr, const int* __restrict__ col,
                                                             const double* __restrict__ val, double* __restrict__ Ainv) {
+  extern __shared__ double sh_dyn[];
   __shared__ double shrow[kAmgDenseMax], shcol[kAmgDenseMax];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int nn = n * n;
-  for (int e = tid; e < nn; e += nt) Ainv[e] = 0.0;
+  double* M = IN_SHARED ? sh_dyn : Ainv;
+  for (int e = tid; e < nn; e += nt) M[e] = 0.0;
   __syncthreads();
   for (int i = tid; i < n; i += nt) {
     const int len = rowptr[i + 1] - rowptr[i];
     const int base = slice_ptr[i >> 5] + (i & 31);
-    for (int k = 0; k < len; ++k) Ainv[i * n + col[base + 32 * k]] = val[base + 32 * k];
+    for (int k = 0; k < len; ++k) M[i * n + col[base + 32 * k]] = val[base + 32 * k];
   }
   __syncthreads();
   for (int k = 0; k < n; ++k) {
-    const double p = 1.0 / Ainv[k * n + k];
+    const double p = 1.0 / M[k * n + k];
     for (int j = tid; j < n; j += nt) {
-      shrow[j] = (j == k) ? p : Ainv[k * n + j] * p;
-      shcol[j] = Ainv[j * n + k];
+      shrow[j] = (j == k) ? p : M[k * n + j] * p;
+      shcol[j] = M[j * n + k];
     }
     __syncthreads();
     for (int e = tid; e < nn; e += nt) {
@@ -364,25 +342,29 @@ __global__ void __launch_bounds__(1024) k_amg_dense_inverse(int n, const int* __
       double v;
       if (i == k) v = shrow[j];
       else if (j == k) v = -(shcol[i] * p);
-      else v = Ainv[e] - shcol[i] * shrow[j];
-      Ainv[e] = v;
+      else v = M[e] - shcol[i] * shrow[j];
+      M[e] = v;
     }
     __syncthreads();
   }
+  if (IN_SHARED)
+    for (int e = tid; e < nn; e += nt) Ainv[e] = M[e];
 }
 
-// x = Ainv b on the coarsest level (one CTA; the inverse of a symmetric matrix is read column-wise = coalesced)
-__global__ void __launch_bounds__(kAmgDenseMax) k_amg_dense_apply(int n, const double* __restrict__ Ainv,
-                                                                const double* __restrict__ b, double* __restrict__ x,
-                                                                const PcgScalars* scal) {
+// x = Ainv b on the coarsest level: one CTA, one warp per row (lanes stride the row: coalesced), warp-shuffle sum
+__global__ void __launch_bounds__(1024) k_amg_dense_apply(int n, const double* __restrict__ Ainv,
+                                                          const double* __restrict__ b, double* __restrict__ x,
+                                                          const PcgScalars* scal) {
   __shared__ double shb[kAmgDenseMax];
   if (scal->done) return;
   for (int j = threadIdx.x; j < n; j += blockDim.x) shb[j] = b[j];
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = wid; i < n; i += nwarp) {
     double s = 0.0;
-    for (int j = 0; j < n; ++j) s += Ainv[j * n + i] * shb[j];
-    x[i] = s;
+    for (int j = lane; j < n; j += 32) s += Ainv[i * n + j] * shb[j];
+    s = warp_sum(s);
+    if (lane == 0) x[i] = s;
   }
 }
 
@@ -427,9 +409,11 @@ __global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int
 
 // x += alpha p; r -= alpha q; the block that finishes last takes the convergence decision, so that the cycle
 // kernels behind it exit immediately once the residual is small enough.
+// Fused: xs = om * dinv * r, the first damped-Jacobi sweep of the V-cycle on the finest level (saves a pass over r).
 __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, int it, int max_it,
                                                            const double* __restrict__ p, const double* __restrict__ q,
                                                            double* __restrict__ x, double* __restrict__ r,
+                                                           const double* __restrict__ dinv, double om, double* __restrict__ xs,
                                                            double* partials, PcgScalars* scal) {
   __shared__ double sh_red[32];
   if (scal->done) return;
@@ -451,6 +435,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, in
     const double ri = r[i] - alpha * q[i];
     x[i] = xi;
     r[i] = ri;
+    xs[i] = om * (dinv[i] * ri);
     s_rr += ri * ri;
     s_max = fmax(s_max, fabs(ri));
   }
@@ -495,8 +480,8 @@ void amg_free(Context* ctx) {
     AmgLevelDev& L = A->lv[l];
     if (L.owns) { amg_release(L.slice_ptr); amg_release(L.col); amg_release(L.rowptr); }
     amg_release(L.val); amg_release(L.dinv);
-    amg_release(L.Pptr); amg_release(L.Pcol); amg_release(L.Pval);
-    amg_release(L.Rptr); amg_release(L.Rrow); amg_release(L.Rval);
+    amg_release(L.Pptr); amg_release(L.Pent);
+    amg_release(L.Rptr); amg_release(L.Rent);
     if (l > 0) { amg_release(L.b); amg_release(L.x2); }
     amg_release(L.x); amg_release(L.t);
   }
@@ -592,15 +577,25 @@ int amg_setup(Context* ctx) {
     if ((rc = amg_alloc(ctx, &L.x, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.t, (size_t)L.n))) return rc;
     if (l + 1 < nlev) {
       L.nc = HL.nc;
-      if ((rc = amg_upload(ctx, &L.Pptr, HL.Pptr)) || (rc = amg_upload(ctx, &L.Pcol, HL.Pcol)) ||
-          (rc = amg_upload(ctx, &L.Pval, HL.Pval)) || (rc = amg_upload(ctx, &L.Rptr, HL.Rptr)) ||
-          (rc = amg_upload(ctx, &L.Rrow, HL.Rrow)) || (rc = amg_upload(ctx, &L.Rval, HL.Rval)))
+      std::vector<int2> pe(HL.Pcol.size()), re(HL.Rrow.size());
+      for (size_t k = 0; k < pe.size(); ++k) {
+        const float pv = (float)HL.Pval[k], rv = (float)HL.Rval[k];   // exact: the host rounded them to fp32 already
+        int pb, rb;
+        memcpy(&pb, &pv, 4); memcpy(&rb, &rv, 4);
+        pe[k] = make_int2(HL.Pcol[k], pb);
+        re[k] = make_int2(HL.Rrow[k], rb);
+      }
+      if ((rc = amg_upload(ctx, &L.Pptr, HL.Pptr)) || (rc = amg_upload(ctx, &L.Pent, pe)) ||
+          (rc = amg_upload(ctx, &L.Rptr, HL.Rptr)) || (rc = amg_upload(ctx, &L.Rent, re)))
         return rc;
+      DDPS_CUDA(cudaStreamSynchronize(ctx->stream));   // pe, re go out of scope
     }
     DDPS_CUDA(cudaStreamSynchronize(ctx->stream));   // the host vectors of this level go out of scope
   }
   const int nL = A->lv[nlev - 1].n;
   if ((rc = amg_alloc(ctx, &A->dense, (size_t)nL * nL))) return rc;
+  DDPS_CUDA(cudaFuncSetAttribute(k_amg_dense_inverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kAmgDenseShared * kAmgDenseShared * (int)sizeof(double)));
   if ((rc = amg_alloc(ctx, &A->z, (size_t)n))) return rc;
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   A->ready = true;
@@ -645,24 +640,24 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv) {
   for (int l = 0; l + 1 < A.nlev; ++l) {
     AmgLevelDev& F = A.lv[l];
     AmgLevelDev& C = A.lv[l + 1];
-    if (ctx->opts.reserved[0] == 1) {   // A/B switch (profiling): the serial-walk kernel
-      k_amg_rap<<<amg_grid(ctx, (int64_t)C.n * 32, 256), 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval,
-                                                                               F.Rptr, F.Rrow, F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
-    } else if (C.wmax <= 16) {          // short coarse rows: small private tables, 48 resident warps per SM
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 6));
-      k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.wmax, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr, F.Rrow,
-                                                       F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+    if (C.wmax <= 16) {   // short coarse rows: small private tables, more resident warps per SM
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 5));
+      k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
+                                                       C.slice_ptr, C.col, C.val, C.dinv);
     } else {
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 3) / 4, (int64_t)ctx->num_sms * 6));
-      k_amg_rap2<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.wmax, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pcol, F.Pval, F.Rptr, F.Rrow,
-                                                       F.Rval, C.rowptr, C.slice_ptr, C.col, C.val, C.dinv);
+      k_amg_rap2<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
+                                                       C.slice_ptr, C.col, C.val, C.dinv);
     }
     C.cur_val = C.val;
     C.cur_dinv = C.dinv;
     ctx->stats.kernel_launches++;
   }
   const AmgLevelDev& L = A.lv[A.nlev - 1];
-  k_amg_dense_inverse<<<1, 1024, 0, ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, A.dense);
+  if (L.n <= kAmgDenseShared)
+    k_amg_dense_inverse<true><<<1, 1024, (size_t)L.n * L.n * sizeof(double), ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, A.dense);
+  else
+    k_amg_dense_inverse<false><<<1, 1024, 0, ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, A.dense);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
   return 0;
@@ -678,7 +673,7 @@ static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x,
 }
 
 // z = B r: one V(1,1) cycle from the zero initial guess.  dot_rz: also leave r.z in scal->sums[1].
-int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz) {
+static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz, bool have_first_sweep) {
   Amg& A = *ctx->amg;
   const double om = A.omega;
   cudaStream_t st = ctx->stream;
@@ -686,19 +681,22 @@ int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz) {
   A.lv[0].x2 = z;
   for (int l = 0; l + 1 < A.nlev; ++l) {
     AmgLevelDev& L = A.lv[l];
-    k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);
+    if (!(l == 0 && have_first_sweep)) {   // the CG's update kernel already produced the first sweep of the finest level
+      k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);
+      ctx->stats.kernel_launches++;
+    }
     launch_amg_spmv<1, false>(ctx, L, L.x, L.b, om, L.t);
-    k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rrow, L.Rval, L.t, A.lv[l + 1].b, ctx->scal);
-    ctx->stats.kernel_launches += 2;
+    k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, A.lv[l + 1].b, ctx->scal);
+    ctx->stats.kernel_launches++;
   }
   {
     AmgLevelDev& L = A.lv[A.nlev - 1];
-    k_amg_dense_apply<<<1, kAmgDenseMax, 0, st>>>(L.n, A.dense, L.b, L.x2, ctx->scal);
+    k_amg_dense_apply<<<1, 1024, 0, st>>>(L.n, A.dense, L.b, L.x2, ctx->scal);
     ctx->stats.kernel_launches++;
   }
   for (int l = A.nlev - 2; l >= 0; --l) {
     AmgLevelDev& L = A.lv[l];
-    k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pcol, L.Pval, A.lv[l + 1].x2, L.x, ctx->scal);
+    k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pent, A.lv[l + 1].x2, L.x, ctx->scal);
     ctx->stats.kernel_launches++;
     if (l == 0 && dot_rz) launch_amg_spmv<2, true>(ctx, L, L.x, L.b, om, L.x2);
     else launch_amg_spmv<2, false>(ctx, L, L.x, L.b, om, L.x2);
@@ -706,6 +704,8 @@ int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz) {
   DDPS_CUDA(cudaGetLastError());
   return 0;
 }
+
+int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz) { return amg_vcycle_impl(ctx, r, z, dot_rz, false); }
 
 // ------------------------------------------------------------------------------------------------------------
 // CG preconditioned with the V-cycle
@@ -717,8 +717,9 @@ int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it) {
   int rc;
   const int g2 = amg_grid(ctx, n, kVecBlock);
   if ((rc = launch_spmv_dot(ctx, A.lv[0].cur_val, ctx->p, ctx->q))) return rc;    // q = A p, p.q -> sums[0]
-  k_apcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, ctx->partials, ctx->scal);
-  if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;                        // z = B r, r.z -> sums[1]
+  k_apcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
+                                                   A.lv[0].x, ctx->partials, ctx->scal);
+  if ((rc = amg_vcycle_impl(ctx, ctx->r, A.z, true, true))) return rc;             // z = B r, r.z -> sums[1]
   k_apcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, 0, 0.0, A.z, ctx->p, ctx->scal);
   ctx->stats.kernel_launches += 2;
   return 0;

@@ -13,7 +13,7 @@ namespace ddps {
 struct AmgParams {
   double theta = 0.25;      // strength threshold
   double omega = 2.0 / 3.0; // prolongator smoothing + Jacobi smoother damping
-  int coarse_max = 400;     // stop coarsening at this size (dense inverse on the device, cap kAmgDenseMax)
+  int coarse_max = 128;     // stop coarsening at this size (dense inverse on the device: shared memory up to 128 rows)
   int max_levels = 12;
   int nthreads = 0;         // 0: min(16, hardware concurrency)
 };

@@ -167,7 +167,9 @@ void smooth_prolongator(AmgHostLevel& L, const unsigned char* fixed, double omeg
     for (int64_t i = lo; i < hi; ++i) {
       const int cnt = prolongator_row(L, fixed, omega, (int)i, ag.data(), v.data());
       std::copy(ag.begin(), ag.begin() + cnt, L.Pcol.begin() + L.Pptr[i]);
-      std::copy(v.begin(), v.begin() + cnt, L.Pval.begin() + L.Pptr[i]);
+      // the transfer operators are stored in fp32 on the device: round here so that P, R = P^T and every Galerkin
+      // product (host and device) use the same numbers
+      for (int c = 0; c < cnt; ++c) L.Pval[L.Pptr[i] + c] = (double)(float)v[c];
     }
   });
 }

@@ -70,7 +70,8 @@ def test_hierarchy_against_scipy(D, O, which):
             S = sp.diags((~fixed).astype(float)) @ S
         ref = (S @ T).tocsr()
         d = (ref - P).tocoo()
-        assert (np.max(np.abs(d.data)) if d.nnz else 0.0) <= 1e-14
+        assert (np.max(np.abs(d.data)) if d.nnz else 0.0) <= 1e-7        # ... stored in fp32 on the device:
+        assert np.array_equal(P.data, P.data.astype(np.float32).astype(np.float64))   # rounded once, on the host
         # coarse base operator = Galerkin product, sorted columns, pattern contains the structural product
         G = (P.T @ Al @ P).tocsr()
         Ac = mats[l + 1][0]
