@@ -136,6 +136,9 @@ def main():
     ap.add_argument("--workload", default="s16", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precond", default="auto", choices=["auto", "amg", "jacobi"],
+                    help="preconditioner of the hand-written CG: amg = smoothed-aggregation multigrid V-cycle (single GPU), "
+                         "jacobi = the diagonal preconditioner; auto = amg on one GPU, jacobi with a communicator")
     ap.add_argument("--pcg-cap", type=int, default=0,
                     help="PROFILING ONLY: cap every PCG solve at this many iterations (keeps an ncu launch list short); "
                          "the printed value is then not a benchmark number")
@@ -169,10 +172,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    precond = args.precond if args.precond != "auto" else ("amg" if world == 1 else "jacobi")
+    if precond == "amg" and world > 1:
+        precond = "jacobi"   # the multigrid hierarchy is single-GPU in this round
+    sopts = dict(precond=1) if precond == "amg" else {}
     pr = problem()
     mesh = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
     smp = D.api.sample_ddpe(mesh, pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
-    s = D.Session(local, comm=comm)
+    s = D.Session(local, comm=comm, **sopts)
     if args.pcg_cap > 0:
         s.set_opts(lin_max_it=args.pcg_cap, lin_cap_ok=1, max_newton=3)
     s.set_mesh(mesh)
@@ -212,8 +219,19 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_spmv<true> (SELL-32 SpMV + fused p.Ap)", "achieved": by_spmv / ms_spmv / 1e6,
                 "peak": peak, "unit": "GB/s", "frac": by_spmv / ms_spmv / 1e6 / peak, "traffic": traffic,
                 "peak_source": peak_src, "algo_bytes_per_launch": by_spmv, "ms_per_launch": ms_spmv,
-                "pcg_iteration": {"achieved": by_pcg / ms_pcg / 1e6, "frac": by_pcg / ms_pcg / 1e6 / peak, "ms": ms_pcg},
+                "pcg_iteration": {"achieved": by_pcg / ms_pcg / 1e6, "frac": by_pcg / ms_pcg / 1e6 / peak, "ms": ms_pcg,
+                                  "what": "one Jacobi-PCG iteration (3 kernels)"},
                 "assembly_uv": {"achieved": by_asm / ms_asm / 1e6, "frac": by_asm / ms_asm / 1e6 / peak, "ms": ms_asm}}
+    if precond == "amg":
+        # the multigrid-preconditioned iteration: fine-level SpMV x3 (this kernel and its two fused-epilogue variants) +
+        # transfers + coarse levels; the per-operator numeric phase (Galerkin products + coarsest inverse)
+        ms_it, _ = s.time_kernel(6, 2, 20)
+        ms_vc, _ = s.time_kernel(8, 2, 20)
+        ms_num, _ = s.time_kernel(7, 2, 10)
+        roofline["amg"] = {"levels": s.amg_levels(), "ms_per_cg_iteration": ms_it, "ms_per_vcycle": ms_vc,
+                           "ms_numeric_phase_per_operator": ms_num,
+                           "fine_spmv_share_of_iteration": 3 * ms_spmv / ms_it,
+                           "t_hierarchy_setup_ms": st1["t_amg_setup_ms"]}
 
     # end to end through the C ABI with host buffers: mesh + coefficient uploads, setup, K steps, D2H of V,u,v
     e2e = None
@@ -225,7 +243,7 @@ def main():
         d2h = 3 * 8 * mesh.nq
         barrier()
         t0 = time.perf_counter()
-        s2 = D.Session(local, comm=comm) if comm is None else None
+        s2 = D.Session(local, comm=comm, **sopts) if comm is None else None
         if s2 is None:   # multi-GPU: a communicator cannot be re-created from the same id; reuse a fresh one
             ident2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
@@ -247,7 +265,9 @@ def main():
             t_e2e = float(t.item())
         e2e = {"value": args.steps / t_e2e, "unit": "1/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e,
-               "note": "cold start: mesh+coefficient H2D from pinned host buffers, pattern build, first K Gummel iterations, D2H of V,u,v"}
+               "note": "cold start: mesh+coefficient H2D from pinned host buffers, pattern build"
+                       + (", multigrid hierarchy setup (host)" if precond == "amg" else "") + ", first K Gummel iterations, D2H of V,u,v",
+               "setup_seconds": s2.stats()["t_setup_ms"] / 1000.0 + s2.stats()["t_amg_setup_ms"] / 1000.0}
         s2.close()
 
     cpu = None
@@ -269,7 +289,10 @@ def main():
                                        f"({2 * nx * ny} triangles, {mesh.nq} nodes), one Gummel iteration per step",
                            "l2": "inputs larger than L2 (CSR values+columns 705 MB at s16); no flush needed",
                            "parallelism": f"node-partitioned x{world}" if world > 1 else "single GPU",
-                           "solver": "Jacobi-PCG, lin_rtol 1e-13, Newton corrections to 0.1*tol"},
+                           "solver": ("hand-written CG preconditioned with a smoothed-aggregation multigrid V(1,1) cycle "
+                                      "(opts.precond=1; SURVEY 8f rank 1), lin_rtol 1e-13, Newton corrections to 0.1*tol"
+                                      if precond == "amg" else "Jacobi-PCG, lin_rtol 1e-13, Newton corrections to 0.1*tol"),
+                           "preconditioner": precond},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "pcg_iterations": int(pcg_its),
                 "control": [float(c) for c in ctrl], "roofline": roofline, "cpu_baseline": cpu}
         if args.pcg_cap > 0:

@@ -525,6 +525,7 @@ int amg_setup(Context* ctx) {
   const double t2 = wall_ms();
   AmgHost H;
   AmgParams prm;
+  if (const char* e = getenv("DDPS_AMG_COARSE_MAX")) prm.coarse_max = std::max(8, std::min(kAmgDenseMax, atoi(e)));   // experiments
   const int nlev = amg_host_build(H, n, std::move(rp), std::move(cc), std::move(vv), fixed.data(), prm);
   const double t3 = wall_ms();
   if (nlev < 2 || nlev > kAmgMaxLevels || H.lv.back().n > kAmgDenseMax) return 0;   // no hierarchy: Jacobi-PCG stays

@@ -66,6 +66,8 @@ void mark_strong(const AmgHostLevel& L, const unsigned char* fixed, double theta
 }
 
 // Greedy aggregation (sequential: the result is a pure function of the matrix).  Returns the number of aggregates.
+int aggregate_small(const AmgHostLevel& L, const std::vector<unsigned char>& strong, std::vector<int>& agg, int cap);
+
 int aggregate(const AmgHostLevel& L, const std::vector<unsigned char>& strong, std::vector<int>& agg) {
   const int n = L.n;
   agg.assign(n, -1);
@@ -112,6 +114,46 @@ int aggregate(const AmgHostLevel& L, const std::vector<unsigned char>& strong, s
     for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
       if (strong[k] && agg[L.col[k]] < 0) agg[L.col[k]] = nc;
     ++nc;
+  }
+  return nc;
+}
+
+// Gentle coarsening for the last, tiny levels (the global smooth modes live there and a coarsening ratio of ~7
+// from a few hundred rows costs CG iterations): a free node takes at most `cap` of its strongest free strong
+// neighbours; leftovers join their strongest aggregated neighbour.
+int aggregate_small(const AmgHostLevel& L, const std::vector<unsigned char>& strong, std::vector<int>& agg, int cap) {
+  const int n = L.n;
+  agg.assign(n, -1);
+  int nc = 0;
+  std::vector<std::pair<double, int>> nb;
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    nb.clear();
+    bool any = false;
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+      if (!strong[k]) continue;
+      any = true;
+      if (agg[L.col[k]] < 0) nb.emplace_back(L.val[k], L.col[k]);   // most negative = strongest first
+    }
+    if (!any || nb.empty()) continue;
+    std::sort(nb.begin(), nb.end());
+    agg[i] = nc;
+    for (int q = 0; q < (int)nb.size() && q < cap; ++q) agg[nb[q].second] = nc;
+    ++nc;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    double best = 0.0;
+    int pick = -1;
+    bool any = false;
+    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+      if (!strong[k]) continue;
+      any = true;
+      const int a = agg[L.col[k]];
+      if (a >= 0 && -L.val[k] > best) { best = -L.val[k]; pick = a; }
+    }
+    if (pick >= 0) agg[i] = pick;
+    else if (any) agg[i] = nc++;
   }
   return nc;
 }
@@ -277,7 +319,8 @@ int amg_host_build(AmgHost& H, int n, std::vector<int>&& rowptr, std::vector<int
     const double t0 = now();
     mark_strong(L, fx, prm.theta, nthreads, strong);
     const double t1 = now();
-    const int nc = aggregate(L, strong, L.agg);
+    const int nc = (L.n <= prm.small_level && prm.small_cap > 0) ? aggregate_small(L, strong, L.agg, prm.small_cap)
+                                                                 : aggregate(L, strong, L.agg);
     const double t2 = now();
     if (nc <= 0 || nc > 0.7 * L.n) { L.agg.clear(); break; }   // coarsening stalled
     L.nc = nc;
@@ -317,6 +360,8 @@ int ddps_amg_host_create(ddps_amg_host** out, int64_t n, const int64_t* rowptr, 
   ddps::AmgParams prm;
   prm.nthreads = nthreads;
   if (coarse_max > 0) prm.coarse_max = coarse_max;
+  if (const char* e = getenv("DDPS_AMG_SMALL_LEVEL")) prm.small_level = atoi(e);   // experiments
+  if (const char* e = getenv("DDPS_AMG_SMALL_CAP")) prm.small_cap = atoi(e);
   ddps::amg_host_build(*h, (int)n, std::move(rp), std::move(cc), std::move(vv), fixed, prm);
   *out = h;
   return DDPS_OK;
