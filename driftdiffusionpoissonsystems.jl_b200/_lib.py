@@ -85,6 +85,7 @@ SIGNATURES = {
     "ddps_amg_host_free": (None, [C.c_void_p]),
     "ddps_amg_levels": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),
     "ddps_amg_numeric": (C.c_int, [C.c_void_p, C.c_int]),
+    "ddps_amg_get_level": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_double_p]),
     "ddps_amg_get_values": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
     "ddps_amg_apply": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
 }

@@ -379,6 +379,25 @@ class Session:
         self._check(self.lib.ddps_amg_levels(self.h, C.byref(nl), _lib.iptr(sizes)))
         return [int(v) for v in sizes[:nl.value]]
 
+    def amg_hierarchy(self):
+        """The hierarchy as it lives on the device: per level a dict with n, nnz, nc, rowptr, col (CSR pattern, sorted
+        columns) and, except on the coarsest level, Pptr, Pcol, Pval (prolongator n x nc, fp32 values)."""
+        out = []
+        for l in range(len(self.amg_levels())):
+            sz = np.zeros(4, dtype=np.int64)
+            self._check(self.lib.ddps_amg_get_level(self.h, l, _lib.iptr(sz), None, None, None, None, None))
+            n, nnz, nc, pnnz = (int(v) for v in sz)
+            lev = dict(n=n, nnz=nnz, nc=nc, rowptr=np.zeros(n + 1, np.int64), col=np.zeros(nnz, np.int64))
+            if nc:
+                lev.update(Pptr=np.zeros(n + 1, np.int64), Pcol=np.zeros(pnnz, np.int64), Pval=np.zeros(pnnz))
+                self._check(self.lib.ddps_amg_get_level(self.h, l, _lib.iptr(sz), _lib.iptr(lev["rowptr"]), _lib.iptr(lev["col"]),
+                                                        _lib.iptr(lev["Pptr"]), _lib.iptr(lev["Pcol"]), _lib.dptr(lev["Pval"])))
+            else:
+                self._check(self.lib.ddps_amg_get_level(self.h, l, _lib.iptr(sz), _lib.iptr(lev["rowptr"]), _lib.iptr(lev["col"]),
+                                                        None, None, None))
+            out.append(lev)
+        return out
+
     def amg_numeric(self, which=MAT_OP):
         self._check(self.lib.ddps_amg_numeric(self.h, int(which)))
 

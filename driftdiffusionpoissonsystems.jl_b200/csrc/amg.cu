@@ -19,42 +19,11 @@
 #include <thread>
 
 #include "amg.h"
+#include "amg_dev.cuh"
 #include "ddps_internal.cuh"
 #include "device_utils.cuh"
 
 namespace ddps {
-
-constexpr int kAmgMaxLevels = 12;
-constexpr int kAmgDenseMax = 512;
-
-struct AmgLevelDev {
-  int n = 0, nslices = 0, nc = 0, wmax = 0;   // wmax: longest row (= widest slice) of this level's matrix
-  int64_t nnz = 0, nentries = 0;
-  bool owns = false;                 // level 0 aliases the fine pattern of the context
-  int* slice_ptr = nullptr;
-  int* col = nullptr;
-  int* rowptr = nullptr;
-  double* val = nullptr;             // level >= 1: Galerkin values of the current operator (SELL order)
-  double* dinv = nullptr;            // level >= 1
-  const double* cur_val = nullptr;   // matrix / inverse diagonal used by the cycle (level 0: set per operator)
-  const double* cur_dinv = nullptr;
-  // transfers to the next level, CSR with packed 8-byte entries {index, float value}: the prolongator values are
-  // rounded to fp32 at setup (P, R = P^T and the Galerkin products all use the same rounded numbers)
-  int *Pptr = nullptr, *Rptr = nullptr;
-  int2 *Pent = nullptr, *Rent = nullptr;
-  double *b = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
-};
-
-struct Amg {
-  bool ready = false;
-  int nlev = 0;
-  AmgLevelDev lv[kAmgMaxLevels];
-  double* dense = nullptr;   // [n_coarsest^2] inverse of the coarsest operator
-  double* z = nullptr;       // [n0] preconditioned residual of the CG
-  double omega = 2.0 / 3.0;
-  double setup_ms = 0.0;
-  std::vector<int> h_rowptr[kAmgMaxLevels], h_slice_ptr[kAmgMaxLevels];   // kept for the debug export (levels >= 1)
-};
 
 namespace {
 
@@ -491,6 +460,64 @@ void amg_free(Context* ctx) {
   ctx->amg = nullptr;
 }
 
+// upload helpers of the host-built part of the hierarchy
+static int amg_install_pattern(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL) {
+  int rc;
+  L = AmgLevelDev();
+  L.n = HL.n;
+  L.nnz = (int64_t)HL.col.size();
+  // SELL-32 layout of the coarse pattern (same convention as the fine pattern: padding = value 0, own column)
+  L.nslices = (HL.n + 31) / 32;
+  std::vector<int> hsp(L.nslices + 1, 0);
+  for (int s = 0; s < L.nslices; ++s) {
+    int w = 0;
+    for (int r = s * 32; r < std::min(HL.n, s * 32 + 32); ++r) w = std::max(w, HL.rowptr[r + 1] - HL.rowptr[r]);
+    hsp[s + 1] = hsp[s] + 32 * w;
+    L.wmax = std::max(L.wmax, w);
+  }
+  L.nentries = hsp[L.nslices];
+  std::vector<int> hcol((size_t)L.nentries, 0);
+  for (int s = 0; s < L.nslices; ++s) {
+    const int w = (hsp[s + 1] - hsp[s]) / 32;
+    for (int lane = 0; lane < 32; ++lane) {
+      const int r = s * 32 + lane;
+      const int beg = r < HL.n ? HL.rowptr[r] : 0, len = r < HL.n ? HL.rowptr[r + 1] - beg : 0;
+      const int self = r < HL.n ? r : 0;
+      for (int k = 0; k < w; ++k) hcol[(size_t)hsp[s] + 32 * k + lane] = k < len ? HL.col[beg + k] : self;
+    }
+  }
+  L.owns = true;
+  if ((rc = amg_upload(ctx, &L.slice_ptr, hsp)) || (rc = amg_upload(ctx, &L.col, hcol)) || (rc = amg_upload(ctx, &L.rowptr, HL.rowptr)))
+    return rc;
+  if ((rc = amg_alloc(ctx, &L.val, (size_t)L.nentries)) || (rc = amg_alloc(ctx, &L.dinv, (size_t)L.n))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(L.val, 0, std::max<size_t>((size_t)L.nentries, 1) * sizeof(double), ctx->stream));
+  DDPS_CUDA(cudaMemsetAsync(L.dinv, 0, std::max<size_t>((size_t)L.n, 1) * sizeof(double), ctx->stream));
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+  return 0;
+}
+
+static int amg_install_transfers(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL) {
+  int rc;
+  L.nc = HL.nc;
+  std::vector<int2> pe(HL.Pcol.size()), re(HL.Rrow.size());
+  for (size_t k = 0; k < pe.size(); ++k) {
+    const float pv = (float)HL.Pval[k], rv = (float)HL.Rval[k];   // exact: the host rounded them to fp32 already
+    int pb, rb;
+    memcpy(&pb, &pv, 4); memcpy(&rb, &rv, 4);
+    pe[k] = make_int2(HL.Pcol[k], pb);
+    re[k] = make_int2(HL.Rrow[k], rb);
+  }
+  if ((rc = amg_upload(ctx, &L.Pptr, HL.Pptr)) || (rc = amg_upload(ctx, &L.Pent, pe)) || (rc = amg_upload(ctx, &L.Rptr, HL.Rptr)) ||
+      (rc = amg_upload(ctx, &L.Rent, re)))
+    return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Hierarchy of the freshly assembled base operator.  Levels with more than DDPS_AMG_DEV_MIN rows (default 100000) are
+// coarsened on the device (amg_setup.cu: only the strong-neighbour lists travel to the host for the greedy
+// aggregation); the small rest of the hierarchy is built by the host reference implementation (amg_host.cu) and
+// uploaded.  DDPS_AMG_HOST_SETUP=1 forces the host path for every level (A/B and fallback).
 int amg_setup(Context* ctx) {
   amg_free(ctx);
   if (ctx->nranks != 1 || !ctx->base_ready) return 0;   // multi-GPU: the Jacobi path stays in charge
@@ -498,100 +525,86 @@ int amg_setup(Context* ctx) {
   const Pattern& P = ctx->pat;
   const int n = P.nrows;
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
-  // fine pattern + base values -> host CSR
-  std::vector<int> rp(n + 1), cc(P.nnz), sp(P.nslices + 1);
-  std::vector<double> sv(P.nentries), vv(P.nnz);
-  std::vector<unsigned char> fixed(n);
-  DDPS_CUDA(cudaMemcpy(rp.data(), P.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  DDPS_CUDA(cudaMemcpy(cc.data(), P.csrcol, cc.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  DDPS_CUDA(cudaMemcpy(sp.data(), P.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  DDPS_CUDA(cudaMemcpy(sv.data(), ctx->val_base, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  DDPS_CUDA(cudaMemcpy(fixed.data(), ctx->isD, fixed.size(), cudaMemcpyDeviceToHost));
-  const double t1 = wall_ms();
-  {
-    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<std::thread> th;
-    const int chunk = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t)
-      th.emplace_back([&, t]() {
-        for (int r = t * chunk; r < std::min(n, (t + 1) * chunk); ++r) {
-          const int base = sp[r >> 5], lane = r & 31;
-          for (int k = 0; k < rp[r + 1] - rp[r]; ++k) vv[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
-        }
-      });
-    for (auto& x : th) x.join();
-  }
-  sv.clear(); sv.shrink_to_fit();
-  const double t2 = wall_ms();
-  AmgHost H;
   AmgParams prm;
   if (const char* e = getenv("DDPS_AMG_COARSE_MAX")) prm.coarse_max = std::max(8, std::min(kAmgDenseMax, atoi(e)));   // experiments
-  const int nlev = amg_host_build(H, n, std::move(rp), std::move(cc), std::move(vv), fixed.data(), prm);
-  const double t3 = wall_ms();
-  if (nlev < 2 || nlev > kAmgMaxLevels || H.lv.back().n > kAmgDenseMax) return 0;   // no hierarchy: Jacobi-PCG stays
+  const bool host_only = getenv("DDPS_AMG_HOST_SETUP") != nullptr;
+  const int dev_min = getenv("DDPS_AMG_DEV_MIN") ? atoi(getenv("DDPS_AMG_DEV_MIN")) : 100000;
+  const bool timing = getenv("DDPS_AMG_TIMING") != nullptr;
 
   Amg* A = new Amg();
   ctx->amg = A;
-  A->nlev = nlev;
   A->omega = prm.omega;
   int rc;
+  {
+    AmgLevelDev& L = A->lv[0];
+    L.n = n; L.nnz = P.nnz; L.nslices = P.nslices; L.nentries = P.nentries; L.wmax = P.max_row_len;
+    L.slice_ptr = P.slice_ptr; L.col = P.col; L.rowptr = P.rowptr; L.owns = false;
+    L.cur_val = ctx->val_base;
+  }
+  int nlev = 1;
+  // ---- device phase ----
+  while (!host_only && A->lv[nlev - 1].n > dev_min && A->lv[nlev - 1].n > prm.coarse_max && nlev < prm.max_levels) {
+    int nc = 0;
+    const double ta = wall_ms();
+    rc = amg_dev_coarsen(ctx, A, nlev - 1, nlev == 1 ? ctx->isD : nullptr, prm, &nc);
+    if (rc < 0) return rc;
+    if (rc > 0 || nc == 0) break;
+    if (timing) fprintf(stderr, "[ddps amg] level %d n=%d -> %d on the device: %.1f ms\n", nlev - 1, A->lv[nlev - 1].n, nc, wall_ms() - ta);
+    ++nlev;
+  }
+  const double t1 = wall_ms();
+  // ---- host phase: the rest of the hierarchy from level ld ----
+  const int ld = nlev - 1;
+  if (A->lv[ld].n > prm.coarse_max && nlev < prm.max_levels) {
+    const AmgLevelDev& LD = A->lv[ld];
+    const int m = LD.n;
+    std::vector<int> rp((size_t)m + 1), sp((size_t)LD.nslices + 1), scol((size_t)LD.nentries), cc((size_t)LD.nnz);
+    std::vector<double> sv((size_t)LD.nentries), vv((size_t)LD.nnz);
+    std::vector<unsigned char> fixed;
+    DDPS_CUDA(cudaMemcpy(rp.data(), LD.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    DDPS_CUDA(cudaMemcpy(sp.data(), LD.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    DDPS_CUDA(cudaMemcpy(scol.data(), LD.col, scol.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    DDPS_CUDA(cudaMemcpy(sv.data(), LD.cur_val, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ld == 0) {
+      fixed.resize(m);
+      DDPS_CUDA(cudaMemcpy(fixed.data(), ctx->isD, fixed.size(), cudaMemcpyDeviceToHost));
+    }
+    {
+      const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> th;
+      const int chunk = (m + nt - 1) / nt;
+      for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+          for (int r = t * chunk; r < std::min(m, (t + 1) * chunk); ++r) {
+            const int base = sp[r >> 5], lane = r & 31;
+            for (int k = 0; k < rp[r + 1] - rp[r]; ++k) {
+              cc[rp[r] + k] = scol[(size_t)base + 32 * k + lane];
+              vv[rp[r] + k] = sv[(size_t)base + 32 * k + lane];
+            }
+          }
+        });
+      for (auto& x : th) x.join();
+    }
+    std::vector<double>().swap(sv);
+    std::vector<int>().swap(scol);
+    AmgHost H;
+    AmgParams sub = prm;
+    sub.max_levels = prm.max_levels - ld;
+    const int nh = amg_host_build(H, m, std::move(rp), std::move(cc), std::move(vv), ld == 0 ? fixed.data() : nullptr, sub);
+    for (int k = 0; k < nh; ++k) {
+      AmgLevelDev& L = A->lv[ld + k];
+      if (k >= 1 && (rc = amg_install_pattern(ctx, L, H.lv[k]))) return rc;
+      if (k + 1 < nh && (rc = amg_install_transfers(ctx, L, H.lv[k]))) return rc;
+    }
+    nlev = ld + nh;
+  }
+  const double t2 = wall_ms();
+  if (nlev < 2 || A->lv[nlev - 1].n > kAmgDenseMax) { amg_free(ctx); return 0; }   // no hierarchy: Jacobi-PCG stays
+  A->nlev = nlev;
   for (int l = 0; l < nlev; ++l) {
-    const AmgHostLevel& HL = H.lv[l];
     AmgLevelDev& L = A->lv[l];
-    L.n = HL.n;
-    L.nnz = (int64_t)HL.col.size();
-    if (l == 0) {
-      L.nslices = P.nslices; L.nentries = P.nentries; L.wmax = P.max_row_len;
-      L.slice_ptr = P.slice_ptr; L.col = P.col; L.rowptr = P.rowptr; L.owns = false;
-    } else {
-      // SELL-32 layout of the coarse pattern (same convention as the fine pattern: padding = value 0, own column)
-      L.nslices = (HL.n + 31) / 32;
-      std::vector<int> hsp(L.nslices + 1, 0);
-      for (int s = 0; s < L.nslices; ++s) {
-        int w = 0;
-        for (int r = s * 32; r < std::min(HL.n, s * 32 + 32); ++r) w = std::max(w, HL.rowptr[r + 1] - HL.rowptr[r]);
-        hsp[s + 1] = hsp[s] + 32 * w;
-        L.wmax = std::max(L.wmax, w);
-      }
-      L.nentries = hsp[L.nslices];
-      std::vector<int> hcol((size_t)L.nentries, 0);
-      for (int s = 0; s < L.nslices; ++s) {
-        const int w = (hsp[s + 1] - hsp[s]) / 32;
-        for (int lane = 0; lane < 32; ++lane) {
-          const int r = s * 32 + lane;
-          const int beg = r < HL.n ? HL.rowptr[r] : 0, len = r < HL.n ? HL.rowptr[r + 1] - beg : 0;
-          const int self = r < HL.n ? r : 0;
-          for (int k = 0; k < w; ++k) hcol[(size_t)hsp[s] + 32 * k + lane] = k < len ? HL.col[beg + k] : self;
-        }
-      }
-      L.owns = true;
-      if ((rc = amg_upload(ctx, &L.slice_ptr, hsp)) || (rc = amg_upload(ctx, &L.col, hcol)) ||
-          (rc = amg_upload(ctx, &L.rowptr, HL.rowptr)))
-        return rc;
-      if ((rc = amg_alloc(ctx, &L.val, (size_t)L.nentries)) || (rc = amg_alloc(ctx, &L.dinv, (size_t)L.n))) return rc;
-      DDPS_CUDA(cudaMemsetAsync(L.val, 0, std::max<size_t>((size_t)L.nentries, 1) * sizeof(double), ctx->stream));
-      DDPS_CUDA(cudaMemsetAsync(L.dinv, 0, std::max<size_t>((size_t)L.n, 1) * sizeof(double), ctx->stream));
-      if ((rc = amg_alloc(ctx, &L.b, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.x2, (size_t)L.n))) return rc;
-      A->h_rowptr[l] = HL.rowptr;
-      A->h_slice_ptr[l] = hsp;
-    }
     if ((rc = amg_alloc(ctx, &L.x, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.t, (size_t)L.n))) return rc;
-    if (l + 1 < nlev) {
-      L.nc = HL.nc;
-      std::vector<int2> pe(HL.Pcol.size()), re(HL.Rrow.size());
-      for (size_t k = 0; k < pe.size(); ++k) {
-        const float pv = (float)HL.Pval[k], rv = (float)HL.Rval[k];   // exact: the host rounded them to fp32 already
-        int pb, rb;
-        memcpy(&pb, &pv, 4); memcpy(&rb, &rv, 4);
-        pe[k] = make_int2(HL.Pcol[k], pb);
-        re[k] = make_int2(HL.Rrow[k], rb);
-      }
-      if ((rc = amg_upload(ctx, &L.Pptr, HL.Pptr)) || (rc = amg_upload(ctx, &L.Pent, pe)) ||
-          (rc = amg_upload(ctx, &L.Rptr, HL.Rptr)) || (rc = amg_upload(ctx, &L.Rent, re)))
-        return rc;
-      DDPS_CUDA(cudaStreamSynchronize(ctx->stream));   // pe, re go out of scope
-    }
-    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));   // the host vectors of this level go out of scope
+    if (l >= 1 && ((rc = amg_alloc(ctx, &L.b, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.x2, (size_t)L.n)))) return rc;
   }
   const int nL = A->lv[nlev - 1].n;
   if ((rc = amg_alloc(ctx, &A->dense, (size_t)nL * nL))) return rc;
@@ -601,9 +614,9 @@ int amg_setup(Context* ctx) {
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   A->ready = true;
   A->setup_ms = wall_ms() - t0;
-  if (getenv("DDPS_AMG_TIMING"))
-    fprintf(stderr, "[ddps amg] setup %.1f ms: D2H %.1f, SELL->CSR %.1f, host hierarchy %.1f, SELL build + uploads %.1f\n", A->setup_ms,
-            t1 - t0, t2 - t1, t3 - t2, wall_ms() - t3);
+  if (timing)
+    fprintf(stderr, "[ddps amg] setup %.1f ms: device levels %.1f (%d), host levels + uploads %.1f, vectors %.1f\n", A->setup_ms, t1 - t0,
+            ld, t2 - t1, wall_ms() - t2);
   return 0;
 }
 
@@ -614,6 +627,43 @@ int amg_debug_levels(Context* ctx, int64_t* nlevels, int64_t* sizes, int cap) {
   return 0;
 }
 
+// Pattern (CSR, sorted columns) and prolongator (CSR) of a level as they live on the device.
+// sizes = {n, nnz, n_coarse (0 on the coarsest level), nnz(P)}; array pointers may be NULL.
+int amg_debug_get_level(Context* ctx, int level, int64_t* sizes, int64_t* rowptr, int64_t* col, int64_t* Pptr, int64_t* Pcol,
+                        double* Pval) {
+  if (!amg_ready(ctx) || level < 0 || level >= ctx->amg->nlev) { ctx->fail(DDPS_ERR_ARG, "no such multigrid level"); return DDPS_ERR_ARG; }
+  const AmgLevelDev& L = ctx->amg->lv[level];
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> pp;
+  if (L.Pptr) {
+    pp.resize((size_t)L.n + 1);
+    DDPS_CUDA(cudaMemcpy(pp.data(), L.Pptr, pp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (sizes) { sizes[0] = L.n; sizes[1] = L.nnz; sizes[2] = L.Pptr ? L.nc : 0; sizes[3] = L.Pptr ? pp[L.n] : 0; }
+  if (rowptr || col) {
+    std::vector<int> rp((size_t)L.n + 1), sp((size_t)L.nslices + 1), sc((size_t)L.nentries);
+    DDPS_CUDA(cudaMemcpy(rp.data(), L.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    DDPS_CUDA(cudaMemcpy(sp.data(), L.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    DDPS_CUDA(cudaMemcpy(sc.data(), L.col, sc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (rowptr) for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
+    if (col)
+      for (int r = 0; r < L.n; ++r)
+        for (int k = 0; k < rp[r + 1] - rp[r]; ++k) col[rp[r] + k] = sc[(size_t)sp[r >> 5] + 32 * k + (r & 31)];
+  }
+  if (L.Pptr && (Pptr || Pcol || Pval)) {
+    std::vector<int2> pe((size_t)pp[L.n]);
+    DDPS_CUDA(cudaMemcpy(pe.data(), L.Pent, pe.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+    if (Pptr) for (size_t i = 0; i < pp.size(); ++i) Pptr[i] = pp[i];
+    for (size_t k = 0; k < pe.size(); ++k) {
+      float f;
+      memcpy(&f, &pe[k].y, 4);
+      if (Pcol) Pcol[k] = pe[k].x;
+      if (Pval) Pval[k] = (double)f;
+    }
+  }
+  return 0;
+}
+
 // values (CSR order of the level's pattern) and inverse diagonal of level >= 1 after the last amg_numeric
 int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv) {
   if (!amg_ready(ctx) || level < 1 || level >= ctx->amg->nlev) { ctx->fail(DDPS_ERR_ARG, "no such multigrid level"); return DDPS_ERR_ARG; }
@@ -621,9 +671,10 @@ int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv)
   const AmgLevelDev& L = A.lv[level];
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<double> sv((size_t)L.nentries);
+  std::vector<int> rp((size_t)L.n + 1), sp((size_t)L.nslices + 1);
   DDPS_CUDA(cudaMemcpy(sv.data(), L.val, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  const std::vector<int>& rp = A.h_rowptr[level];
-  const std::vector<int>& sp = A.h_slice_ptr[level];
+  DDPS_CUDA(cudaMemcpy(rp.data(), L.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(sp.data(), L.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
   if (val_csr)
     for (int r = 0; r < L.n; ++r)
       for (int k = 0; k < rp[r + 1] - rp[r]; ++k) val_csr[rp[r] + k] = sv[(size_t)sp[r >> 5] + 32 * k + (r & 31)];
@@ -634,6 +685,19 @@ int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv)
 // ------------------------------------------------------------------------------------------------------------
 // per-operator numeric phase and the V-cycle
 // ------------------------------------------------------------------------------------------------------------
+void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, AmgLevelDev& C) {
+  if (C.wmax <= 16) {   // short coarse rows: small private tables, more resident warps per SM
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 5));
+    k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
+                                                     C.slice_ptr, C.col, C.val, C.dinv);
+  } else {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 3) / 4, (int64_t)ctx->num_sms * 6));
+    k_amg_rap2<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
+                                                     C.slice_ptr, C.col, C.val, C.dinv);
+  }
+  ctx->stats.kernel_launches++;
+}
+
 int amg_numeric(Context* ctx, const double* val, const double* dinv) {
   Amg& A = *ctx->amg;
   A.lv[0].cur_val = val;
@@ -641,18 +705,9 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv) {
   for (int l = 0; l + 1 < A.nlev; ++l) {
     AmgLevelDev& F = A.lv[l];
     AmgLevelDev& C = A.lv[l + 1];
-    if (C.wmax <= 16) {   // short coarse rows: small private tables, more resident warps per SM
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 5));
-      k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
-                                                       C.slice_ptr, C.col, C.val, C.dinv);
-    } else {
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 3) / 4, (int64_t)ctx->num_sms * 6));
-      k_amg_rap2<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, F.cur_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
-                                                       C.slice_ptr, C.col, C.val, C.dinv);
-    }
+    amg_launch_rap(ctx, F, F.cur_val, C);
     C.cur_val = C.val;
     C.cur_dinv = C.dinv;
-    ctx->stats.kernel_launches++;
   }
   const AmgLevelDev& L = A.lv[A.nlev - 1];
   if (L.n <= kAmgDenseShared)

@@ -36,6 +36,10 @@ struct AmgHost {
   std::vector<AmgHostLevel> lv;
 };
 
+inline int amg_small_cap(const AmgParams& prm, int n) { return (n <= prm.small_level) ? prm.small_cap : 0; }
+// aggregation on sorted strong-neighbour lists (shared by the host and the device setup paths); returns #aggregates
+int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::vector<int>& agg);
+
 int amg_host_build(AmgHost& H, int n, std::vector<int>&& rowptr, std::vector<int>&& col, std::vector<double>&& val,
                    const unsigned char* fixed, const AmgParams& prm);
 

@@ -1,0 +1,51 @@
+// Device-side structures of the multigrid hierarchy, shared by amg.cu (kernels, cycle, CG) and amg_setup.cu
+// (device-side hierarchy construction).
+#pragma once
+
+#include <vector>
+
+#include "amg.h"
+#include "ddps_internal.cuh"
+
+namespace ddps {
+
+constexpr int kAmgMaxLevels = 12;
+constexpr int kAmgDenseMax = 512;
+
+struct AmgLevelDev {
+  int n = 0, nslices = 0, nc = 0, wmax = 0;   // wmax: longest row (= widest slice) of this level's matrix
+  int64_t nnz = 0, nentries = 0;
+  bool owns = false;                 // level 0 aliases the fine pattern of the context
+  int* slice_ptr = nullptr;
+  int* col = nullptr;
+  int* rowptr = nullptr;
+  double* val = nullptr;             // level >= 1: Galerkin values of the current operator (SELL order)
+  double* dinv = nullptr;            // level >= 1
+  const double* cur_val = nullptr;   // matrix / inverse diagonal used by the cycle (level 0: set per operator)
+  const double* cur_dinv = nullptr;
+  // transfers to the next level, CSR with packed 8-byte entries {index, float value}: the prolongator values are
+  // rounded to fp32 at setup (P, R = P^T and the Galerkin products all use the same rounded numbers)
+  int *Pptr = nullptr, *Rptr = nullptr;
+  int2 *Pent = nullptr, *Rent = nullptr;
+  double *b = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
+};
+
+struct Amg {
+  bool ready = false;
+  int nlev = 0;
+  AmgLevelDev lv[kAmgMaxLevels];
+  double* dense = nullptr;   // [n_coarsest^2] inverse of the coarsest operator
+  double* z = nullptr;       // [n0] preconditioned residual of the CG
+  double omega = 2.0 / 3.0;
+  double setup_ms = 0.0;
+};
+
+
+// amg.cu: Galerkin product of the fine matrix values `f_val` (SELL order of level F) into level C (values + inverse diagonal)
+void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, AmgLevelDev& C);
+// amg_setup.cu: build transfers of level l and the pattern + base values of level l+1 on the device.
+// Returns 0 on success with *nc_out = rows of the next level (0: coarsening stalled, nothing installed), <0 on error,
+// >0 when the device path does not apply (caller falls back to the host path).
+int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, const AmgParams& prm, int* nc_out);
+
+}  // namespace ddps

@@ -44,10 +44,14 @@ void parallel_ranges(int64_t n, int nthreads, F&& fn) {
   for (auto& x : th) x.join();
 }
 
-// strong[k] = 1 when entry k (row i, column j != i) is a strong negative coupling of row i
-void mark_strong(const AmgHostLevel& L, const unsigned char* fixed, double theta, int nthreads, std::vector<unsigned char>& strong) {
-  strong.assign(L.col.size(), 0);
-  parallel_ranges(L.n, nthreads, [&](int, int64_t lo, int64_t hi) {
+// Strong-neighbour lists: for every row the columns j != i with -a_ij >= theta * max_k(-a_ik) (fixed rows/columns
+// excluded), sorted by strength (strongest first, ties by column).  The device setup (amg_setup.cu) produces the
+// same lists with a kernel; everything downstream (aggregation) only sees the lists.
+void strong_lists(const AmgHostLevel& L, const unsigned char* fixed, double theta, int nthreads, std::vector<int>& sptr,
+                  std::vector<int>& scol) {
+  const int n = L.n;
+  sptr.assign(n + 1, 0);
+  parallel_ranges(n, nthreads, [&](int, int64_t lo, int64_t hi) {
     for (int64_t i = lo; i < hi; ++i) {
       if (fixed && fixed[i]) continue;
       double m = 0.0;
@@ -57,106 +61,98 @@ void mark_strong(const AmgHostLevel& L, const unsigned char* fixed, double theta
       }
       if (!(m > 0.0)) continue;
       const double cut = theta * m;
+      int c = 0;
       for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
         const int j = L.col[k];
-        if (j != i && !(fixed && fixed[j]) && -L.val[k] >= cut) strong[k] = 1;
+        if (j != i && !(fixed && fixed[j]) && -L.val[k] >= cut) ++c;
       }
+      sptr[i + 1] = c;
+    }
+  });
+  for (int i = 0; i < n; ++i) sptr[i + 1] += sptr[i];
+  scol.resize(sptr[n]);
+  parallel_ranges(n, nthreads, [&](int, int64_t lo, int64_t hi) {
+    std::vector<std::pair<double, int>> nb;
+    for (int64_t i = lo; i < hi; ++i) {
+      if (sptr[i + 1] == sptr[i]) continue;
+      double m = 0.0;
+      for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+        const int j = L.col[k];
+        if (j != i && !(fixed && fixed[j])) m = std::max(m, -L.val[k]);
+      }
+      const double cut = theta * m;
+      nb.clear();
+      for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+        const int j = L.col[k];
+        if (j != i && !(fixed && fixed[j]) && -L.val[k] >= cut) nb.emplace_back(L.val[k], j);   // most negative first
+      }
+      std::sort(nb.begin(), nb.end());
+      for (size_t q = 0; q < nb.size(); ++q) scol[sptr[i] + q] = nb[q].second;
     }
   });
 }
 
-// Greedy aggregation (sequential: the result is a pure function of the matrix).  Returns the number of aggregates.
-int aggregate_small(const AmgHostLevel& L, const std::vector<unsigned char>& strong, std::vector<int>& agg, int cap);
+}  // namespace
 
-int aggregate(const AmgHostLevel& L, const std::vector<unsigned char>& strong, std::vector<int>& agg) {
-  const int n = L.n;
+// Greedy aggregation on the strong-neighbour lists (sequential: the result is a pure function of the lists).
+// cap == 0: a node whose strong neighbourhood is still free becomes the root of a new aggregate with all of it;
+// leftovers join the aggregate of their strongest aggregated neighbour; what is still free forms new aggregates.
+// cap > 0 (gentle coarsening for the last, tiny levels: the global smooth modes live there and a coarsening ratio
+// of ~7 from a few hundred rows costs CG iterations): a free node takes at most `cap` of its strongest free strong
+// neighbours; leftovers join their strongest aggregated neighbour or stay alone.
+int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::vector<int>& agg) {
   agg.assign(n, -1);
   int nc = 0;
-  // pass 1: a node whose strong neighbourhood is still free becomes the root of a new aggregate
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] >= 0) continue;
-    bool any = false, free_nb = true;
-    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
-      if (!strong[k]) continue;
-      any = true;
-      if (agg[L.col[k]] >= 0) { free_nb = false; break; }
+  if (cap > 0) {
+    for (int i = 0; i < n; ++i) {
+      if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;
+      int taken = 0;
+      for (int k = sptr[i]; k < sptr[i + 1] && taken < cap; ++k)
+        if (agg[scol[k]] < 0) { agg[scol[k]] = nc; ++taken; }
+      if (!taken) continue;
+      agg[i] = nc++;
     }
-    if (!any || !free_nb) continue;
+    for (int i = 0; i < n; ++i) {
+      if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;
+      int pick = -1;
+      for (int k = sptr[i]; k < sptr[i + 1]; ++k)
+        if (agg[scol[k]] >= 0) { pick = agg[scol[k]]; break; }
+      agg[i] = pick >= 0 ? pick : nc++;
+    }
+    return nc;
+  }
+  // pass 1
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;
+    bool free_nb = true;
+    for (int k = sptr[i]; k < sptr[i + 1]; ++k)
+      if (agg[scol[k]] >= 0) { free_nb = false; break; }
+    if (!free_nb) continue;
     agg[i] = nc;
-    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
-      if (strong[k]) agg[L.col[k]] = nc;
+    for (int k = sptr[i]; k < sptr[i + 1]; ++k) agg[scol[k]] = nc;
     ++nc;
   }
-  // pass 2: leftovers join the pass-1 aggregate they are most strongly coupled to (no chaining: decisions use
-  // the pass-1 state only)
+  // pass 2 (no chaining: decisions use the pass-1 state only)
   std::vector<int> join(n, -1);
   for (int i = 0; i < n; ++i) {
     if (agg[i] >= 0) continue;
-    double best = 0.0;
-    int pick = -1;
-    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
-      if (!strong[k]) continue;
-      const int a = agg[L.col[k]];
-      if (a >= 0 && -L.val[k] > best) { best = -L.val[k]; pick = a; }
-    }
-    join[i] = pick;
+    for (int k = sptr[i]; k < sptr[i + 1]; ++k)
+      if (agg[scol[k]] >= 0) { join[i] = agg[scol[k]]; break; }
   }
   for (int i = 0; i < n; ++i)
     if (agg[i] < 0 && join[i] >= 0) agg[i] = join[i];
-  // pass 3: what is still free (strongly coupled only to other leftovers) forms new aggregates
+  // pass 3
   for (int i = 0; i < n; ++i) {
-    if (agg[i] >= 0) continue;
-    bool any = false;
-    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
-      if (strong[k]) { any = true; break; }
-    if (!any) continue;   // isolated row (diagonally dominant): smoother only
+    if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;   // isolated row (diagonally dominant): smoother only
     agg[i] = nc;
-    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k)
-      if (strong[k] && agg[L.col[k]] < 0) agg[L.col[k]] = nc;
+    for (int k = sptr[i]; k < sptr[i + 1]; ++k)
+      if (agg[scol[k]] < 0) agg[scol[k]] = nc;
     ++nc;
   }
   return nc;
 }
 
-// Gentle coarsening for the last, tiny levels (the global smooth modes live there and a coarsening ratio of ~7
-// from a few hundred rows costs CG iterations): a free node takes at most `cap` of its strongest free strong
-// neighbours; leftovers join their strongest aggregated neighbour.
-int aggregate_small(const AmgHostLevel& L, const std::vector<unsigned char>& strong, std::vector<int>& agg, int cap) {
-  const int n = L.n;
-  agg.assign(n, -1);
-  int nc = 0;
-  std::vector<std::pair<double, int>> nb;
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] >= 0) continue;
-    nb.clear();
-    bool any = false;
-    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
-      if (!strong[k]) continue;
-      any = true;
-      if (agg[L.col[k]] < 0) nb.emplace_back(L.val[k], L.col[k]);   // most negative = strongest first
-    }
-    if (!any || nb.empty()) continue;
-    std::sort(nb.begin(), nb.end());
-    agg[i] = nc;
-    for (int q = 0; q < (int)nb.size() && q < cap; ++q) agg[nb[q].second] = nc;
-    ++nc;
-  }
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] >= 0) continue;
-    double best = 0.0;
-    int pick = -1;
-    bool any = false;
-    for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
-      if (!strong[k]) continue;
-      any = true;
-      const int a = agg[L.col[k]];
-      if (a >= 0 && -L.val[k] > best) { best = -L.val[k]; pick = a; }
-    }
-    if (pick >= 0) agg[i] = pick;
-    else if (any) agg[i] = nc++;
-  }
-  return nc;
-}
+namespace {
 
 // One row of P = (I - omega D^-1 A) T: distinct aggregates of the row's neighbourhood, sorted by aggregate id; the
 // contributions to one aggregate are added in entry order (own term first).  Returns the number of entries.
@@ -315,12 +311,11 @@ int amg_host_build(AmgHost& H, int n, std::vector<int>&& rowptr, std::vector<int
     AmgHostLevel& L = H.lv.back();
     if (L.n <= prm.coarse_max) break;
     const unsigned char* fx = H.lv.size() == 1 ? fixed : nullptr;
-    std::vector<unsigned char> strong;
+    std::vector<int> sptr, scol;
     const double t0 = now();
-    mark_strong(L, fx, prm.theta, nthreads, strong);
+    strong_lists(L, fx, prm.theta, nthreads, sptr, scol);
     const double t1 = now();
-    const int nc = (L.n <= prm.small_level && prm.small_cap > 0) ? aggregate_small(L, strong, L.agg, prm.small_cap)
-                                                                 : aggregate(L, strong, L.agg);
+    const int nc = amg_aggregate_lists(L.n, sptr.data(), scol.data(), amg_small_cap(prm, L.n), L.agg);
     const double t2 = now();
     if (nc <= 0 || nc > 0.7 * L.n) { L.agg.clear(); break; }   // coarsening stalled
     L.nc = nc;

@@ -1105,6 +1105,13 @@ int ddps_amg_get_values(ddps_ctx* ctx, int level, double* val, double* dinv) {
   return amg_debug_get_values(ctx, level, val, dinv);
 }
 
+int ddps_amg_get_level(ddps_ctx* ctx, int level, int64_t sizes[4], int64_t* rowptr, int64_t* col, int64_t* Pptr, int64_t* Pcol,
+                       double* Pval) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return amg_debug_get_level(ctx, level, sizes, rowptr, col, Pptr, Pcol, Pval);
+}
+
 int ddps_amg_apply(ddps_ctx* ctx, const double* r, double* z) {
   if (!ctx || !r || !z) return DDPS_ERR_ARG;
   cudaSetDevice(ctx->device);

@@ -313,6 +313,8 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
 int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it);
 int amg_debug_levels(Context* ctx, int64_t* nlevels, int64_t* sizes, int cap);
 int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv);
+int amg_debug_get_level(Context* ctx, int level, int64_t* sizes, int64_t* rowptr, int64_t* col, int64_t* Pptr, int64_t* Pcol,
+                        double* Pval);
 
 // ---- comm.cu ----
 int halo_exchange(Context* ctx, double* vec);            // fill ghost part of a [n_loc] vector

@@ -236,10 +236,15 @@ void ddps_amg_host_free(ddps_amg_host* h);
 /* Device-side parity/debug exports (single-GPU contexts, opts.precond = DDPS_PRECOND_AMG, after a base assembly):
  * levels : number of levels and rows per level (sizes capacity 16);
  * numeric: run the per-operator numeric phase on DDPS_MAT_OP / DDPS_MAT_BASE;
+ * level  : the hierarchy as it lives on the device: sizes = {n, nnz, n_coarse (0 on the coarsest level), nnz(P)}, CSR pattern
+ *          of the level (sorted columns) and its prolongator P [n x n_coarse] (the library stores P in fp32); any array
+ *          pointer may be NULL;
  * values : CSR-ordered values + inverse diagonal of level >= 1 after the last numeric phase;
  * apply  : z = one V(1,1) cycle applied to r (length nq each, caller's numbering). */
 int ddps_amg_levels(ddps_ctx* ctx, int64_t* nlevels, int64_t* sizes);
 int ddps_amg_numeric(ddps_ctx* ctx, int which);
+int ddps_amg_get_level(ddps_ctx* ctx, int level, int64_t sizes[4], int64_t* rowptr, int64_t* col, int64_t* Pptr, int64_t* Pcol,
+                       double* Pval);
 int ddps_amg_get_values(ddps_ctx* ctx, int level, double* val, double* dinv);
 int ddps_amg_apply(ddps_ctx* ctx, const double* r, double* z);
 

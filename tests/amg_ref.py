@@ -6,11 +6,11 @@ import scipy.sparse as sp
 
 
 def hierarchy_matrices(levels):
-    """scipy views of ddps_b200.amg.host_hierarchy(): list of (A_base, P or None)."""
+    """scipy views of ddps_b200.amg.host_hierarchy() / Session.amg_hierarchy(): list of (A_base or None, P or None)."""
     out = []
     for lev in levels:
         n = lev["n"]
-        A = sp.csr_matrix((lev["val"], lev["col"], lev["rowptr"]), shape=(n, n))
+        A = sp.csr_matrix((lev["val"], lev["col"], lev["rowptr"]), shape=(n, n)) if "val" in lev else None
         P = sp.csr_matrix((lev["Pval"], lev["Pcol"], lev["Pptr"]), shape=(n, lev["nc"])) if lev["nc"] else None
         out.append((A, P))
     return out

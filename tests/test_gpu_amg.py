@@ -47,24 +47,52 @@ MESHES = {
 }
 
 
+def _same_hierarchy(dev, host):
+    assert [lev["n"] for lev in dev] == [lev["n"] for lev in host]
+    for d, h in zip(dev, host):
+        assert np.array_equal(d["rowptr"], h["rowptr"]) and np.array_equal(d["col"], h["col"])
+        if d["nc"]:
+            assert d["nc"] == h["nc"] and np.array_equal(d["Pptr"], h["Pptr"]) and np.array_equal(d["Pcol"], h["Pcol"])
+            assert np.array_equal(d["Pval"], h["Pval"])          # same arithmetic, same order, same fp32 rounding
+
+
+@pytest.mark.parametrize("setup", ["device", "host"])
 @pytest.mark.parametrize("which", ["F2", "S"])
-def test_device_hierarchy_matches_restatement(D, which):
-    """Galerkin operators on every level (k_amg_rap), their inverse diagonals and one V-cycle (smoother, residual,
-    restriction, coarsest inverse, prolongation) against numpy on the same frozen prolongators."""
+def test_device_hierarchy_matches_restatement(D, which, setup, monkeypatch):
+    """Hierarchy construction (device-side coarsening of the large levels / host reference path), Galerkin operators
+    on every level (k_amg_rap2), their inverse diagonals and one V-cycle (smoother, residual, restriction, coarsest
+    inverse, prolongation) against numpy on the same frozen prolongators."""
+    if setup == "device":
+        monkeypatch.setenv("DDPS_AMG_DEV_MIN", "500")     # small meshes: push them through the device path as well
+    else:
+        monkeypatch.setenv("DDPS_AMG_HOST_SETUP", "1")
     mesh, pr = MESHES[which](D)
     V, u, v = smooth_fields(mesh, 5)
     with _session(D, mesh, pr) as s:
         s.debug_assemble_base(False)
         sizes = s.amg_levels()
-        assert len(sizes) >= 2 and sizes[0] == mesh.nq
+        assert len(sizes) >= 3 and sizes[0] == mesh.nq
         MV = s.get_csr(0)
-        levels = D.amg.host_hierarchy(MV.indptr, MV.indices, MV.data, _fixed(D, mesh, pr))
+        levels = s.amg_hierarchy()
         assert [lev["n"] for lev in levels] == sizes
+        # level 0 -> 1 sees bitwise identical inputs on the host and on the device: identical aggregates, prolongator and
+        # coarse pattern (deeper levels inherit last-bit differences of the coarse base values, so only their sizes and
+        # the mathematical properties below are compared)
+        host = D.amg.host_hierarchy(MV.indptr, MV.indices, MV.data, _fixed(D, mesh, pr))
+        _same_hierarchy(levels[:1], host[:1])
+        assert np.array_equal(levels[1]["rowptr"], host[1]["rowptr"]) and np.array_equal(levels[1]["col"], host[1]["col"])
+        if setup == "host":
+            _same_hierarchy(levels, host)
         s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)
         A = s.get_csr(1)
         s.amg_numeric()
         ops, Ps = amg_ref.operator_levels(A, levels)
         for l in range(1, len(levels)):
+            # the frozen pattern holds every structural product
+            G = ops[l].copy()
+            G.data[:] = 1.0
+            pat = sp.csr_matrix((np.ones(levels[l]["col"].size), levels[l]["col"], levels[l]["rowptr"]), shape=G.shape)
+            assert (G - G.multiply(pat)).nnz == 0 or abs(G - G.multiply(pat)).max() == 0
             val, dinv = s.amg_get_values(l, levels[l]["col"].size)
             dev = sp.csr_matrix((val, levels[l]["col"], levels[l]["rowptr"]), shape=(sizes[l], sizes[l]))
             d = (dev - ops[l]).tocoo()
