@@ -237,9 +237,13 @@ def main():
     e2e = None
     if not args.no_e2e:
         s.close()
+        # host buffers in the ABI's layout (= the memory layout of the reference's Julia arrays: nodes 2 x nq and elements
+        # 5 x nme column-major), pinned; the Mesh handed to the library is a zero-copy view of them
         nodes = torch.from_numpy(np.ascontiguousarray(mesh.nodes.T)).pin_memory().numpy()
+        elems = torch.from_numpy(np.ascontiguousarray(mesh.elements.T)).pin_memory().numpy()
+        mesh_p = D.Mesh(nodes.T, mesh.edges, elems.T)
         pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in smp.items()}
-        h2d = nodes.nbytes + mesh.elements.nbytes + sum(pinned[k].nbytes for k in ("lambda2", "mu_p", "mu_n", "C_mid")) + 3 * 16 * len(smp["n"])
+        h2d = nodes.nbytes + elems.nbytes + sum(pinned[k].nbytes for k in ("lambda2", "mu_p", "mu_n", "C_mid")) + 3 * 16 * len(smp["n"])
         d2h = 3 * 8 * mesh.nq
         barrier()
         t0 = time.perf_counter()
@@ -252,7 +256,7 @@ def main():
                 ident2 = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
             dist.broadcast(ident2, 0)
             s2 = D.Session(local, comm=(bytes(ident2.cpu().numpy().tobytes()), rank, world))
-        s2.set_mesh(mesh)
+        s2.set_mesh(mesh_p)
         s2.upload_ddpe(pinned)
         s2.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
         s2.ddpe_step(args.steps)

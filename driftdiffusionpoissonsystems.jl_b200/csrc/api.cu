@@ -62,6 +62,33 @@ __global__ void k_count_negative(const int4* __restrict__ elem, const double2* _
   if (ar < 0.0) atomicAdd(out, 1);
 }
 
+// Mesh.elements (int64, 1-based, 5 x nme column-major, src:17) -> int4 {n1,n2,n3,tag} 0-based; bad[0] = 1 + index of a
+// triangle that references a node outside 1..nq (0: none)
+__global__ void k_convert_elements(const long long* __restrict__ el, int nme, long long nq, int4* __restrict__ out,
+                                   int* __restrict__ bad) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nme) return;
+  const long long* c = el + 5LL * e;
+  const long long a = c[0] - 1, b = c[1] - 1, d = c[2] - 1;
+  if (a < 0 || b < 0 || d < 0 || a >= nq || b >= nq || d >= nq) { atomicMax(bad, e + 1); out[e] = make_int4(0, 0, 0, 0); return; }
+  out[e] = make_int4((int)a, (int)b, (int)d, (int)c[4]);
+}
+
+// Dirichlet data: flags + values scattered from the (node, value) list
+__global__ void k_scatter_dirichlet(int nd, const long long* __restrict__ ids, const double* __restrict__ vals,
+                                    unsigned char* __restrict__ isD, double* __restrict__ gD) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nd) return;
+  isD[ids[i]] = 1;
+  gD[ids[i]] = vals[i];
+}
+
+__global__ void k_check_finite(size_t n, const double* __restrict__ a, int* __restrict__ flag) {
+  bool bad = false;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) bad = bad || !isfinite(a[i]);
+  if (bad) *flag = 1;
+}
+
 __global__ void k_scatter_global(int n, const long long* __restrict__ glob, const double* __restrict__ src,
                                  double* __restrict__ dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -577,6 +604,28 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     ctx->n_own = ctx->n_loc = (int)nq;
     if (nme >= (1LL << 29)) { ctx->fail(DDPS_ERR_ARG, "too many triangles for one GPU"); return DDPS_ERR_ARG; }
     ctx->nme = (int)nme;
+    if (user_of_int.empty()) {
+      // the caller's arrays go to the device as they are (full PCIe speed when they are pinned); the conversion to the
+      // packed 0-based int4 records and the range check run on the device
+      long long* d_el = nullptr;
+      int* d_bad = nullptr;
+      DDPS_CUDA(cudaMalloc(&d_el, (size_t)5 * nme * sizeof(long long)));
+      if ((rc = dev_alloc(ctx, &ctx->elem, (size_t)nme)) || (rc = dev_alloc(ctx, &ctx->xy, (size_t)nq))) { cudaFree(d_el); return rc; }
+      cudaMalloc(&d_bad, sizeof(int));
+      cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+      cudaMemcpyAsync(d_el, elements, (size_t)5 * nme * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+      cudaMemcpyAsync(ctx->xy, nodes, (size_t)2 * nq * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+      k_convert_elements<<<(unsigned)((nme + 255) / 256), 256, 0, ctx->stream>>>(d_el, (int)nme, (long long)nq, ctx->elem, d_bad);
+      int bad = 0;
+      cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+      cudaFree(d_el); cudaFree(d_bad);
+      if (ce != cudaSuccess) { ctx->fail(DDPS_ERR_CUDA, cudaGetErrorString(ce)); return DDPS_ERR_CUDA; }
+      if (bad) {
+        ctx->fail(DDPS_ERR_ARG, "element " + std::to_string(bad) + " references a node outside 1..nq");
+        return DDPS_ERR_ARG;
+      }
+    } else {
     hel.resize(nme);
     for (int64_t e = 0; e < nme; ++e) {
       const int64_t* c = elements + 5 * e;
@@ -589,6 +638,7 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     }
     if ((rc = dev_alloc(ctx, &ctx->xy, (size_t)nq))) return rc;
     if ((rc = upload(ctx, (double*)ctx->xy, nodes, (size_t)2 * nq))) return rc;
+    }
     if (!user_of_int.empty()) {
       ctx->loc2glob = user_of_int;
       if ((rc = dev_alloc(ctx, &ctx->d_own_glob, (size_t)nq))) return rc;
@@ -623,8 +673,10 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     if ((rc = upload(ctx, ctx->d_own_glob, og.data(), og.size()))) return rc;
     DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  if ((rc = dev_alloc(ctx, &ctx->elem, (size_t)ctx->nme))) return rc;
-  if ((rc = upload(ctx, ctx->elem, hel.data(), hel.size()))) return rc;
+  if (!hel.empty() || !ctx->elem) {
+    if ((rc = dev_alloc(ctx, &ctx->elem, (size_t)ctx->nme))) return rc;
+    if ((rc = upload(ctx, ctx->elem, hel.data(), hel.size()))) return rc;
+  }
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   hel.clear(); hel.shrink_to_fit();
 
@@ -711,6 +763,25 @@ int ddps_dirichlet_set(ddps_ctx* ctx, int field, const int64_t* idx1, const doub
     }
   }
   ctx->Dset = sorted;
+  if (ctx->loc2glob.empty()) {   // single GPU in the caller's numbering: scatter the list on the device
+    long long* d_ids = nullptr;
+    double* d_vals = nullptr;
+    DDPS_CUDA(cudaMalloc(&d_ids, std::max<size_t>(nd, 1) * sizeof(long long)));
+    DDPS_CUDA(cudaMalloc(&d_vals, std::max<size_t>(nd, 1) * sizeof(double)));
+    cudaMemsetAsync(ctx->isD, 0, (size_t)ctx->n_loc, ctx->stream);
+    cudaMemsetAsync(ctx->gD[field], 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream);
+    if (nd > 0) {
+      cudaMemcpyAsync(d_ids, ids.data(), (size_t)nd * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+      cudaMemcpyAsync(d_vals, val, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+      k_scatter_dirichlet<<<(unsigned)((nd + 255) / 256), 256, 0, ctx->stream>>>((int)nd, d_ids, d_vals, ctx->isD, ctx->gD[field]);
+    }
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ids); cudaFree(d_vals);
+    if (ce != cudaSuccess) { ctx->fail(DDPS_ERR_CUDA, cudaGetErrorString(ce)); return DDPS_ERR_CUDA; }
+    ctx->have_D[field] = true;
+    ctx->base_ready = false;
+    return DDPS_OK;
+  }
   std::vector<double> gl(ctx->nq_global, 0.0);
   std::vector<unsigned char> fl(ctx->nq_global, 0);
   for (int64_t i = 0; i < nd; ++i) { gl[ids[i]] = val[i]; fl[ids[i]] = 1; }
@@ -741,14 +812,30 @@ int ddps_coeff_set(ddps_ctx* ctx, int slot, const double* data, int64_t len) {
   else { ctx->fail(DDPS_ERR_ARG, "unknown coefficient slot"); return DDPS_ERR_ARG; }
   int64_t want = kind == 0 ? ctx->nme_global : kind == 1 ? 3 * ctx->nme_global : ctx->nq_global;
   if (len != want) { ctx->fail(DDPS_ERR_ARG, "coefficient array has the wrong length"); return DDPS_ERR_ARG; }
-  for (int64_t i = 0; i < len; ++i)
-    if (!std::isfinite(data[i])) { ctx->fail(DDPS_ERR_ARG, "coefficient array contains a non-finite value"); return DDPS_ERR_ARG; }
+  const bool direct = (kind == 2) ? ctx->loc2glob.empty() : ctx->elem_glob.empty();
+  if (!direct)
+    for (int64_t i = 0; i < len; ++i)
+      if (!std::isfinite(data[i])) { ctx->fail(DDPS_ERR_ARG, "coefficient array contains a non-finite value"); return DDPS_ERR_ARG; }
   size_t nloc = kind == 0 ? (size_t)ctx->nme : kind == 1 ? (size_t)3 * ctx->nme : (size_t)ctx->n_loc;
   if ((rc = dev_alloc(ctx, &ctx->coeff[slot], nloc))) return rc;
   ctx->coeff_len[slot] = (int64_t)nloc;
-  const bool direct = (kind == 2) ? ctx->loc2glob.empty() : ctx->elem_glob.empty();
   if (direct) {
+    // straight H2D (full PCIe speed from pinned memory); the finiteness check runs on the device
     if ((rc = upload(ctx, ctx->coeff[slot], data, nloc))) return rc;
+    int* d_flag = nullptr;
+    DDPS_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream);
+    if (nloc) k_check_finite<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(nloc, ctx->coeff[slot], d_flag);
+    int flag = 0;
+    cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_flag);
+    if (ce != cudaSuccess) { ctx->fail(DDPS_ERR_CUDA, cudaGetErrorString(ce)); return DDPS_ERR_CUDA; }
+    if (flag) {
+      dev_free(ctx->coeff[slot]);
+      ctx->fail(DDPS_ERR_ARG, "coefficient array contains a non-finite value");
+      return DDPS_ERR_ARG;
+    }
   } else {
     std::vector<double> tmp(nloc);
     if (kind == 0) for (int e = 0; e < ctx->nme; ++e) tmp[e] = data[ctx->elem_glob[e]];
