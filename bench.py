@@ -236,7 +236,8 @@ def main():
     # end to end through the C ABI with host buffers: mesh + coefficient uploads, setup, K steps, D2H of V,u,v
     e2e = None
     if not args.no_e2e:
-        s.close()
+        # (the resident session stays open: a cudaFree -> cudaMalloc sequence of ~10 GB makes the driver's allocation
+        # path slow and erratic, which would be timed as "setup")
         # host buffers in the ABI's layout (= the memory layout of the reference's Julia arrays: nodes 2 x nq and elements
         # 5 x nme column-major), pinned; the Mesh handed to the library is a zero-copy view of them
         nodes = torch.from_numpy(np.ascontiguousarray(mesh.nodes.T)).pin_memory().numpy()
@@ -270,9 +271,10 @@ def main():
         e2e = {"value": args.steps / t_e2e, "unit": "1/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e,
                "note": "cold start: mesh+coefficient H2D from pinned host buffers, pattern build"
-                       + (", multigrid hierarchy setup (host)" if precond == "amg" else "") + ", first K Gummel iterations, D2H of V,u,v",
+                       + (", multigrid hierarchy setup (device, greedy aggregation on the host)" if precond == "amg" else "") + ", first K Gummel iterations, D2H of V,u,v",
                "setup_seconds": s2.stats()["t_setup_ms"] / 1000.0 + s2.stats()["t_amg_setup_ms"] / 1000.0}
         s2.close()
+    s.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -692,7 +692,9 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     cudaFree(d_neg);
     ctx->stats.n_negative_area = neg;
   }
+  const double t_up = now_ms();
   if ((rc = build_pattern(ctx))) { free_mesh(ctx); return rc; }
+  const double t_pat = now_ms();
 
   const size_t nl = ctx->n_loc, no = ctx->n_own, ne = (size_t)ctx->pat.nentries;
   if ((rc = dev_alloc(ctx, &ctx->isD, nl))) return rc;
@@ -728,6 +730,9 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
   if ((rc = p2p_setup(ctx))) return rc;
   ctx->have_mesh = true;
   ctx->stats.t_setup_ms = now_ms() - t0;
+  if (getenv("DDPS_AMG_TIMING"))
+    fprintf(stderr, "[ddps] mesh_set %.1f ms: uploads + conversion %.1f, pattern build %.1f, allocations %.1f\n", ctx->stats.t_setup_ms,
+            t_up - t0, t_pat - t_up, now_ms() - t_pat);
   return DDPS_OK;
 }
 
