@@ -139,6 +139,7 @@ __global__ void k_amg_prolong(int n, const int* __restrict__ Pptr, const int2* _
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double s = 0.0;
     const int e = Pptr[i + 1];
+#pragma unroll 1   // rows hold 2-4 entries: a 16x unrolled body would never run
     for (int m = Pptr[i]; m < e; ++m) {
       const int2 en = Pent[m];
       s += (double)__int_as_float(en.y) * __ldg(xc + en.x);
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, const int* __re
     const int cbase = c_slice_ptr[I >> 5] + (I & 31);
     const int q0 = Rptr[I], nq = Rptr[I + 1] - q0;
     if (len <= SLOTS) {
-      if (lane < len) ccols[lane] = c_col[cbase + 32 * lane];
+      for (int t = lane; t < len; t += 32) ccols[t] = c_col[cbase + 32 * t];
       for (int t = 0; t < len; ++t) tab[lane * STRIDE + t] = 0.0;
       __syncwarp();
       // widest fine row among the rows of R(I,:) (lanes beyond it have nothing to do)
@@ -236,11 +237,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, const int* __re
         }
       }
       __syncwarp();
-      if (lane < len) {
+      for (int t = lane; t < len; t += 32) {
         double s = 0.0;
-        for (int l = 0; l < 32; ++l) s += tab[l * STRIDE + lane];
-        c_val[cbase + 32 * lane] = s;
-        if (ccols[lane] == I) c_dinv[I] = 1.0 / s;
+        for (int l = 0; l < 32; ++l) s += tab[l * STRIDE + t];
+        c_val[cbase + 32 * t] = s;
+        if (ccols[t] == I) c_dinv[I] = 1.0 / s;
       }
       __syncwarp();
     } else {
@@ -690,10 +691,14 @@ void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, Amg
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 5));
     k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
                                                      C.slice_ptr, C.col, C.val, C.dinv);
-  } else {
+  } else if (C.wmax <= 32) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 3) / 4, (int64_t)ctx->num_sms * 6));
     k_amg_rap2<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
                                                      C.slice_ptr, C.col, C.val, C.dinv);
+  } else {              // the last, gently coarsened levels have long rows; longer ones still take the serial walk inside
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 1) / 2, (int64_t)ctx->num_sms * 6));
+    k_amg_rap2<64, 2><<<grid, 64, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
+                                                    C.slice_ptr, C.col, C.val, C.dinv);
   }
   ctx->stats.kernel_launches++;
 }
