@@ -59,9 +59,11 @@ double wall_ms() {
 // ------------------------------------------------------------------------------------------------------------
 // SELL-32 SpMV with fused epilogue.  MODE 0: y = A x;  1: y = b - A x;  2: y = x + om * dinv * (b - A x)
 // (one damped-Jacobi sweep, out of place).  DOT (MODE 2, finest level): also sums b.y = r.z for the CG.
-template <int MODE, bool DOT>
+// VT = float: the cycle's copy of the matrix values in fp32 (the cycle is only a preconditioner; arithmetic stays FP64,
+// so the cycle remains an exactly linear, symmetric operator) -- a third less matrix traffic per cycle SpMV.
+template <int MODE, bool DOT, typename VT>
 __global__ void __launch_bounds__(kVecBlock, 8) k_amg_spmv(int nrows, int nslices, const int* __restrict__ slice_ptr,
-                                                        const int* __restrict__ col, const double* __restrict__ val,
+                                                        const int* __restrict__ col, const VT* __restrict__ val,
                                                         const double* __restrict__ x, const double* __restrict__ b,
                                                         const double* __restrict__ dinv, double om,
                                                         double* __restrict__ y, double* partials, PcgScalars* scal) {
@@ -80,15 +82,15 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_amg_spmv(int nrows, int nslice
     for (; k + 4 <= w; k += 4) {
       const int c0 = ld_stream(col + idx), c1 = ld_stream(col + idx + 32), c2 = ld_stream(col + idx + 64),
                 c3 = ld_stream(col + idx + 96);
-      const double v0 = ld_stream(val + idx), v1 = ld_stream(val + idx + 32), v2 = ld_stream(val + idx + 64),
-                   v3 = ld_stream(val + idx + 96);
+      const double v0 = (double)ld_stream(val + idx), v1 = (double)ld_stream(val + idx + 32), v2 = (double)ld_stream(val + idx + 64),
+                   v3 = (double)ld_stream(val + idx + 96);
       const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
       sum += v0 * x0; sum += v1 * x1; sum += v2 * x2; sum += v3 * x3;
       idx += 128;
     }
     for (; k < w; ++k) {
       const int c0 = ld_stream(col + idx);
-      const double v0 = ld_stream(val + idx);
+      const double v0 = (double)ld_stream(val + idx);
       sum += v0 * __ldg(x + c0);
       idx += 32;
     }
@@ -108,6 +110,11 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_amg_spmv(int nrows, int nslice
       if (threadIdx.x == 0) scal->sums[1] = tot[0];
     }
   }
+}
+
+__global__ void k_amg_to_float(size_t n, const double* __restrict__ in, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __double2float_rn(ld_stream(in + i));
 }
 
 // x = om * dinv * b  (first damped-Jacobi sweep from the zero initial guess)
@@ -449,7 +456,7 @@ void amg_free(Context* ctx) {
   for (int l = 0; l < kAmgMaxLevels; ++l) {
     AmgLevelDev& L = A->lv[l];
     if (L.owns) { amg_release(L.slice_ptr); amg_release(L.col); amg_release(L.rowptr); }
-    amg_release(L.val); amg_release(L.dinv);
+    amg_release(L.val); amg_release(L.dinv); amg_release(L.val32);
     amg_release(L.Pptr); amg_release(L.Pent);
     amg_release(L.Rptr); amg_release(L.Rent);
     if (l > 0) { amg_release(L.b); amg_release(L.x2); }
@@ -602,8 +609,11 @@ int amg_setup(Context* ctx) {
   const double t2 = wall_ms();
   if (nlev < 2 || A->lv[nlev - 1].n > kAmgDenseMax) { amg_free(ctx); return 0; }   // no hierarchy: Jacobi-PCG stays
   A->nlev = nlev;
+  const bool cycle_fp32 = getenv("DDPS_AMG_FP64_CYCLE") == nullptr;   // A/B switch: keep the cycle's matrices in FP64
+  const int fp32_min = getenv("DDPS_AMG_FP32_MIN") ? atoi(getenv("DDPS_AMG_FP32_MIN")) : 50000;   // (tests lower it)
   for (int l = 0; l < nlev; ++l) {
     AmgLevelDev& L = A->lv[l];
+    if (cycle_fp32 && L.n > fp32_min && (rc = amg_alloc(ctx, &L.val32, (size_t)L.nentries))) return rc;
     if ((rc = amg_alloc(ctx, &L.x, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.t, (size_t)L.n))) return rc;
     if (l >= 1 && ((rc = amg_alloc(ctx, &L.b, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.x2, (size_t)L.n)))) return rc;
   }
@@ -714,6 +724,12 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv) {
     C.cur_val = C.val;
     C.cur_dinv = C.dinv;
   }
+  for (int l = 0; l < A.nlev; ++l) {   // fp32 copies of the large levels' values for the cycle's SpMVs
+    AmgLevelDev& L = A.lv[l];
+    if (!L.val32) continue;
+    k_amg_to_float<<<amg_grid(ctx, L.nentries, 256), 256, 0, ctx->stream>>>((size_t)L.nentries, L.cur_val, L.val32);
+    ctx->stats.kernel_launches++;
+  }
   const AmgLevelDev& L = A.lv[A.nlev - 1];
   if (L.n <= kAmgDenseShared)
     k_amg_dense_inverse<true><<<1, 1024, (size_t)L.n * L.n * sizeof(double), ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, A.dense);
@@ -727,7 +743,11 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv) {
 template <int MODE, bool DOT>
 static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x, const double* b, double om, double* y) {
   const int grid = amg_grid(ctx, (int64_t)L.nslices * 32, kVecBlock);
-  k_amg_spmv<MODE, DOT><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur_val, x, b, L.cur_dinv,
+  if (L.val32)
+    k_amg_spmv<MODE, DOT, float><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.val32, x, b, L.cur_dinv,
+                                                                     om, y, ctx->partials, ctx->scal);
+  else
+    k_amg_spmv<MODE, DOT, double><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur_val, x, b, L.cur_dinv,
                                                             om, y, ctx->partials, ctx->scal);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;

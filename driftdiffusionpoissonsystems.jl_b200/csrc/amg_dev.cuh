@@ -21,6 +21,7 @@ struct AmgLevelDev {
   int* rowptr = nullptr;
   double* val = nullptr;             // level >= 1: Galerkin values of the current operator (SELL order)
   double* dinv = nullptr;            // level >= 1
+  float* val32 = nullptr;            // large levels: fp32 copy of the current values for the cycle's SpMVs
   const double* cur_val = nullptr;   // matrix / inverse diagonal used by the cycle (level 0: set per operator)
   const double* cur_dinv = nullptr;
   // transfers to the next level, CSR with packed 8-byte entries {index, float value}: the prolongator values are

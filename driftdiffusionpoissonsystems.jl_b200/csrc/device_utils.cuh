@@ -98,5 +98,6 @@ __device__ __forceinline__ bool grid_reduce_mixed(double (&v)[NV], double* parti
 
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 
 }  // namespace ddps

@@ -25,16 +25,22 @@ def operator_levels(A, levels):
     return ops, [P for (_, P) in mats]
 
 
-def vcycle(ops, Ps, r, omega=2.0 / 3.0, level=0):
+def vcycle(ops, Ps, r, omega=2.0 / 3.0, level=0, fp32_min=None):
+    """fp32_min: levels with more rows than this keep an fp32-rounded copy of their matrix for the two SpMVs of the
+    cycle (what the device does for the large levels; the inverse diagonal stays FP64)."""
     A = ops[level]
     if Ps[level] is None:
         return np.linalg.solve(A.toarray(), r)
     dinv = 1.0 / A.diagonal()
+    As = A
+    if fp32_min is not None and A.shape[0] > fp32_min:
+        As = A.copy()
+        As.data = As.data.astype(np.float32).astype(np.float64)
     x = omega * dinv * r
-    t = r - A @ x
-    xc = vcycle(ops, Ps, Ps[level].T @ t, omega, level + 1)
+    t = r - As @ x
+    xc = vcycle(ops, Ps, Ps[level].T @ t, omega, level + 1, fp32_min)
     x = x + Ps[level] @ xc
-    return x + omega * dinv * (r - A @ x)
+    return x + omega * dinv * (r - As @ x)
 
 
 def pcg(A, b, M, rtol=1e-13, maxit=2000):

@@ -109,6 +109,30 @@ def test_device_hierarchy_matches_restatement(D, which, setup, monkeypatch):
         assert np.array_equal(s.amg_apply(r), z)
 
 
+def test_fp32_cycle_matrices(D, monkeypatch):
+    """The large levels keep an fp32 copy of their matrix values for the two SpMVs of the cycle (the cycle is only a
+    preconditioner; arithmetic stays FP64).  Forced on a small mesh here and checked against the restatement with the
+    same rounding; the solve still reaches the direct solution."""
+    monkeypatch.setenv("DDPS_AMG_FP32_MIN", "1000")
+    mesh, pr = MESHES["S"](D)
+    V, u, v = smooth_fields(mesh, 9)
+    with _session(D, mesh, pr) as s:
+        s.debug_assemble_base(False)
+        levels = s.amg_hierarchy()
+        assert levels[0]["n"] > 1000 and levels[1]["n"] > 1000
+        s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)
+        A = s.get_csr(1)
+        b = s.get_vector(0)
+        s.amg_numeric()
+        ops, Ps = amg_ref.operator_levels(A, levels)
+        r = np.random.default_rng(2).standard_normal(mesh.nq)
+        z = s.amg_apply(r)
+        assert rel_max(z, amg_ref.vcycle(ops, Ps, r, fp32_min=1000)) <= 1e-10
+        assert rel_max(z, amg_ref.vcycle(ops, Ps, r)) > 1e-12          # it really is the fp32 copy that ran
+        x, it, _ = s.debug_pcg(b, rtol=1e-13)
+        assert rel_l2(x, spla.spsolve(A.tocsc(), b)) <= 1e-10 and it <= 40
+
+
 @pytest.mark.parametrize("which", ["F2", "S"])
 def test_amg_pcg_against_direct_solve(D, which):
     mesh, pr = MESHES[which](D)
