@@ -124,9 +124,11 @@ __global__ void k_amg_jac0(int n, double om, const double* __restrict__ dinv, co
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = om * (dinv[i] * b[i]);
 }
 
-// bc = R t   (R = P^T stored row-wise: a deterministic gather)
+// bc = R t   (R = P^T stored row-wise: a deterministic gather); fused: xc = om * dinv_c * bc, the first damped-Jacobi
+// sweep of the coarse level from the zero initial guess (dinv_c == nullptr on the coarsest level)
 __global__ void k_amg_restrict(int nc, const int* __restrict__ Rptr, const int2* __restrict__ Rent,
-                               const double* __restrict__ t, double* __restrict__ bc, const PcgScalars* scal) {
+                               const double* __restrict__ t, double* __restrict__ bc, const double* __restrict__ dinv_c,
+                               double om, double* __restrict__ xc, const PcgScalars* scal) {
   if (scal->done) return;
   for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += gridDim.x * blockDim.x) {
     double s = 0.0;
@@ -136,6 +138,7 @@ __global__ void k_amg_restrict(int nc, const int* __restrict__ Rptr, const int2*
       s += (double)__int_as_float(en.y) * __ldg(t + en.x);
     }
     bc[I] = s;
+    if (dinv_c) xc[I] = om * (dinv_c[I] * s);
   }
 }
 
@@ -762,12 +765,15 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
   A.lv[0].x2 = z;
   for (int l = 0; l + 1 < A.nlev; ++l) {
     AmgLevelDev& L = A.lv[l];
-    if (!(l == 0 && have_first_sweep)) {   // the CG's update kernel already produced the first sweep of the finest level
-      k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);
-      ctx->stats.kernel_launches++;
+    if (l == 0 && !have_first_sweep) {   // (inside the CG the update kernel already produced the first sweep of the finest
+      k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);   // level; coarser
+      ctx->stats.kernel_launches++;                                                                    // levels: fused in restrict)
     }
     launch_amg_spmv<1, false>(ctx, L, L.x, L.b, om, L.t);
-    k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, A.lv[l + 1].b, ctx->scal);
+    AmgLevelDev& C = A.lv[l + 1];
+    const bool coarsest = (l + 2 == A.nlev);
+    k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, coarsest ? nullptr : C.cur_dinv, om, C.x,
+                                                            ctx->scal);
     ctx->stats.kernel_launches++;
   }
   {
