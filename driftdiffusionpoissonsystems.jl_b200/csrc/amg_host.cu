@@ -121,26 +121,62 @@ int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::v
     }
     return nc;
   }
-  // pass 1
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;
-    bool free_nb = true;
-    for (int k = sptr[i]; k < sptr[i + 1]; ++k)
-      if (agg[scol[k]] >= 0) { free_nb = false; break; }
-    if (!free_nb) continue;
-    agg[i] = nc;
-    for (int k = sptr[i]; k < sptr[i + 1]; ++k) agg[scol[k]] = nc;
-    ++nc;
+  // pass 1.  Large levels: the rows are cut into kAggChunks contiguous chunks that run concurrently; a root and its
+  // whole strong neighbourhood must lie inside one chunk (the few rows along the seams become leftovers of pass 2/3).
+  // The chunk count is a constant, so the result does not depend on the number of threads.
+  constexpr int kAggChunks = 16;
+  // (measured: chunking a 8.4M-row level saves 30 ms of 100 but the seams' leftovers densify the coarser levels and cost
+  // +12 % CG iterations -> the chunked path is kept for experiments only, DDPS_AMG_AGG_CHUNKS=1)
+  const int nchunks = (n >= 200000 && getenv("DDPS_AMG_AGG_CHUNKS")) ? kAggChunks : 1;
+  const int64_t csize = ((int64_t)n + nchunks - 1) / nchunks;
+  std::vector<int> cbase(nchunks + 1, 0);
+  auto pass1 = [&](int c) {
+    const int lo = (int)std::min<int64_t>(n, c * csize), hi = (int)std::min<int64_t>(n, lo + csize);
+    int local = 0;
+    for (int i = lo; i < hi; ++i) {
+      if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;
+      bool ok = true;
+      for (int k = sptr[i]; k < sptr[i + 1]; ++k) {
+        const int j = scol[k];
+        if (j < lo || j >= hi || agg[j] >= 0) { ok = false; break; }
+      }
+      if (!ok) continue;
+      agg[i] = local;
+      for (int k = sptr[i]; k < sptr[i + 1]; ++k) agg[scol[k]] = local;
+      ++local;
+    }
+    cbase[c + 1] = local;
+  };
+  if (nchunks == 1) pass1(0);
+  else {
+    const int nt = (int)std::max(1u, std::min((unsigned)nchunks, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() { for (int c = t; c < nchunks; c += nt) pass1(c); });
+    for (auto& x : th) x.join();
+    for (int c = 0; c < nchunks; ++c) cbase[c + 1] += cbase[c];
+    parallel_ranges(n, nt, [&](int, int64_t lo, int64_t hi) {
+      for (int64_t i = lo; i < hi; ++i)
+        if (agg[i] >= 0) agg[i] += cbase[i / csize];
+    });
   }
+  nc = cbase[nchunks];
   // pass 2 (no chaining: decisions use the pass-1 state only)
   std::vector<int> join(n, -1);
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] >= 0) continue;
-    for (int k = sptr[i]; k < sptr[i + 1]; ++k)
-      if (agg[scol[k]] >= 0) { join[i] = agg[scol[k]]; break; }
+  {
+    const int nt = nchunks == 1 ? 1 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    parallel_ranges(n, nt, [&](int, int64_t lo, int64_t hi) {
+      for (int64_t i = lo; i < hi; ++i) {
+        if (agg[i] >= 0) continue;
+        for (int k = sptr[i]; k < sptr[i + 1]; ++k)
+          if (agg[scol[k]] >= 0) { join[i] = agg[scol[k]]; break; }
+      }
+    });
+    parallel_ranges(n, nt, [&](int, int64_t lo, int64_t hi) {
+      for (int64_t i = lo; i < hi; ++i)
+        if (agg[i] < 0 && join[i] >= 0) agg[i] = join[i];
+    });
   }
-  for (int i = 0; i < n; ++i)
-    if (agg[i] < 0 && join[i] >= 0) agg[i] = join[i];
   // pass 3
   for (int i = 0; i < n; ++i) {
     if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;   // isolated row (diagonally dominant): smoother only

@@ -13,6 +13,10 @@
 //   6. SELL-32 layout of the coarse pattern and the Galerkin product of the BASE values (k_amg_rap2 of amg.cu), which
 //      the next level's strength / prolongator smoothing need.
 // The arrays built here are installed in the hierarchy as they are (no host round trip, no upload).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "amg_dev.cuh"
@@ -245,6 +249,9 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   const double* fval = F.cur_val;        // BASE values of this level (SELL order)
   Tmp tmp;
   int rc;
+  const bool timing = getenv("DDPS_AMG_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
 
   // ---- 1. strong-neighbour lists -> host ----
   int *d_cnt, *d_sptr, *d_scol;
@@ -263,12 +270,14 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   DDPS_CUDA(cudaMemcpyAsync(scol.data(), d_scol, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, st));
   DDPS_CUDA(cudaStreamSynchronize(st));
 
+  const double t1 = now();
   // ---- 2. aggregation (host, sequential greedy: the quality of the coarsening lives here) ----
   std::vector<int> agg;
   const int nc = amg_aggregate_lists(n, sptr.data(), scol.data(), amg_small_cap(prm, n), agg);
   if (nc <= 0 || nc > 0.7 * n) return 0;   // coarsening stalled
   std::vector<int>().swap(sptr);
   std::vector<int>().swap(scol);
+  const double t2 = now();
   int* d_agg;
   DDPS_CUDA(tmp.alloc(&d_agg, (size_t)n));
   DDPS_CUDA(cudaMemcpyAsync(d_agg, agg.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -313,6 +322,8 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   }
   k_lower_bound_sorted<int><<<(nc + 1 + T - 1) / T, T, 0, st>>>(d_rkey, nP, nc + 1, 0, Rptr);
 
+  if (timing) DDPS_CUDA(cudaStreamSynchronize(st));
+  const double t3 = now();
   // ---- 5. symbolic Galerkin product: coarse CSR pattern with sorted columns ----
   long long *d_qcnt, *d_qoff;
   DDPS_CUDA(tmp.alloc(&d_qcnt, (size_t)nP + 1));
@@ -359,6 +370,8 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   DDPS_CUDA(tmp.alloc(&d_ccol, (size_t)cnnz));
   k_low32_keys<<<(unsigned)((cnnz + T - 1) / T), T, 0, st>>>(d_k0, cnnz, d_ccol);
 
+  if (timing) DDPS_CUDA(cudaStreamSynchronize(st));
+  const double t4 = now();
   // ---- 6. SELL-32 layout + Galerkin product of the base values ----
   {
     long long *w32, *w32scan;
@@ -392,6 +405,9 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   DDPS_CUDA(cudaStreamSynchronize(st));
   DDPS_CUDA(cudaGetLastError());
   *nc_out = nc;
+  if (timing)
+    fprintf(stderr, "[ddps amg]   device level n=%d: strong lists + D2H %.1f ms, host aggregation %.1f, P + R %.1f, symbolic (%lld keys) %.1f, "
+                    "SELL + base Galerkin %.1f\n", n, t1 - t0, t2 - t1, t3 - t2, nk, t4 - t3, now() - t4);
   return 0;
 }
 
