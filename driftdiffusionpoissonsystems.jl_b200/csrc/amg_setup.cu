@@ -27,11 +27,15 @@ namespace {
 
 constexpr int kMaxLocalRow = 64;   // longest matrix row the per-thread kernels of this file handle
 
+// Temporaries come from the device's default stream-ordered memory pool (cudaMallocAsync on the library stream; every
+// use is on that stream): a plain cudaFree of several GB is synchronous and was measured at up to 100 ms per level.
 struct Tmp {
+  cudaStream_t st;
   std::vector<void*> ptrs;
-  ~Tmp() { for (void* p : ptrs) cudaFree(p); }
+  explicit Tmp(cudaStream_t s) : st(s) {}
+  ~Tmp() { for (void* p : ptrs) cudaFreeAsync(p, st); }
   template <typename T> cudaError_t alloc(T** p, size_t n) {
-    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)p, std::max<size_t>(n, 1) * sizeof(T), st);
     if (e == cudaSuccess) ptrs.push_back(*p);
     return e;
   }
@@ -159,36 +163,37 @@ __global__ void k_lower_bound_sorted(const K* __restrict__ sorted, long long n, 
 }
 
 // ---- 5. symbolic Galerkin product ---------------------------------------------------------------------------
-// per entry q of R (coarse row I = rkey[q], fine row i): number of structural products sum_k |P(col_k,:)|
-__global__ void k_sym_count(int nR, const int2* __restrict__ Rent, const int* __restrict__ rowptr,
-                            const int* __restrict__ slice_ptr, const int* __restrict__ col, const int* __restrict__ Pptr,
-                            long long* __restrict__ cnt) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nR) return;
-  const int i = Rent[q].x;
-  const int len = rowptr[i + 1] - rowptr[i];
-  const int base = slice_ptr[i >> 5] + (i & 31);
-  long long c = 0;
-  for (int k = 0; k < len; ++k) {
-    const int j = col[base + 32 * k];
-    c += Pptr[j + 1] - Pptr[j];
-  }
-  cnt[q] = c;
-}
-
-__global__ void k_sym_fill(int nR, const int2* __restrict__ Rent, const int* __restrict__ rkey, const int* __restrict__ rowptr,
+// per entry q of R (coarse row I = rkey[q], fine row i): the DISTINCT coarse columns J reachable through the entries of
+// fine row i (= the pattern of row i of A P), counted (FILL == false) or written as keys (I << 32 | J)
+template <bool FILL>
+__global__ void k_sym_keys(int nR, const int2* __restrict__ Rent, const int* __restrict__ rkey, const int* __restrict__ rowptr,
                            const int* __restrict__ slice_ptr, const int* __restrict__ col, const int* __restrict__ Pptr,
-                           const int2* __restrict__ Pent, const long long* __restrict__ off, unsigned long long* __restrict__ keys) {
+                           const int2* __restrict__ Pent, long long* __restrict__ cnt, const long long* __restrict__ off,
+                           unsigned long long* __restrict__ keys, int* __restrict__ overflow) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nR) return;
   const int i = Rent[q].x;
-  const unsigned long long hi = (unsigned long long)(unsigned)rkey[q] << 32;
   const int len = rowptr[i + 1] - rowptr[i];
   const int base = slice_ptr[i >> 5] + (i & 31);
-  long long o = off[q];
+  int seen[kMaxLocalRow];
+  int c = 0;
   for (int k = 0; k < len; ++k) {
     const int j = col[base + 32 * k];
-    for (int m = Pptr[j]; m < Pptr[j + 1]; ++m) keys[o++] = hi | (unsigned long long)(unsigned)Pent[m].x;
+    for (int m = Pptr[j]; m < Pptr[j + 1]; ++m) {
+      const int J = Pent[m].x;
+      int p = 0;
+      while (p < c && seen[p] != J) ++p;
+      if (p == c) {
+        if (c == kMaxLocalRow) { *overflow = 1; break; }
+        seen[c++] = J;
+      }
+    }
+  }
+  if (!FILL) cnt[q] = c;
+  else {
+    const unsigned long long hi = (unsigned long long)(unsigned)rkey[q] << 32;
+    long long o = off[q];
+    for (int p = 0; p < c; ++p) keys[o++] = hi | (unsigned long long)(unsigned)seen[p];
   }
 }
 
@@ -227,6 +232,13 @@ __global__ void k_sell_fill(const int* __restrict__ rowptr, const int* __restric
   for (int k = 0; k < w; ++k) col[base + k * 32 + lane] = (k < len) ? csrcol[beg + k] : self;
 }
 
+void amg_release_transfers(AmgLevelDev& F) {
+  cudaFree(F.Pptr); cudaFree(F.Pent); cudaFree(F.Rptr); cudaFree(F.Rent);
+  F.Pptr = F.Rptr = nullptr;
+  F.Pent = F.Rent = nullptr;
+  F.nc = 0;
+}
+
 template <typename T>
 int scan_exclusive(Context* ctx, Tmp& tmp, const T* in, T* out, int n) {
   size_t bytes = 0;
@@ -247,7 +259,14 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   cudaStream_t st = ctx->stream;
   const int T = 256;
   const double* fval = F.cur_val;        // BASE values of this level (SELL order)
-  Tmp tmp;
+  {   // keep freed temporaries cached in the pool (the next level / the next solve reuses them)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  Tmp tmp(st);
   int rc;
   const bool timing = getenv("DDPS_AMG_TIMING") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -329,18 +348,26 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   DDPS_CUDA(tmp.alloc(&d_qcnt, (size_t)nP + 1));
   DDPS_CUDA(tmp.alloc(&d_qoff, (size_t)nP + 1));
   DDPS_CUDA(cudaMemsetAsync(d_qcnt, 0, ((size_t)nP + 1) * sizeof(long long), st));
-  k_sym_count<<<(nP + T - 1) / T, T, 0, st>>>(nP, Rent, F.rowptr, F.slice_ptr, F.col, Pptr, d_qcnt);
+  int* d_ovf;
+  DDPS_CUDA(tmp.alloc(&d_ovf, 4));
+  DDPS_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(int), st));
+  k_sym_keys<false><<<(nP + T - 1) / T, T, 0, st>>>(nP, Rent, d_rkey, F.rowptr, F.slice_ptr, F.col, Pptr, Pent, d_qcnt, nullptr, nullptr, d_ovf);
   if ((rc = scan_exclusive(ctx, tmp, d_qcnt, d_qoff, nP + 1))) return rc;
   long long nk = 0;
+  int ovf = 0;
   DDPS_CUDA(cudaMemcpyAsync(&nk, d_qoff + nP, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  DDPS_CUDA(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
   DDPS_CUDA(cudaStreamSynchronize(st));
-  if (nk >= (1LL << 31) - 1) return 1;   // too many structural products for 32-bit item counts: host path
+  if (ovf || nk >= (1LL << 31) - 1) {   // a row of A P with more than kMaxLocalRow entries, or too many keys: host path
+    amg_release_transfers(F);
+    return 1;
+  }
   unsigned long long *d_k0, *d_k1;
   int* d_num;
   DDPS_CUDA(tmp.alloc(&d_k0, (size_t)nk));
   DDPS_CUDA(tmp.alloc(&d_k1, (size_t)nk));
   DDPS_CUDA(tmp.alloc(&d_num, 4));
-  k_sym_fill<<<(nP + T - 1) / T, T, 0, st>>>(nP, Rent, d_rkey, F.rowptr, F.slice_ptr, F.col, Pptr, Pent, d_qoff, d_k0);
+  k_sym_keys<true><<<(nP + T - 1) / T, T, 0, st>>>(nP, Rent, d_rkey, F.rowptr, F.slice_ptr, F.col, Pptr, Pent, nullptr, d_qoff, d_k0, d_ovf);
   {
     const int endbit = 32 + bits_for(nc);
     size_t bytes = 0;
