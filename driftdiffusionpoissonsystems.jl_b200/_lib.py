@@ -25,7 +25,7 @@ class SolverOpts(C.Structure):
     _fields_ = [("lin_rtol", C.c_double), ("newton_eta", C.c_double), ("lin_max_it", C.c_int64),
                 ("max_newton", C.c_int32), ("max_gummel", C.c_int32), ("check_every", C.c_int32),
                 ("warm_start", C.c_int32), ("verbose", C.c_int32), ("lin_cap_ok", C.c_int32), ("no_alt_traversal", C.c_int32), ("warm_start_v", C.c_int32),
-                ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("precond", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("precond", C.c_int32), ("amg_no_lag", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -33,7 +33,7 @@ class Stats(C.Structure):
                 ("spmv_total", C.c_int64), ("kernel_launches", C.c_int64), ("control", C.c_double),
                 ("t_setup_ms", C.c_double), ("t_solve_ms", C.c_double), ("t_asm_ms", C.c_double),
                 ("t_pcg_ms", C.c_double), ("t_wall_ms", C.c_double), ("status", C.c_int32), ("n_negative_area", C.c_int32),
-                ("amg_levels", C.c_int32), ("reserved0", C.c_int32), ("t_amg_setup_ms", C.c_double),
+                ("amg_levels", C.c_int32), ("amg_reuses", C.c_int32), ("t_amg_setup_ms", C.c_double),
                 ("reserved", C.c_int32 * 4)]
 
     def as_dict(self):

@@ -467,6 +467,11 @@ void amg_free(Context* ctx) {
   }
   amg_release(A->dense);
   amg_release(A->z);
+  for (int k = 0; k < kAmgKinds; ++k) {
+    AmgOpSet& S = A->sets[k];
+    amg_release(S.snap); amg_release(S.dense);
+    for (int l = 0; l < kAmgMaxLevels; ++l) { amg_release(S.val[l]); amg_release(S.dinv[l]); amg_release(S.val32[l]); }
+  }
   delete A;
   ctx->amg = nullptr;
 }
@@ -686,59 +691,143 @@ int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv)
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<double> sv((size_t)L.nentries);
   std::vector<int> rp((size_t)L.n + 1), sp((size_t)L.nslices + 1);
-  DDPS_CUDA(cudaMemcpy(sv.data(), L.val, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  DDPS_CUDA(cudaMemcpy(sv.data(), L.cur_val, sv.size() * sizeof(double), cudaMemcpyDeviceToHost));
   DDPS_CUDA(cudaMemcpy(rp.data(), L.rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
   DDPS_CUDA(cudaMemcpy(sp.data(), L.slice_ptr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
   if (val_csr)
     for (int r = 0; r < L.n; ++r)
       for (int k = 0; k < rp[r + 1] - rp[r]; ++k) val_csr[rp[r] + k] = sv[(size_t)sp[r >> 5] + 32 * k + (r & 31)];
-  if (dinv) DDPS_CUDA(cudaMemcpy(dinv, L.dinv, (size_t)L.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (dinv) DDPS_CUDA(cudaMemcpy(dinv, L.cur_dinv, (size_t)L.n * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // per-operator numeric phase and the V-cycle
 // ------------------------------------------------------------------------------------------------------------
-void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, AmgLevelDev& C) {
+// How far is the operator from the snapshot its coarse operators were computed from?  out (scal->sums[0..3]) =
+// {max|a - s|, max|s|, max|rowsum(a) - rowsum(s)|, max|rowsum(s)|} (entries: the stiffness part; row sums: the mass part)
+__global__ void __launch_bounds__(kVecBlock, 8) k_amg_change(int nrows, int nslices, const int* __restrict__ slice_ptr,
+                                                          const double* __restrict__ a, const double* __restrict__ s,
+                                                          double* partials, PcgScalars* scal) {
+  __shared__ double sh_red[32];
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  double m1 = 0.0, n1 = 0.0, m2 = 0.0, n2 = 0.0;
+  for (int slice = gw; slice < nslices; slice += nw) {
+    const int base = slice_ptr[slice];
+    const int w = (slice_ptr[slice + 1] - base) >> 5;
+    double ra = 0.0, rs = 0.0;
+    for (int k = 0; k < w; ++k) {
+      const double va = ld_stream(a + base + 32 * k + lane), vs = ld_stream(s + base + 32 * k + lane);
+      m1 = fmax(m1, fabs(va - vs));
+      n1 = fmax(n1, fabs(vs));
+      ra += va; rs += vs;
+    }
+    if (slice * 32 + lane < nrows) { m2 = fmax(m2, fabs(ra - rs)); n2 = fmax(n2, fabs(rs)); }
+  }
+  double v[4] = {m1, n1, m2, n2}, tot[4];
+  if (grid_reduce_mixed<4, 15u>(v, partials, &scal->cnt[3], sh_red, tot)) {
+    if (threadIdx.x == 0) { scal->sums[0] = tot[0]; scal->sums[1] = tot[1]; scal->sums[2] = tot[2]; scal->sums[3] = tot[3]; }
+  }
+}
+
+void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv) {
   if (C.wmax <= 16) {   // short coarse rows: small private tables, more resident warps per SM
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 5));
     k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
-                                                     C.slice_ptr, C.col, C.val, C.dinv);
+                                                     C.slice_ptr, C.col, out_val, out_dinv);
   } else if (C.wmax <= 32) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 3) / 4, (int64_t)ctx->num_sms * 6));
     k_amg_rap2<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
-                                                     C.slice_ptr, C.col, C.val, C.dinv);
+                                                     C.slice_ptr, C.col, out_val, out_dinv);
   } else {              // the last, gently coarsened levels have long rows; longer ones still take the serial walk inside
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 1) / 2, (int64_t)ctx->num_sms * 6));
     k_amg_rap2<64, 2><<<grid, 64, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
-                                                    C.slice_ptr, C.col, C.val, C.dinv);
+                                                    C.slice_ptr, C.col, out_val, out_dinv);
   }
   ctx->stats.kernel_launches++;
 }
 
-int amg_numeric(Context* ctx, const double* val, const double* dinv) {
+static int amg_alloc_set(Context* ctx, Amg& A, AmgOpSet& S) {
+  int rc;
+  if ((rc = amg_alloc(ctx, &S.snap, (size_t)A.lv[0].nentries))) return rc;
+  for (int l = 1; l < A.nlev; ++l) {
+    const AmgLevelDev& L = A.lv[l];
+    if ((rc = amg_alloc(ctx, &S.val[l], (size_t)L.nentries)) || (rc = amg_alloc(ctx, &S.dinv[l], (size_t)L.n))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(S.val[l], 0, std::max<size_t>((size_t)L.nentries, 1) * sizeof(double), ctx->stream));   // SELL padding stays 0
+    DDPS_CUDA(cudaMemsetAsync(S.dinv[l], 0, std::max<size_t>((size_t)L.n, 1) * sizeof(double), ctx->stream));
+    if (L.val32 && (rc = amg_alloc(ctx, &S.val32[l], (size_t)L.nentries))) return rc;
+  }
+  const int nL = A.lv[A.nlev - 1].n;
+  if ((rc = amg_alloc(ctx, &S.dense, (size_t)nL * nL))) return rc;
+  S.allocated = true;
+  return 0;
+}
+
+// kind: which operator this is (0: first Newton system of a Vsolve / semlin, 3: later Newton systems, 1: u-, 2: v-continuity
+// system; < 0: unknown -> always recompute).  Returns through the level structs the matrices the cycle will use.
+int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind) {
   Amg& A = *ctx->amg;
+  int rc;
   A.lv[0].cur_val = val;
   A.lv[0].cur_dinv = dinv;
-  for (int l = 0; l + 1 < A.nlev; ++l) {
-    AmgLevelDev& F = A.lv[l];
-    AmgLevelDev& C = A.lv[l + 1];
-    amg_launch_rap(ctx, F, F.cur_val, C);
-    C.cur_val = C.val;
-    C.cur_dinv = C.dinv;
+  const bool lag = kind >= 0 && kind < kAmgKinds && !ctx->opts.amg_no_lag;
+  AmgOpSet* S = lag ? &A.sets[kind] : nullptr;
+  if (S && !S->allocated && (rc = amg_alloc_set(ctx, A, *S))) return rc;
+  bool reuse = false;
+  if (S && S->valid) {
+    const AmgLevelDev& L0 = A.lv[0];
+    k_amg_change<<<amg_grid(ctx, (int64_t)L0.nslices * 32, kVecBlock), kVecBlock, 0, ctx->stream>>>(L0.n, L0.nslices, L0.slice_ptr, val, S->snap,
+                                                                                               ctx->partials, ctx->scal);
+    ctx->stats.kernel_launches++;
+    DDPS_CUDA(cudaMemcpyAsync(ctx->scal_host, ctx->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double* m = ctx->scal_host->sums;
+    const double tau = 0.01;
+    reuse = (m[0] <= tau * m[1]) && (m[2] <= tau * m[3] || m[2] <= 1e-12 * m[1]);
   }
-  for (int l = 0; l < A.nlev; ++l) {   // fp32 copies of the large levels' values for the cycle's SpMVs
+  for (int l = 1; l < A.nlev; ++l) {
     AmgLevelDev& L = A.lv[l];
-    if (!L.val32) continue;
-    k_amg_to_float<<<amg_grid(ctx, L.nentries, 256), 256, 0, ctx->stream>>>((size_t)L.nentries, L.cur_val, L.val32);
+    L.cur_val = S ? S->val[l] : L.val;
+    L.cur_dinv = S ? S->dinv[l] : L.dinv;
+    L.cur32 = S ? S->val32[l] : L.val32;
+  }
+  A.cur_dense = S ? S->dense : A.dense;
+  if (!reuse) {
+    for (int l = 0; l + 1 < A.nlev; ++l) {
+      const AmgLevelDev& F = A.lv[l];
+      const AmgLevelDev& C = A.lv[l + 1];
+      amg_launch_rap(ctx, F, F.cur_val, C, const_cast<double*>(C.cur_val), const_cast<double*>(C.cur_dinv));
+    }
+    for (int l = 1; l < A.nlev; ++l) {   // fp32 copies of the large coarse levels' values for the cycle's SpMVs
+      AmgLevelDev& L = A.lv[l];
+      if (!L.cur32) continue;
+      k_amg_to_float<<<amg_grid(ctx, L.nentries, 256), 256, 0, ctx->stream>>>((size_t)L.nentries, L.cur_val, const_cast<float*>(L.cur32));
+      ctx->stats.kernel_launches++;
+    }
+    const AmgLevelDev& L = A.lv[A.nlev - 1];
+    double* dense = const_cast<double*>(A.cur_dense);
+    if (L.n <= kAmgDenseShared)
+      k_amg_dense_inverse<true><<<1, 1024, (size_t)L.n * L.n * sizeof(double), ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, dense);
+    else
+      k_amg_dense_inverse<false><<<1, 1024, 0, ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, dense);
+    ctx->stats.kernel_launches++;
+    if (S) {
+      DDPS_CUDA(cudaMemcpyAsync(S->snap, val, (size_t)A.lv[0].nentries * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      S->valid = true;
+    }
+    A.numerics++;
+  } else {
+    A.reuses++;
+  }
+  ctx->stats.amg_reuses = (int32_t)A.reuses;
+  // the finest level's fp32 copy always follows the current operator
+  AmgLevelDev& L0 = A.lv[0];
+  L0.cur32 = L0.val32;
+  if (L0.val32) {
+    k_amg_to_float<<<amg_grid(ctx, L0.nentries, 256), 256, 0, ctx->stream>>>((size_t)L0.nentries, val, L0.val32);
     ctx->stats.kernel_launches++;
   }
-  const AmgLevelDev& L = A.lv[A.nlev - 1];
-  if (L.n <= kAmgDenseShared)
-    k_amg_dense_inverse<true><<<1, 1024, (size_t)L.n * L.n * sizeof(double), ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, A.dense);
-  else
-    k_amg_dense_inverse<false><<<1, 1024, 0, ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, A.dense);
-  ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -746,8 +835,8 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv) {
 template <int MODE, bool DOT>
 static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x, const double* b, double om, double* y) {
   const int grid = amg_grid(ctx, (int64_t)L.nslices * 32, kVecBlock);
-  if (L.val32)
-    k_amg_spmv<MODE, DOT, float><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.val32, x, b, L.cur_dinv,
+  if (L.cur32)
+    k_amg_spmv<MODE, DOT, float><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur32, x, b, L.cur_dinv,
                                                                      om, y, ctx->partials, ctx->scal);
   else
     k_amg_spmv<MODE, DOT, double><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur_val, x, b, L.cur_dinv,
@@ -778,7 +867,7 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
   }
   {
     AmgLevelDev& L = A.lv[A.nlev - 1];
-    k_amg_dense_apply<<<1, 1024, 0, st>>>(L.n, A.dense, L.b, L.x2, ctx->scal);
+    k_amg_dense_apply<<<1, 1024, 0, st>>>(L.n, A.cur_dense, L.b, L.x2, ctx->scal);
     ctx->stats.kernel_launches++;
   }
   for (int l = A.nlev - 2; l >= 0; --l) {
@@ -820,7 +909,7 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
   if (max_it <= 0) max_it = 200000;
   if (max_it > 2000000000LL) max_it = 2000000000LL;
   cudaStream_t st = ctx->stream;
-  if ((rc = amg_numeric(ctx, val, dinv))) return rc;
+  if ((rc = amg_numeric(ctx, val, dinv, ctx->amg_kind))) return rc;
   const int g = amg_grid(ctx, std::max(n, 1), kVecBlock);
   if (x0_nonzero) {
     DDPS_CUDA(cudaMemcpyAsync(ctx->p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));

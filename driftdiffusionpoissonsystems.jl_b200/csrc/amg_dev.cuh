@@ -22,6 +22,7 @@ struct AmgLevelDev {
   double* val = nullptr;             // level >= 1: Galerkin values of the current operator (SELL order)
   double* dinv = nullptr;            // level >= 1
   float* val32 = nullptr;            // large levels: fp32 copy of the current values for the cycle's SpMVs
+  const float* cur32 = nullptr;      // the fp32 copy the cycle uses (level-owned or of the active operator set)
   const double* cur_val = nullptr;   // matrix / inverse diagonal used by the cycle (level 0: set per operator)
   const double* cur_dinv = nullptr;
   // transfers to the next level, CSR with packed 8-byte entries {index, float value}: the prolongator values are
@@ -31,11 +32,27 @@ struct AmgLevelDev {
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
 };
 
+// Galerkin values of one KIND of operator (first Newton system of a Vsolve / later Newton systems / u- / v-continuity
+// system): consecutive operators of the same kind differ little once the outer iteration settles, so their coarse
+// operators are reused while the fine operator stays within a tolerance of the snapshot they were computed from.
+constexpr int kAmgKinds = 4;
+struct AmgOpSet {
+  bool allocated = false, valid = false;
+  double* snap = nullptr;                      // fine values the coarse operators were computed from (SELL order)
+  double* val[kAmgMaxLevels] = {nullptr};      // levels >= 1
+  double* dinv[kAmgMaxLevels] = {nullptr};
+  float* val32[kAmgMaxLevels] = {nullptr};
+  double* dense = nullptr;
+};
+
 struct Amg {
   bool ready = false;
   int nlev = 0;
   AmgLevelDev lv[kAmgMaxLevels];
   double* dense = nullptr;   // [n_coarsest^2] inverse of the coarsest operator
+  const double* cur_dense = nullptr;
+  AmgOpSet sets[kAmgKinds];
+  long long reuses = 0, numerics = 0;
   double* z = nullptr;       // [n0] preconditioned residual of the CG
   double omega = 2.0 / 3.0;
   double setup_ms = 0.0;
@@ -43,7 +60,7 @@ struct Amg {
 
 
 // amg.cu: Galerkin product of the fine matrix values `f_val` (SELL order of level F) into level C (values + inverse diagonal)
-void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, AmgLevelDev& C);
+void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv);
 // amg_setup.cu: build transfers of level l and the pattern + base values of level l+1 on the device.
 // Returns 0 on success with *nc_out = rows of the next level (0: coarsening stalled, nothing installed), <0 on error,
 // >0 when the device path does not apply (caller falls back to the host path).

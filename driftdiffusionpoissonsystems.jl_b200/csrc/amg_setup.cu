@@ -426,7 +426,7 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   DDPS_CUDA(cudaMemsetAsync(C.val, 0, std::max<size_t>((size_t)C.nentries, 1) * sizeof(double), st));
   DDPS_CUDA(cudaMemsetAsync(C.dinv, 0, (size_t)nc * sizeof(double), st));
   F.nc = nc;
-  amg_launch_rap(ctx, F, fval, C);
+  amg_launch_rap(ctx, F, fval, C, C.val, C.dinv);
   C.cur_val = C.val;     // base values of the next level (overwritten by the first per-operator numeric phase)
   C.cur_dinv = C.dinv;
   DDPS_CUDA(cudaStreamSynchronize(st));

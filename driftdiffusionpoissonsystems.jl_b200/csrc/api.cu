@@ -403,8 +403,10 @@ int vsolve(Context* ctx) {
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
     // Newton correction: the linear residual only has to be below the Newton tolerance (so that, like the
     // reference's direct solve, a linear problem converges in one step); newton_eta is a relative floor.
+    ctx->amg_kind = newton == 0 ? 0 : 3;
     rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * ctx->tol,
                    ctx->opts.lin_max_it, nullptr, nullptr);
+    ctx->amg_kind = -1;
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
     if (rc) return rc;
@@ -424,8 +426,10 @@ int uvsolve(Context* ctx, int which) {
   ta.stop();
   double* field = (which == DDPS_FIELD_U) ? ctx->U : ctx->W;
   EventTimer tp(ctx, ctx->ev2, ctx->ev3);
+  ctx->amg_kind = (which == DDPS_FIELD_U) ? 1 : 2;
   rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->b, field, ctx->opts.warm_start != 0, ctx->opts.lin_rtol, 0.0,
                  ctx->opts.lin_max_it, nullptr, nullptr);                                     // src:588
+  ctx->amg_kind = -1;
   tp.stop();
   ctx->stats.t_pcg_ms += tp.ms();
   ctx->stats.t_asm_ms += ta.ms();
@@ -993,8 +997,10 @@ int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats
     if (!(res > tol)) break;                                                                  // src:1040
     if (count >= cap) { ctx->fail(DDPS_ERR_NOCONV, "semlin: Newton iteration cap reached"); rc = DDPS_ERR_NOCONV; break; }
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
+    ctx->amg_kind = count == 0 ? 0 : 3;
     rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
                    ctx->opts.lin_max_it, nullptr, nullptr);                                   // src:1063
+    ctx->amg_kind = -1;
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
     if (rc) break;
@@ -1186,7 +1192,7 @@ int ddps_amg_numeric(ddps_ctx* ctx, int which) {
     ctx->fail(DDPS_ERR_ARG, "numeric phase runs on DDPS_MAT_OP (assemble an operator first)");
     return DDPS_ERR_ARG;
   }
-  if ((rc = amg_numeric(ctx, ctx->val_op, ctx->dinv))) return rc;
+  if ((rc = amg_numeric(ctx, ctx->val_op, ctx->dinv, -1))) return rc;
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   return DDPS_OK;
 }
@@ -1234,7 +1240,7 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
       case 4: return assemble_base(ctx, ctx->base_is_semlin);
       case 5: return launch_spmv_dot(ctx, ctx->last_val ? ctx->last_val : ctx->val_op, ctx->p, ctx->q);
       case 6: return amg_pcg_iteration_launch(ctx, ctx->x, it, 1 << 30);
-      case 7: return amg_numeric(ctx, ctx->val_op, ctx->dinv);
+      case 7: return amg_numeric(ctx, ctx->val_op, ctx->dinv, -1);
       case 8: return amg_vcycle(ctx, ctx->r, ctx->q, false);
     }
     ctx->fail(DDPS_ERR_ARG, "unknown kernel id");

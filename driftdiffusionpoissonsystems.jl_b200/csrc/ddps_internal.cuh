@@ -219,6 +219,7 @@ struct Context {
 
   // optional multigrid preconditioner (opts.precond == DDPS_PRECOND_AMG, single GPU)
   Amg* amg = nullptr;
+  int amg_kind = -1;   // which kind of operator the next solve_system call handles (amg_numeric: lagged coarse operators)
 
   void fail(int code, const std::string& msg) {
     err_code = code;
@@ -306,7 +307,7 @@ int amg_setup(Context* ctx);      // build the hierarchy from the base operator 
 void amg_free(Context* ctx);
 bool amg_ready(const Context* ctx);
 // per-operator numeric phase: Galerkin products of `val` on the frozen pattern + coarsest-level inverse
-int amg_numeric(Context* ctx, const double* val, const double* dinv);
+int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind);
 int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz);
 int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
                   double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);

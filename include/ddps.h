@@ -101,7 +101,10 @@ typedef struct ddps_solver_opts {
                            V(1,1) cycle (frozen prolongators from the base stiffness, Galerkin operators of every assembled
                            M - J0 recomputed on the device); same stop rules, same solutions to solver tolerance.
                            Single-GPU contexts only; with a communicator the Jacobi path stays in charge */
-  int32_t reserved[1];
+  int32_t amg_no_lag;   /* multigrid path: 1 = recompute the coarse (Galerkin) operators for every assembled operator.  Default 0:
+                           they are reused while the operator of the same kind (first / later Newton system, u-, v-continuity
+                           system) stays within 1 % (entries and row sums) of the one they were computed from -- the cycle is
+                           only a preconditioner, the solutions are the same to solver tolerance */
 } ddps_solver_opts;
 
 #define DDPS_PRECOND_JACOBI 0
@@ -122,7 +125,7 @@ typedef struct ddps_stats {
   int32_t status;          /* DDPS_OK / DDPS_ERR_NOCONV / DDPS_ERR_BREAKDOWN */
   int32_t n_negative_area; /* elements with signed area < 0 (Q2: mass uses signed ar, src:375) */
   int32_t amg_levels;      /* multigrid levels in use (0: Jacobi-PCG) */
-  int32_t reserved0;
+  int32_t amg_reuses;      /* solves that reused lagged coarse operators (opts.amg_no_lag = 0) */
   double t_amg_setup_ms;   /* host wall: one-time hierarchy setup (aggregation, prolongators, coarse patterns, uploads) */
   int32_t reserved[4];
 } ddps_stats;

@@ -52,14 +52,14 @@ struct SolverOpts
     max_newton::Int32; max_gummel::Int32; check_every::Int32; warm_start::Int32; verbose::Int32; lin_cap_ok::Int32
     no_alt_traversal::Int32; warm_start_v::Int32; no_sym_scaling::Int32; renumber::Int32
     precond::Int32        # 0 = Jacobi-PCG (default), 1 = CG preconditioned with the smoothed-aggregation multigrid V-cycle
-    reserved::NTuple{1,Int32}
+    amg_no_lag::Int32     # 1: recompute the multigrid coarse operators for every assembled operator (default 0: lagged)
 end
 
 struct Stats
     outer_iters::Int32; newton_total::Int32; pcg_total::Int64; spmv_total::Int64; kernel_launches::Int64
     control::Cdouble; t_setup_ms::Cdouble; t_solve_ms::Cdouble; t_asm_ms::Cdouble; t_pcg_ms::Cdouble; t_wall_ms::Cdouble
     status::Int32; n_negative_area::Int32
-    amg_levels::Int32; reserved0::Int32; t_amg_setup_ms::Cdouble; reserved::NTuple{4,Int32}
+    amg_levels::Int32; amg_reuses::Int32; t_amg_setup_ms::Cdouble; reserved::NTuple{4,Int32}
 end
 
 lasterr(h) = unsafe_string(ccall((:ddps_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
@@ -80,7 +80,7 @@ function with_ctx(f; device = 0, verbose = true)
         v = o[]
         o[] = SolverOpts(v.lin_rtol, v.newton_eta, v.lin_max_it, v.max_newton, v.max_gummel, v.check_every, v.warm_start,
                          Int32(verbose), v.lin_cap_ok, v.no_alt_traversal, v.warm_start_v, v.no_sym_scaling, v.renumber, PRECOND[],
-                         v.reserved)
+                         v.amg_no_lag)
         chk(h, ccall((:ddps_set_opts, LIB), Cint, (Ptr{Cvoid}, Ref{SolverOpts}), h, o))
         return f(h)
     finally

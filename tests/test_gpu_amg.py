@@ -228,3 +228,25 @@ def test_amg_and_jacobi_agree_on_a_structured_diode_and_renumbering(D, O):
     with D.Session(0, precond=1) as s:
         V2, u2, v2 = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, verbose=False)
     assert np.array_equal(V2, out["amg"][0]) and np.array_equal(u2, out["amg"][1]) and np.array_equal(v2, out["amg"][2])
+
+
+def test_lagged_coarse_operators(D, O):
+    """opts.amg_no_lag = 0 (default): the Galerkin operators of a kind of system (first / later Newton system, u-, v-continuity
+    system) are reused while the fine operator stays within 1 % of the one they were computed from.  Only the preconditioner
+    changes: same fields (north-star tolerance against the oracle), same Gummel / Newton counts, a few more CG iterations at
+    most; the late Gummel iterations do reuse."""
+    mesh = D.structured_mesh(160, 80, 0.0, 2.0, 0.0, 1.0)
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
+    ref = O.solve_ddpe(oracle_mesh(mesh), *[pr[k] for k in KEYS])
+    out = {}
+    for name, opts in (("lagged", dict(precond=1)), ("exact", dict(precond=1, amg_no_lag=1))):
+        with D.Session(0, **opts) as s:
+            V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+        out[name] = (V, u, v, st)
+        for a, b in zip((V, u, v), ref):
+            assert rel_l2(a, b) <= FIELD_TOL
+    sl, se = out["lagged"][3], out["exact"][3]
+    assert se["amg_reuses"] == 0 and sl["amg_reuses"] >= 8, (sl["amg_reuses"], se["amg_reuses"])
+    assert sl["outer_iters"] == se["outer_iters"]
+    assert [int(k) for k in sl["newton_per_vsolve"]] == [int(k) for k in se["newton_per_vsolve"]]
+    assert sl["pcg_total"] <= 1.1 * se["pcg_total"] + 4, (sl["pcg_total"], se["pcg_total"])
