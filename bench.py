@@ -298,7 +298,11 @@ def main():
                            "solver": ("hand-written CG preconditioned with a smoothed-aggregation multigrid V(1,1) cycle "
                                       "(opts.precond=1; SURVEY 8f rank 1), lin_rtol 1e-13, Newton corrections to 0.1*tol"
                                       if precond == "amg" else "Jacobi-PCG, lin_rtol 1e-13, Newton corrections to 0.1*tol"),
-                           "preconditioner": precond},
+                           "preconditioner": precond,
+                           "precision": ("CG operator, vectors, dots and all arithmetic f64; the multigrid cycle (a preconditioner only) "
+                                         "stores its transfer operators and a copy of the large levels' matrix values in fp32; coarse "
+                                         "operators lagged per operator kind (opts.amg_no_lag=0); parity tests: fields <= 1e-8 vs the oracle"
+                                         if precond == "amg" else "f64 throughout")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "pcg_iterations": int(pcg_its),
                 "control": [float(c) for c in ctrl], "roofline": roofline, "cpu_baseline": cpu}
         if args.pcg_cap > 0:
