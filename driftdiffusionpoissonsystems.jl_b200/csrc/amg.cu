@@ -112,6 +112,56 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_amg_spmv(int nrows, int nslice
   }
 }
 
+// Small levels (a few thousand rows, 15-40 entries per row): one WARP per row instead of one lane per row, so the row's
+// entries are loaded by 32 lanes at once (one dependent load chain instead of len/4 of them; these kernels are pure
+// latency).  Same SELL-32 addressing, fixed shuffle-tree summation (deterministic).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_amg_spmv_wpr(int nrows, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr,
+                                                      const int* __restrict__ col, const double* __restrict__ val,
+                                                      const double* __restrict__ x, const double* __restrict__ b,
+                                                      const double* __restrict__ dinv, double om, double* __restrict__ y,
+                                                      const PcgScalars* scal) {
+  if (scal->done) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int row = gw; row < nrows; row += nw) {
+    const int len = rowptr[row + 1] - rowptr[row];
+    const int base = slice_ptr[row >> 5] + (row & 31);
+    double sum = 0.0;
+    for (int k = lane; k < len; k += 32) sum += val[base + 32 * k] * __ldg(x + col[base + 32 * k]);
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      double out;
+      if (MODE == 0) out = sum;
+      else if (MODE == 1) out = b[row] - sum;
+      else out = x[row] + om * (dinv[row] * (b[row] - sum));
+      y[row] = out;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_amg_restrict_wpr(int nc, const int* __restrict__ Rptr, const int2* __restrict__ Rent,
+                                                          const double* __restrict__ t, double* __restrict__ bc,
+                                                          const double* __restrict__ dinv_c, double om, double* __restrict__ xc,
+                                                          const PcgScalars* scal) {
+  if (scal->done) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int I = gw; I < nc; I += nw) {
+    const int q0 = Rptr[I], q1 = Rptr[I + 1];
+    double s = 0.0;
+    for (int q = q0 + lane; q < q1; q += 32) {
+      const int2 en = Rent[q];
+      s += (double)__int_as_float(en.y) * __ldg(t + en.x);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      bc[I] = s;
+      if (dinv_c) xc[I] = om * (dinv_c[I] * s);
+    }
+  }
+}
+
 __global__ void k_amg_to_float(size_t n, const double* __restrict__ in, float* __restrict__ out) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __double2float_rn(ld_stream(in + i));
@@ -832,8 +882,17 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind) {
   return 0;
 }
 
+constexpr int kAmgSmallLevel = 32768;   // rows; below this the warp-per-row kernels run
+
 template <int MODE, bool DOT>
 static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x, const double* b, double om, double* y) {
+  if (!DOT && L.n <= kAmgSmallLevel && !L.cur32) {
+    k_amg_spmv_wpr<MODE><<<amg_grid(ctx, (int64_t)L.n * 32, 256), 256, 0, ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, x, b,
+                                                                                        L.cur_dinv, om, y, ctx->scal);
+    ctx->stats.kernel_launches++;
+    ctx->stats.spmv_total++;
+    return;
+  }
   const int grid = amg_grid(ctx, (int64_t)L.nslices * 32, kVecBlock);
   if (L.cur32)
     k_amg_spmv<MODE, DOT, float><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur32, x, b, L.cur_dinv,
@@ -861,8 +920,12 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
     launch_amg_spmv<1, false>(ctx, L, L.x, L.b, om, L.t);
     AmgLevelDev& C = A.lv[l + 1];
     const bool coarsest = (l + 2 == A.nlev);
-    k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, coarsest ? nullptr : C.cur_dinv, om, C.x,
-                                                            ctx->scal);
+    if (L.nc <= kAmgSmallLevel)
+      k_amg_restrict_wpr<<<amg_grid(ctx, (int64_t)L.nc * 32, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, coarsest ? nullptr : C.cur_dinv,
+                                                                                om, C.x, ctx->scal);
+    else
+      k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, coarsest ? nullptr : C.cur_dinv, om, C.x,
+                                                              ctx->scal);
     ctx->stats.kernel_launches++;
   }
   {
