@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) k_amg_restrict_wpr(int nc, const int* __r
 // CTA: residual, restriction, ..., coarsest solve, ..., prolongation, smoothing sweep, with __syncthreads() between the
 // phases instead of 4 launches per level (these levels are pure launch + latency).  Same arithmetic and summation order
 // as the per-level warp-per-row kernels above.
-constexpr int kAmgBottomRows = 256;    // (4096 was measured: one SM cannot hide the latency of ~2000 rows -> +156 us per cycle)
+constexpr int kAmgBottomRows = 4096;
 constexpr int kAmgBottomMax = 6;
 struct AmgBottomLevel {
   int n, nc;
@@ -999,10 +999,9 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
   A.lv[0].b = const_cast<double*>(r);
   A.lv[0].x2 = z;
   // levels lb .. nlev-1 (at most kAmgBottomRows rows each, fp64 values) run in one single-CTA launch
-  static const int bottom_rows = getenv("DDPS_AMG_BOTTOM_ROWS") ? atoi(getenv("DDPS_AMG_BOTTOM_ROWS")) : kAmgBottomRows;   // (A/B switch)
   int lb = A.nlev - 1;
-  while (lb > 1 && A.lv[lb - 1].n <= bottom_rows && !A.lv[lb - 1].cur32 && A.nlev - (lb - 1) <= kAmgBottomMax) --lb;
-  if (A.lv[A.nlev - 1].n > kAmgDenseMax) lb = A.nlev - 1;
+  while (lb > 1 && A.lv[lb - 1].n <= kAmgBottomRows && !A.lv[lb - 1].cur32 && A.nlev - (lb - 1) <= kAmgBottomMax) --lb;
+  if (getenv("DDPS_AMG_NO_BOTTOM") || A.lv[A.nlev - 1].n > kAmgDenseMax) lb = A.nlev - 1;   // (A/B switch)
   const bool bottom = lb < A.nlev - 1;
   const int ltop = bottom ? lb : A.nlev - 1;   // levels 0 .. ltop-1 run level by level
   for (int l = 0; l < ltop; ++l) {
