@@ -162,93 +162,6 @@ __global__ void __launch_bounds__(256) k_amg_restrict_wpr(int nc, const int* __r
   }
 }
 
-// The bottom of the V-cycle (levels with at most kAmgBottomRows rows: a few thousand rows in total) in ONE launch of one
-// CTA: residual, restriction, ..., coarsest solve, ..., prolongation, smoothing sweep, with __syncthreads() between the
-// phases instead of 4 launches per level (these levels are pure launch + latency).  Same arithmetic and summation order
-// as the per-level warp-per-row kernels above.
-constexpr int kAmgBottomRows = 4096;
-constexpr int kAmgBottomMax = 6;
-struct AmgBottomLevel {
-  int n, nc;
-  const int *rowptr, *slice_ptr, *col;
-  const double *val, *dinv;
-  const int *Pptr, *Rptr;
-  const int2 *Pent, *Rent;
-  double *b, *x, *x2, *t;
-};
-struct AmgBottomArgs {
-  int nlev;                       // levels[0] is the finest level of the bottom part, levels[nlev-1] the coarsest of the hierarchy
-  AmgBottomLevel lv[kAmgBottomMax];
-  const double* dense;
-  double om;
-};
-
-__device__ __forceinline__ void bottom_spmv(const AmgBottomLevel& L, int mode, double om, const double* x, double* y) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int row = wid; row < L.n; row += nw) {
-    const int len = L.rowptr[row + 1] - L.rowptr[row];
-    const int base = L.slice_ptr[row >> 5] + (row & 31);
-    double sum = 0.0;
-    for (int k = lane; k < len; k += 32) sum += L.val[base + 32 * k] * x[L.col[base + 32 * k]];
-    sum = warp_sum(sum);
-    if (lane == 0) y[row] = mode == 1 ? L.b[row] - sum : x[row] + om * (L.dinv[row] * (L.b[row] - sum));
-  }
-}
-
-__global__ void __launch_bounds__(1024) k_amg_bottom(const AmgBottomArgs A, const PcgScalars* scal) {
-  __shared__ double shb[kAmgDenseMax];
-  if (scal->done) return;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  // down: levels[0].b and levels[0].x (first sweep) were produced by the restriction kernel of the level above
-  for (int l = 0; l + 1 < A.nlev; ++l) {
-    const AmgBottomLevel& L = A.lv[l];
-    const AmgBottomLevel& C = A.lv[l + 1];
-    bottom_spmv(L, 1, A.om, L.x, L.t);
-    __syncthreads();
-    const bool coarsest = (l + 2 == A.nlev);
-    for (int I = wid; I < L.nc; I += nw) {
-      double s = 0.0;
-      for (int q = L.Rptr[I] + lane; q < L.Rptr[I + 1]; q += 32) {
-        const int2 en = L.Rent[q];
-        s += (double)__int_as_float(en.y) * L.t[en.x];
-      }
-      s = warp_sum(s);
-      if (lane == 0) {
-        C.b[I] = s;
-        if (!coarsest) C.x[I] = A.om * (C.dinv[I] * s);
-      }
-    }
-    __syncthreads();
-  }
-  {  // coarsest level: x2 = Ainv b
-    const AmgBottomLevel& L = A.lv[A.nlev - 1];
-    for (int j = threadIdx.x; j < L.n; j += blockDim.x) shb[j] = L.b[j];
-    __syncthreads();
-    for (int i = wid; i < L.n; i += nw) {
-      double s = 0.0;
-      for (int j = lane; j < L.n; j += 32) s += A.dense[i * L.n + j] * shb[j];
-      s = warp_sum(s);
-      if (lane == 0) L.x2[i] = s;
-    }
-    __syncthreads();
-  }
-  for (int l = A.nlev - 2; l >= 0; --l) {
-    const AmgBottomLevel& L = A.lv[l];
-    const AmgBottomLevel& C = A.lv[l + 1];
-    for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
-      double s = 0.0;
-      for (int m = L.Pptr[i]; m < L.Pptr[i + 1]; ++m) {
-        const int2 en = L.Pent[m];
-        s += (double)__int_as_float(en.y) * C.x2[en.x];
-      }
-      L.x[i] += s;
-    }
-    __syncthreads();
-    bottom_spmv(L, 2, A.om, L.x, L.x2);
-    __syncthreads();
-  }
-}
-
 __global__ void k_amg_to_float(size_t n, const double* __restrict__ in, float* __restrict__ out) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __double2float_rn(ld_stream(in + i));
@@ -998,13 +911,7 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
   cudaStream_t st = ctx->stream;
   A.lv[0].b = const_cast<double*>(r);
   A.lv[0].x2 = z;
-  // levels lb .. nlev-1 (at most kAmgBottomRows rows each, fp64 values) run in one single-CTA launch
-  int lb = A.nlev - 1;
-  while (lb > 1 && A.lv[lb - 1].n <= kAmgBottomRows && !A.lv[lb - 1].cur32 && A.nlev - (lb - 1) <= kAmgBottomMax) --lb;
-  if (getenv("DDPS_AMG_NO_BOTTOM") || A.lv[A.nlev - 1].n > kAmgDenseMax) lb = A.nlev - 1;   // (A/B switch)
-  const bool bottom = lb < A.nlev - 1;
-  const int ltop = bottom ? lb : A.nlev - 1;   // levels 0 .. ltop-1 run level by level
-  for (int l = 0; l < ltop; ++l) {
+  for (int l = 0; l + 1 < A.nlev; ++l) {
     AmgLevelDev& L = A.lv[l];
     if (l == 0 && !have_first_sweep) {   // (inside the CG the update kernel already produced the first sweep of the finest
       k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);   // level; coarser
@@ -1021,26 +928,12 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
                                                               ctx->scal);
     ctx->stats.kernel_launches++;
   }
-  if (bottom) {
-    AmgBottomArgs B;
-    memset(&B, 0, sizeof(B));
-    B.nlev = A.nlev - lb;
-    B.dense = A.cur_dense;
-    B.om = om;
-    for (int k = 0; k < B.nlev; ++k) {
-      const AmgLevelDev& L = A.lv[lb + k];
-      AmgBottomLevel& o = B.lv[k];
-      o.n = L.n; o.nc = L.nc; o.rowptr = L.rowptr; o.slice_ptr = L.slice_ptr; o.col = L.col; o.val = L.cur_val; o.dinv = L.cur_dinv;
-      o.Pptr = L.Pptr; o.Rptr = L.Rptr; o.Pent = L.Pent; o.Rent = L.Rent; o.b = L.b; o.x = L.x; o.x2 = L.x2; o.t = L.t;
-    }
-    k_amg_bottom<<<1, 1024, 0, st>>>(B, ctx->scal);
-    ctx->stats.kernel_launches++;
-  } else {
+  {
     AmgLevelDev& L = A.lv[A.nlev - 1];
     k_amg_dense_apply<<<1, 1024, 0, st>>>(L.n, A.cur_dense, L.b, L.x2, ctx->scal);
     ctx->stats.kernel_launches++;
   }
-  for (int l = ltop - 1; l >= 0; --l) {
+  for (int l = A.nlev - 2; l >= 0; --l) {
     AmgLevelDev& L = A.lv[l];
     k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pent, A.lv[l + 1].x2, L.x, ctx->scal);
     ctx->stats.kernel_launches++;
