@@ -246,6 +246,7 @@ def main():
         pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in smp.items()}
         h2d = nodes.nbytes + elems.nbytes + sum(pinned[k].nbytes for k in ("lambda2", "mu_p", "mu_n", "C_mid")) + 3 * 16 * len(smp["n"])
         d2h = 3 * 8 * mesh.nq
+        outs = tuple(torch.empty(mesh.nq, dtype=torch.float64).pin_memory().numpy() for _ in range(3))   # caller-owned outputs
         barrier()
         t0 = time.perf_counter()
         s2 = D.Session(local, comm=comm, **sopts) if comm is None else None
@@ -261,7 +262,7 @@ def main():
         s2.upload_ddpe(pinned)
         s2.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
         s2.ddpe_step(args.steps)
-        s2.ddpe_fetch()
+        s2.ddpe_fetch(out=outs)
         barrier()
         t_e2e = time.perf_counter() - t0
         if dist is not None:

@@ -252,9 +252,14 @@ class Session:
         self._check(self.lib.ddps_ddpe_step(self.h, int(nsteps), int(bool(stop_at_tol)), _lib.dptr(ctrl), C.byref(done)))
         return ctrl[:done.value]
 
-    def ddpe_fetch(self):
+    def ddpe_fetch(self, out=None):
+        """Copy the current V, u, v to the host.  ``out`` = three caller-owned float64 arrays of length nq (e.g. pinned
+        memory, like the caller-allocated outputs of the C ABI); default: fresh numpy arrays."""
         nq = self.mesh.nq
-        V, u, v = np.empty(nq), np.empty(nq), np.empty(nq)
+        V, u, v = out if out is not None else (np.empty(nq), np.empty(nq), np.empty(nq))
+        for a in (V, u, v):
+            if a.shape != (nq,) or a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("ddpe_fetch outputs must be contiguous float64 arrays of length nq")
         self._check(self.lib.ddps_ddpe_fetch(self.h, _lib.dptr(V), _lib.dptr(u), _lib.dptr(v)))
         return V, u, v
 
