@@ -4,6 +4,7 @@
 
 #include <stdint.h>
 
+#include <atomic>
 #include <vector>
 
 #include "../../include/ddps.h"
@@ -38,7 +39,10 @@ struct AmgHost {
 
 inline int amg_small_cap(const AmgParams& prm, int n) { return (n <= prm.small_level) ? prm.small_cap : 0; }
 // aggregation on sorted strong-neighbour lists (shared by the host and the device setup paths); returns #aggregates
-int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::vector<int>& agg);
+// rows_ready (optional): the lists of rows [0, *rows_ready) have arrived (a producer thread is still copying the rest from
+// the device); the first, sequential pass consumes the rows as they come.
+int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::vector<int>& agg,
+                        const std::atomic<long long>* rows_ready = nullptr);
 
 int amg_host_build(AmgHost& H, int n, std::vector<int>&& rowptr, std::vector<int>&& col, std::vector<double>&& val,
                    const unsigned char* fixed, const AmgParams& prm);

@@ -100,10 +100,16 @@ void strong_lists(const AmgHostLevel& L, const unsigned char* fixed, double thet
 // cap > 0 (gentle coarsening for the last, tiny levels: the global smooth modes live there and a coarsening ratio
 // of ~7 from a few hundred rows costs CG iterations): a free node takes at most `cap` of its strongest free strong
 // neighbours; leftovers join their strongest aggregated neighbour or stay alone.
-int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::vector<int>& agg) {
+int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::vector<int>& agg,
+                        const std::atomic<long long>* rows_ready) {
   agg.assign(n, -1);
   int nc = 0;
+  auto wait_all = [&]() {
+    if (rows_ready)
+      while (rows_ready->load(std::memory_order_acquire) < n) std::this_thread::yield();
+  };
   if (cap > 0) {
+    wait_all();
     for (int i = 0; i < n; ++i) {
       if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;
       int taken = 0;
@@ -128,12 +134,17 @@ int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::v
   // (measured: chunking a 8.4M-row level saves 30 ms of 100 but the seams' leftovers densify the coarser levels and cost
   // +12 % CG iterations -> the chunked path is kept for experiments only, DDPS_AMG_AGG_CHUNKS=1)
   const int nchunks = (n >= 200000 && getenv("DDPS_AMG_AGG_CHUNKS")) ? kAggChunks : 1;
+  if (nchunks > 1) wait_all();
   const int64_t csize = ((int64_t)n + nchunks - 1) / nchunks;
   std::vector<int> cbase(nchunks + 1, 0);
   auto pass1 = [&](int c) {
     const int lo = (int)std::min<int64_t>(n, c * csize), hi = (int)std::min<int64_t>(n, lo + csize);
     int local = 0;
+    long long avail = rows_ready ? 0 : n;
     for (int i = lo; i < hi; ++i) {
+      if (i >= avail) {   // streamed input: wait until the producer has delivered this row's list
+        while ((avail = rows_ready->load(std::memory_order_acquire)) <= i) std::this_thread::yield();
+      }
       if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;
       bool ok = true;
       for (int k = sptr[i]; k < sptr[i + 1]; ++k) {

@@ -13,9 +13,12 @@
 //   6. SELL-32 layout of the coarse pattern and the Galerkin product of the BASE values (k_amg_rap2 of amg.cu), which
 //      the next level's strength / prolongator smoothing need.
 // The arrays built here are installed in the hierarchy as they are (no host round trip, no upload).
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
+#include <thread>
 
 #include <cub/cub.cuh>
 
@@ -284,18 +287,35 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
   DDPS_CUDA(cudaStreamSynchronize(st));
   DDPS_CUDA(tmp.alloc(&d_scol, (size_t)ns));
   k_strong<true><<<(n + T - 1) / T, T, 0, st>>>(n, F.rowptr, F.slice_ptr, F.col, fval, d_fixed, prm.theta, nullptr, d_sptr, d_scol);
-  std::vector<int> sptr((size_t)n + 1), scol((size_t)std::max(ns, 1));
+  std::vector<int> sptr((size_t)n + 1);
   DDPS_CUDA(cudaMemcpyAsync(sptr.data(), d_sptr, sptr.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-  DDPS_CUDA(cudaMemcpyAsync(scol.data(), d_scol, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, st));
-  DDPS_CUDA(cudaStreamSynchronize(st));
+  DDPS_CUDA(cudaStreamSynchronize(st));   // the lists are complete on the device, the row pointers on the host
 
   const double t1 = now();
-  // ---- 2. aggregation (host, sequential greedy: the quality of the coarsening lives here) ----
+  // ---- 2. aggregation (host, sequential greedy: the quality of the coarsening lives here).  The neighbour lists are
+  //         copied by a producer thread in row chunks while the first, sequential pass already consumes them ----
+  std::unique_ptr<int[]> scol(new int[(size_t)std::max(ns, 1)]);   // not value-initialised: the producer touches the pages
+  std::atomic<long long> rows_ready(0);
+  std::atomic<int> copy_err(0);
+  const int dev = ctx->device;
+  std::thread producer([&]() {
+    cudaSetDevice(dev);
+    const int nchunk = 32;
+    for (int c = 0; c < nchunk; ++c) {
+      const long long r0 = (long long)n * c / nchunk, r1 = (long long)n * (c + 1) / nchunk;
+      const size_t o0 = (size_t)sptr[r0], o1 = (size_t)sptr[r1];
+      if (o1 > o0 && cudaMemcpy(scol.get() + o0, d_scol + o0, (o1 - o0) * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        copy_err.store(1);
+      rows_ready.store(r1, std::memory_order_release);
+    }
+  });
   std::vector<int> agg;
-  const int nc = amg_aggregate_lists(n, sptr.data(), scol.data(), amg_small_cap(prm, n), agg);
+  const int nc = amg_aggregate_lists(n, sptr.data(), scol.get(), amg_small_cap(prm, n), agg, &rows_ready);
+  producer.join();
+  if (copy_err.load()) { ctx->fail(DDPS_ERR_CUDA, "copy of the strong-neighbour lists failed"); return DDPS_ERR_CUDA; }
   if (nc <= 0 || nc > 0.7 * n) return 0;   // coarsening stalled
   std::vector<int>().swap(sptr);
-  std::vector<int>().swap(scol);
+  scol.reset();
   const double t2 = now();
   int* d_agg;
   DDPS_CUDA(tmp.alloc(&d_agg, (size_t)n));
