@@ -505,6 +505,13 @@ int ddps_ctx_create(ddps_ctx** out, int device) {
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
   ctx->num_sms = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  {   // setup temporaries live in the stream-ordered pool: keep freed blocks cached for the next setup
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
   cudaEventCreate(&ctx->ev4); cudaEventCreate(&ctx->ev5);
   if ((e = cudaMalloc(&ctx->scal, sizeof(PcgScalars))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -613,8 +620,8 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
       // packed 0-based int4 records and the range check run on the device
       long long* d_el = nullptr;
       int* d_bad = nullptr;
-      DDPS_CUDA(cudaMalloc(&d_el, (size_t)5 * nme * sizeof(long long)));
-      if ((rc = dev_alloc(ctx, &ctx->elem, (size_t)nme)) || (rc = dev_alloc(ctx, &ctx->xy, (size_t)nq))) { cudaFree(d_el); return rc; }
+      DDPS_CUDA(cudaMallocAsync(&d_el, (size_t)5 * nme * sizeof(long long), ctx->stream));   // (pool: see setup.cu)
+      if ((rc = dev_alloc(ctx, &ctx->elem, (size_t)nme)) || (rc = dev_alloc(ctx, &ctx->xy, (size_t)nq))) { cudaFreeAsync(d_el, ctx->stream); return rc; }
       cudaMalloc(&d_bad, sizeof(int));
       cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
       cudaMemcpyAsync(d_el, elements, (size_t)5 * nme * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
@@ -622,8 +629,9 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
       k_convert_elements<<<(unsigned)((nme + 255) / 256), 256, 0, ctx->stream>>>(d_el, (int)nme, (long long)nq, ctx->elem, d_bad);
       int bad = 0;
       cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaFreeAsync(d_el, ctx->stream);
       cudaError_t ce = cudaStreamSynchronize(ctx->stream);
-      cudaFree(d_el); cudaFree(d_bad);
+      cudaFree(d_bad);
       if (ce != cudaSuccess) { ctx->fail(DDPS_ERR_CUDA, cudaGetErrorString(ce)); return DDPS_ERR_CUDA; }
       if (bad) {
         ctx->fail(DDPS_ERR_ARG, "element " + std::to_string(bad) + " references a node outside 1..nq");
