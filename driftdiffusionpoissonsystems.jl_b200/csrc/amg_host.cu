@@ -175,7 +175,8 @@ int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::v
   // pass 2 (no chaining: decisions use the pass-1 state only)
   std::vector<int> join(n, -1);
   {
-    const int nt = nchunks == 1 ? 1 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    // (reads the pass-1 state only: the result does not depend on the number of threads)
+    const int nt = n < 200000 ? 1 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     parallel_ranges(n, nt, [&](int, int64_t lo, int64_t hi) {
       for (int64_t i = lo; i < hi; ++i) {
         if (agg[i] >= 0) continue;
