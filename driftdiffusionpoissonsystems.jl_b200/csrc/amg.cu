@@ -2,15 +2,19 @@
 // preconditioner behind the same PCG interface", the replacement of the reference's `\`, src:394,588,1063).
 //
 // Split of the work:
-//   * once per base operator (host, amg_host.cu): aggregates, frozen smoothed prolongators P_l, R_l = P_l^T
-//     stored row-wise, and the coarse sparsity patterns;
+//   * once per base operator: aggregates, frozen smoothed prolongators P_l (fp32, packed), R_l = P_l^T stored
+//     row-wise, and the coarse sparsity patterns -- on the device for the large levels (amg_setup.cu; only the
+//     strong-neighbour lists go to the host for the sequential greedy aggregation), by the host reference
+//     implementation (amg_host.cu) for the small rest;
 //   * once per operator A = M - J0 (device, k_amg_rap2): the Galerkin products A_{l+1} = R_l A_l P_l on the frozen
 //     patterns -- one warp per coarse row, the (fine row, fine entry) pairs dealt to the lanes, lane-private
 //     accumulator rows in shared memory, fixed-order reduction: no atomics, bitwise reproducible; then the dense
-//     inverse of the coarsest operator (Gauss-Jordan in one CTA, in shared memory);
+//     inverse of the coarsest operator (Gauss-Jordan in one CTA, in shared memory).  Coarse operators are kept per
+//     KIND of system and reused while the fine operator stays within 1 % of the snapshot they came from (amg_numeric);
 //   * per CG iteration (device): one V(1,1) cycle with damped-Jacobi smoothing; all matrices are SELL-32 like the
-//     fine operator, the smoother and the residual are fused into the SpMV epilogue, restriction/prolongation are
-//     deterministic row gathers.  The cycle is a fixed SPD linear operator, so plain (non-flexible) CG applies.
+//     fine operator (the large levels also as an fp32 copy for the cycle's SpMVs; arithmetic is FP64 throughout), the
+//     smoother and the residual are fused into the SpMV epilogue, restriction/prolongation are deterministic row
+//     gathers.  The cycle is a fixed SPD linear operator, so plain (non-flexible) CG applies.
 // The PCG control flow (alpha, beta, stop test, iteration counter) stays on the device like in the Jacobi path;
 // every kernel of the cycle early-exits once the `done` flag is up.
 #include <chrono>
