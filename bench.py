@@ -306,6 +306,9 @@ def main():
                                          if precond == "amg" else "f64 throughout")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "pcg_iterations": int(pcg_its),
                 "control": [float(c) for c in ctrl], "roofline": roofline, "cpu_baseline": cpu}
+        if world > 1:
+            line["note"] = ("node-partitioned Jacobi-PCG (the multigrid hierarchy is single-GPU in this round, DESIGN.md section 9): on this "
+                            "workload ONE GPU with the multigrid-preconditioned CG delivers ~14.6 Gummel it/s (profiles/r01_bench_s16_n1_amg.json)")
         if args.pcg_cap > 0:
             line["invalid"] = f"profiling run: PCG capped at {args.pcg_cap} iterations per solve"
         print(json.dumps(line), flush=True)
