@@ -342,6 +342,106 @@ __global__ void __launch_bounds__(WARPS * 32) k_amg_rap2(int nc, const int* __re
   }
 }
 
+// Two-stage Galerkin product (device-built levels).  Stage 1: row i of A*P on its fixed sorted pattern -- one thread per fine
+// row (consecutive lanes read neighbouring SELL entries and prolongator rows), products added in entry order into a
+// thread-private accumulator (slot by a search in the row's short column list).  Stage 2 (k_amg_rap_ap): C(I,:) = sum_i R(I,i)
+// (A*P)(i,:) with the lane-private tables of k_amg_rap2 -- a third of the products of the one-stage kernel and one gather
+// level less.  Both orders of summation are fixed functions of the patterns: bitwise reproducible.
+constexpr int kApRowMax = 64;   // = kMaxLocalRow of amg_setup.cu (longer rows: no A*P pattern, one-stage kernel)
+
+__global__ void __launch_bounds__(128) k_amg_ap(int n, const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                                                const double* __restrict__ val, const int* __restrict__ Pptr,
+                                                const int2* __restrict__ Pent, const int* __restrict__ APptr,
+                                                const int* __restrict__ APcol, double* __restrict__ APval) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = APptr[i], cnt = APptr[i + 1] - o;
+  if (cnt == 0) return;
+  int cols[kApRowMax];
+  double acc[kApRowMax];
+  for (int t = 0; t < cnt; ++t) { cols[t] = APcol[o + t]; acc[t] = 0.0; }
+  const int fb = slice_ptr[i >> 5];
+  const int w = (slice_ptr[(i >> 5) + 1] - fb) >> 5;
+  int idx = fb + (i & 31);
+  for (int k = 0; k < w; ++k, idx += 32) {
+    const double a = val[idx];
+    if (a == 0.0) continue;   // padding and exact zeros
+    const int j = col[idx];
+    const int m1 = Pptr[j + 1];
+    for (int m = Pptr[j]; m < m1; ++m) {
+      const int2 pe = Pent[m];
+      int t = 0;
+      while (t < cnt - 1 && cols[t] != pe.x) ++t;
+      acc[t] += a * (double)__int_as_float(pe.y);
+    }
+  }
+  for (int t = 0; t < cnt; ++t) APval[o + t] = acc[t];
+}
+
+template <int SLOTS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_amg_rap_ap(int nc, const int* __restrict__ Rptr, const int2* __restrict__ Rent,
+                                                          const int* __restrict__ APptr, const int* __restrict__ APcol,
+                                                          const double* __restrict__ APval, const int* __restrict__ c_rowptr,
+                                                          const int* __restrict__ c_slice_ptr, const int* __restrict__ c_col,
+                                                          double* __restrict__ c_val, double* __restrict__ c_dinv) {
+  constexpr int STRIDE = SLOTS + 1;
+  __shared__ double sh_tab[WARPS][32 * STRIDE];
+  __shared__ int sh_col[WARPS][SLOTS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* tab = sh_tab[wid];
+  int* ccols = sh_col[wid];
+  const int gw = blockIdx.x * WARPS + wid, nw = gridDim.x * WARPS;
+  for (int I = gw; I < nc; I += nw) {
+    const int len = c_rowptr[I + 1] - c_rowptr[I];
+    const int cbase = c_slice_ptr[I >> 5] + (I & 31);
+    const int q0 = Rptr[I], q1 = Rptr[I + 1];
+    if (len <= SLOTS) {
+      for (int t = lane; t < len; t += 32) ccols[t] = c_col[cbase + 32 * t];
+      for (int t = 0; t < len; ++t) tab[lane * STRIDE + t] = 0.0;
+      __syncwarp();
+      for (int q = q0 + lane; q < q1; q += 32) {
+        const int2 re = Rent[q];
+        const double r = (double)__int_as_float(re.y);
+        const int e1 = APptr[re.x + 1];
+        for (int e = APptr[re.x]; e < e1; ++e) {
+          const int J = APcol[e];
+          int lo = 0, hi = len;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ccols[mid] < J) lo = mid + 1; else hi = mid;
+          }
+          tab[lane * STRIDE + lo] += r * APval[e];
+        }
+      }
+      __syncwarp();
+      for (int t = lane; t < len; t += 32) {
+        double s = 0.0;
+        for (int l = 0; l < 32; ++l) s += tab[l * STRIDE + t];
+        c_val[cbase + 32 * t] = s;
+        if (ccols[t] == I) c_dinv[I] = 1.0 / s;
+      }
+      __syncwarp();
+    } else {
+      for (int t0 = 0; t0 < len; t0 += 32) {   // long coarse row: every lane walks all products and keeps its own column(s)
+        const int t = t0 + lane;
+        const int myJ = t < len ? c_col[cbase + 32 * t] : -1;
+        double acc = 0.0;
+        for (int q = q0; q < q1; ++q) {
+          const int2 re = Rent[q];
+          const double r = (double)__int_as_float(re.y);
+          const int e1 = APptr[re.x + 1];
+          for (int e = APptr[re.x]; e < e1; ++e)
+            if (APcol[e] == myJ) acc += r * APval[e];
+        }
+        if (t < len) {
+          c_val[cbase + 32 * t] = acc;
+          if (myJ == I) c_dinv[I] = 1.0 / acc;
+        }
+      }
+    }
+  }
+}
+
 // Dense inverse of the coarsest operator: in-place Gauss-Jordan without pivoting (the operator is SPD), one CTA.
 // IN_SHARED: the n x n matrix lives in dynamic shared memory (n <= kAmgDenseShared) and is written out at the end;
 // otherwise it is eliminated in global memory (fallback for hierarchies whose coarsening stalled early).
@@ -514,7 +614,7 @@ void amg_free(Context* ctx) {
     AmgLevelDev& L = A->lv[l];
     if (L.owns) { amg_release(L.slice_ptr); amg_release(L.col); amg_release(L.rowptr); }
     amg_release(L.val); amg_release(L.dinv); amg_release(L.val32);
-    amg_release(L.Pptr); amg_release(L.Pent);
+    amg_release(L.Pptr); amg_release(L.Pent); amg_release(L.APptr); amg_release(L.APcol); amg_release(L.APval);
     amg_release(L.Rptr); amg_release(L.Rent);
     if (l > 0) { amg_release(L.b); amg_release(L.x2); }
     amg_release(L.x); amg_release(L.t);
@@ -786,6 +886,24 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_amg_change(int nrows, int nsli
 }
 
 void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv) {
+  if (F.APptr) {   // two-stage product
+    k_amg_ap<<<(F.n + 127) / 128, 128, 0, ctx->stream>>>(F.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.APptr, F.APcol, F.APval);
+    if (C.wmax <= 16) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 6));
+      k_amg_rap_ap<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.Rptr, F.Rent, F.APptr, F.APcol, F.APval, C.rowptr, C.slice_ptr, C.col, out_val,
+                                                         out_dinv);
+    } else if (C.wmax <= 32) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 3) / 4, (int64_t)ctx->num_sms * 6));
+      k_amg_rap_ap<32, 4><<<grid, 128, 0, ctx->stream>>>(C.n, F.Rptr, F.Rent, F.APptr, F.APcol, F.APval, C.rowptr, C.slice_ptr, C.col, out_val,
+                                                         out_dinv);
+    } else {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 1) / 2, (int64_t)ctx->num_sms * 6));
+      k_amg_rap_ap<64, 2><<<grid, 64, 0, ctx->stream>>>(C.n, F.Rptr, F.Rent, F.APptr, F.APcol, F.APval, C.rowptr, C.slice_ptr, C.col, out_val,
+                                                        out_dinv);
+    }
+    ctx->stats.kernel_launches += 2;
+    return;
+  }
   if (C.wmax <= 16) {   // short coarse rows: small private tables, more resident warps per SM
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 5));
     k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,

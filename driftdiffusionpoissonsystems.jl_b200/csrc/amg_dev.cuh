@@ -29,6 +29,11 @@ struct AmgLevelDev {
   // rounded to fp32 at setup (P, R = P^T and the Galerkin products all use the same rounded numbers)
   int *Pptr = nullptr, *Rptr = nullptr;
   int2 *Pent = nullptr, *Rent = nullptr;
+  // two-stage Galerkin product (device-built levels): pattern of A*P row by row (sorted distinct coarse columns; rows with
+  // an empty prolongator row are left out, nothing reads them) and the value workspace stage 1 fills for stage 2
+  int *APptr = nullptr, *APcol = nullptr;
+  double* APval = nullptr;
+  int64_t nAP = 0;
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
 };
 

@@ -144,6 +144,45 @@ __global__ void k_prolongator(int n, const int* __restrict__ rowptr, const int* 
   }
 }
 
+// Pattern of row i of A*P: the sorted distinct coarse columns reachable through the (structural) entries of row i.
+// Rows whose prolongator row is empty belong to no restriction row, so their A*P row is never read: left empty.
+template <bool FILL>
+__global__ void k_ap_pattern(int n, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                             const int* __restrict__ Pptr, const int2* __restrict__ Pent, int* __restrict__ cnt,
+                             const int* __restrict__ APptr, int* __restrict__ APcol, int* __restrict__ overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int seen[kMaxLocalRow];
+  int c = 0;
+  if (Pptr[i + 1] > Pptr[i]) {
+    const int len = rowptr[i + 1] - rowptr[i];
+    const int base = slice_ptr[i >> 5] + (i & 31);
+    for (int k = 0; k < len; ++k) {
+      const int j = col[base + 32 * k];
+      for (int m = Pptr[j]; m < Pptr[j + 1]; ++m) {
+        const int J = Pent[m].x;
+        int p = 0;
+        while (p < c && seen[p] != J) ++p;
+        if (p == c) {
+          if (c == kMaxLocalRow) { *overflow = 1; break; }
+          seen[c++] = J;
+        }
+      }
+    }
+  }
+  if (!FILL) cnt[i] = c;
+  else {
+    for (int p = 1; p < c; ++p) {   // ascending columns
+      const int J = seen[p];
+      int q = p - 1;
+      while (q >= 0 && seen[q] > J) { seen[q + 1] = seen[q]; --q; }
+      seen[q + 1] = J;
+    }
+    const int o = APptr[i];
+    for (int p = 0; p < c; ++p) APcol[o + p] = seen[p];
+  }
+}
+
 // entry (fine row i, slot m of P) -> 64-bit value {row, float bits} laid out like an int2 {x = row, y = bits}
 __global__ void k_transpose_values(int n, const int* __restrict__ Pptr, const int2* __restrict__ Pent,
                                    unsigned long long* __restrict__ out) {
@@ -236,8 +275,9 @@ __global__ void k_sell_fill(const int* __restrict__ rowptr, const int* __restric
 }
 
 void amg_release_transfers(AmgLevelDev& F) {
-  cudaFree(F.Pptr); cudaFree(F.Pent); cudaFree(F.Rptr); cudaFree(F.Rent);
-  F.Pptr = F.Rptr = nullptr;
+  cudaFree(F.Pptr); cudaFree(F.Pent); cudaFree(F.Rptr); cudaFree(F.Rent); cudaFree(F.APptr); cudaFree(F.APcol); cudaFree(F.APval);
+  F.Pptr = F.Rptr = F.APptr = F.APcol = nullptr;
+  F.APval = nullptr;
   F.Pent = F.Rent = nullptr;
   F.nc = 0;
 }
@@ -360,6 +400,30 @@ int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, c
     DDPS_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, d_pkey, d_rkey, d_pv, (unsigned long long*)Rent, nP, 0, bits_for(nc), st));
   }
   k_lower_bound_sorted<int><<<(nc + 1 + T - 1) / T, T, 0, st>>>(d_rkey, nP, nc + 1, 0, Rptr);
+
+  // ---- 4b. pattern of A*P for the two-stage Galerkin product (skipped when a row is too long: one-stage kernel) ----
+  {
+    int* d_ovf2;
+    DDPS_CUDA(tmp.alloc(&d_ovf2, 4));
+    DDPS_CUDA(cudaMemsetAsync(d_ovf2, 0, sizeof(int), st));
+    DDPS_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)n + 1) * sizeof(int), st));
+    k_ap_pattern<false><<<(n + T - 1) / T, T, 0, st>>>(n, F.rowptr, F.slice_ptr, F.col, Pptr, Pent, d_cnt, nullptr, nullptr, d_ovf2);
+    DDPS_CUDA(cudaMalloc(&F.APptr, ((size_t)n + 1) * sizeof(int)));
+    if ((rc = scan_exclusive(ctx, tmp, d_cnt, F.APptr, n + 1))) return rc;
+    int nAP = 0, ovf2 = 0;
+    DDPS_CUDA(cudaMemcpyAsync(&nAP, F.APptr + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DDPS_CUDA(cudaMemcpyAsync(&ovf2, d_ovf2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DDPS_CUDA(cudaStreamSynchronize(st));
+    if (ovf2 || getenv("DDPS_AMG_ONE_STAGE")) {
+      cudaFree(F.APptr);
+      F.APptr = nullptr;
+    } else {
+      F.nAP = nAP;
+      DDPS_CUDA(cudaMalloc(&F.APcol, std::max<size_t>(nAP, 1) * sizeof(int)));
+      DDPS_CUDA(cudaMalloc(&F.APval, std::max<size_t>(nAP, 1) * sizeof(double)));
+      k_ap_pattern<true><<<(n + T - 1) / T, T, 0, st>>>(n, F.rowptr, F.slice_ptr, F.col, Pptr, Pent, nullptr, F.APptr, F.APcol, d_ovf2);
+    }
+  }
 
   if (timing) DDPS_CUDA(cudaStreamSynchronize(st));
   const double t3 = now();
