@@ -623,8 +623,9 @@ void amg_free(Context* ctx) {
   amg_release(A->z);
   for (int k = 0; k < kAmgKinds; ++k) {
     AmgOpSet& S = A->sets[k];
-    amg_release(S.snap); amg_release(S.dense);
-    for (int l = 0; l < kAmgMaxLevels; ++l) { amg_release(S.val[l]); amg_release(S.dinv[l]); amg_release(S.val32[l]); }
+    auto rel = [&](auto*& p) { if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; } };
+    rel(S.snap); rel(S.dense);
+    for (int l = 0; l < kAmgMaxLevels; ++l) { rel(S.val[l]); rel(S.dinv[l]); rel(S.val32[l]); }
   }
   delete A;
   ctx->amg = nullptr;
@@ -920,18 +921,27 @@ void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, con
   ctx->stats.kernel_launches++;
 }
 
+// The per-kind copies come from the stream-ordered pool (only the library stream touches them): when lagging is armed, a
+// few outer iterations into the solve, the pool still holds the setup's freed temporaries, so nothing new is mapped (a
+// legacy cudaMalloc of these ~3 GB was measured at 0.3 s inside one Gummel iteration).
+template <typename T>
+static int amg_alloc_pooled(Context* ctx, T** p, size_t n) {
+  DDPS_CUDA(cudaMallocAsync((void**)p, std::max<size_t>(n, 1) * sizeof(T), ctx->stream));
+  return 0;
+}
+
 static int amg_alloc_set(Context* ctx, Amg& A, AmgOpSet& S) {
   int rc;
-  if ((rc = amg_alloc(ctx, &S.snap, (size_t)A.lv[0].nentries))) return rc;
+  if ((rc = amg_alloc_pooled(ctx, &S.snap, (size_t)A.lv[0].nentries))) return rc;
   for (int l = 1; l < A.nlev; ++l) {
     const AmgLevelDev& L = A.lv[l];
-    if ((rc = amg_alloc(ctx, &S.val[l], (size_t)L.nentries)) || (rc = amg_alloc(ctx, &S.dinv[l], (size_t)L.n))) return rc;
+    if ((rc = amg_alloc_pooled(ctx, &S.val[l], (size_t)L.nentries)) || (rc = amg_alloc_pooled(ctx, &S.dinv[l], (size_t)L.n))) return rc;
     DDPS_CUDA(cudaMemsetAsync(S.val[l], 0, std::max<size_t>((size_t)L.nentries, 1) * sizeof(double), ctx->stream));   // SELL padding stays 0
     DDPS_CUDA(cudaMemsetAsync(S.dinv[l], 0, std::max<size_t>((size_t)L.n, 1) * sizeof(double), ctx->stream));
-    if (L.val32 && (rc = amg_alloc(ctx, &S.val32[l], (size_t)L.nentries))) return rc;
+    if (L.val32 && (rc = amg_alloc_pooled(ctx, &S.val32[l], (size_t)L.nentries))) return rc;
   }
   const int nL = A.lv[A.nlev - 1].n;
-  if ((rc = amg_alloc(ctx, &S.dense, (size_t)nL * nL))) return rc;
+  if ((rc = amg_alloc_pooled(ctx, &S.dense, (size_t)nL * nL))) return rc;
   S.allocated = true;
   return 0;
 }
