@@ -953,9 +953,7 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind) {
   int rc;
   A.lv[0].cur_val = val;
   A.lv[0].cur_dinv = dinv;
-  // (not before the outer iteration has settled: the operators of the first outer iterations differ by far more than the
-  // tolerance, their snapshots and per-kind copies would only cost memory and allocation time)
-  const bool lag = kind >= 0 && kind < kAmgKinds && !ctx->opts.amg_no_lag && ctx->amg_lag_armed;
+  const bool lag = kind >= 0 && kind < kAmgKinds && !ctx->opts.amg_no_lag;
   AmgOpSet* S = lag ? &A.sets[kind] : nullptr;
   if (S && !S->allocated && (rc = amg_alloc_set(ctx, A, *S))) return rc;
   bool reuse = false;

@@ -447,9 +447,7 @@ int gummel_step(Context* ctx, double* control) {
   if ((rc = vsolve(ctx))) return rc;                   // src:597
   if ((rc = uvsolve(ctx, DDPS_FIELD_U))) return rc;    // src:598
   if ((rc = uvsolve(ctx, DDPS_FIELD_W))) return rc;    // src:599 (uses the OLD u0)
-  rc = launch_max_abs_diff3(ctx, ctx->U, ctx->U0, ctx->W, ctx->W0, ctx->V, ctx->V0, ctx->n_own, control);
-  if (!rc) ctx->amg_lag_armed = (*control <= 0.05);
-  return rc;
+  return launch_max_abs_diff3(ctx, ctx->U, ctx->U0, ctx->W, ctx->W0, ctx->V, ctx->V0, ctx->n_own, control);
 }
 
 void reset_stats(Context* ctx) {
@@ -900,7 +898,6 @@ int ddps_ddpe_begin(ddps_ctx* ctx, int rec_mode, double delta, double tau_p, dou
     return rc;
   ctx->rec_mode = rec_mode; ctx->delta = delta; ctx->tau_p = tau_p; ctx->tau_n = tau_n; ctx->tol = tol;
   reset_stats(ctx);
-  ctx->amg_lag_armed = false;
   if ((rc = assemble_base(ctx, false))) return rc;                              // src:643, once per solve
   {
     const double ta = now_ms();
@@ -984,7 +981,6 @@ int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats
   int rc;
   if ((rc = require_mesh(ctx))) return rc;
   reset_stats(ctx);
-  ctx->amg_lag_armed = false;
   ctx->ddpe_active = false;
   double t0 = now_ms();
   if ((rc = assemble_base(ctx, true))) return rc;                                            // src:924-1028
@@ -1005,7 +1001,6 @@ int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats
     ctx->stats.t_asm_ms += ta.ms();
     ctx->hist_outer.push_back(res);
     ctx->stats.control = res;
-    ctx->amg_lag_armed = (res <= 0.05);
     if (count > 0 && ctx->opts.verbose) printf("iteration %d, tolerance: %.17g\n", count, res);   // src:1093
     if (!(res > tol)) break;                                                                  // src:1040
     if (count >= cap) { ctx->fail(DDPS_ERR_NOCONV, "semlin: Newton iteration cap reached"); rc = DDPS_ERR_NOCONV; break; }

@@ -220,7 +220,6 @@ struct Context {
   // optional multigrid preconditioner (opts.precond == DDPS_PRECOND_AMG, single GPU)
   Amg* amg = nullptr;
   int amg_kind = -1;   // which kind of operator the next solve_system call handles (amg_numeric: lagged coarse operators)
-  bool amg_lag_armed = false;   // the outer iteration has settled enough (last update norm / Newton residual <= 0.05) for lagging to pay
 
   void fail(int code, const std::string& msg) {
     err_code = code;
