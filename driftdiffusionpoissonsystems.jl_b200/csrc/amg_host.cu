@@ -102,6 +102,9 @@ void strong_lists(const AmgHostLevel& L, const unsigned char* fixed, double thet
 // neighbours; leftovers join their strongest aggregated neighbour or stay alone.
 int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::vector<int>& agg,
                         const std::atomic<long long>* rows_ready) {
+  const bool timing = getenv("DDPS_AMG_TIMING") != nullptr && n > 1000000;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double ta = now();
   agg.assign(n, -1);
   int nc = 0;
   auto wait_all = [&]() {
@@ -172,23 +175,27 @@ int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::v
     });
   }
   nc = cbase[nchunks];
-  // pass 2 (no chaining: decisions use the pass-1 state only)
-  std::vector<int> join(n, -1);
+  const double tb = now();
+  // pass 2 (no chaining: decisions use the pass-1 state only).  In place: a leftover row stores its choice as -2 - aggregate,
+  // which readers still see as "not aggregated in pass 1" (negative); a second sweep decodes.  Reads the pass-1 state only,
+  // so the result does not depend on the number of threads.
   {
-    // (reads the pass-1 state only: the result does not depend on the number of threads)
     const int nt = n < 200000 ? 1 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     parallel_ranges(n, nt, [&](int, int64_t lo, int64_t hi) {
       for (int64_t i = lo; i < hi; ++i) {
         if (agg[i] >= 0) continue;
-        for (int k = sptr[i]; k < sptr[i + 1]; ++k)
-          if (agg[scol[k]] >= 0) { join[i] = agg[scol[k]]; break; }
+        for (int k = sptr[i]; k < sptr[i + 1]; ++k) {
+          const int a = agg[scol[k]];
+          if (a >= 0) { agg[i] = -2 - a; break; }
+        }
       }
     });
     parallel_ranges(n, nt, [&](int, int64_t lo, int64_t hi) {
       for (int64_t i = lo; i < hi; ++i)
-        if (agg[i] < 0 && join[i] >= 0) agg[i] = join[i];
+        if (agg[i] < -1) agg[i] = -2 - agg[i];
     });
   }
+  const double tc = now();
   // pass 3
   for (int i = 0; i < n; ++i) {
     if (agg[i] >= 0 || sptr[i + 1] == sptr[i]) continue;   // isolated row (diagonally dominant): smoother only
@@ -197,6 +204,7 @@ int amg_aggregate_lists(int n, const int* sptr, const int* scol, int cap, std::v
       if (agg[scol[k]] < 0) agg[scol[k]] = nc;
     ++nc;
   }
+  if (timing) fprintf(stderr, "[ddps amg]     aggregation n=%d: pass 1 %.1f ms, pass 2 %.1f, pass 3 %.1f\n", n, tb - ta, tc - tb, now() - tc);
   return nc;
 }
 
