@@ -107,3 +107,31 @@ def test_thread_count_does_not_change_the_hierarchy(D, O):
     for la, lc in zip(a, c):
         for k in la:
             assert np.array_equal(la[k], lc[k]), k
+
+
+def test_prolongator_preserves_constants_and_gentle_last_levels(D, O):
+    """Interior rows of the un-eliminated part of a stiffness matrix have zero row sums, so P must interpolate the constant
+    exactly there (partition of unity, up to the fp32 rounding of the stored entries); and the last, tiny levels are
+    coarsened gently (aggregates of <= 3 rows, ratio ~3 instead of ~7) so that the coarsest operator stays small without
+    costing CG iterations."""
+    mesh, pr = _mesh_and_problem(D, O, "S")
+    MV, A, b, fixed = _systems(D, O, mesh, pr)
+    levels = D.amg.host_hierarchy(MV.indptr, MV.indices, MV.data, fixed, coarse_max=12)
+    mats = amg_ref.hierarchy_matrices(levels)
+    A0, P0 = mats[0]
+    rowsum = np.abs(np.asarray(A0.sum(axis=1)).ravel())
+    touches_fixed = np.asarray((abs(A0) @ fixed.astype(float))).ravel() > 0
+    agg = levels[0]["agg"]
+    nb_unagg = np.asarray((abs(A0) @ (agg < 0).astype(float))).ravel() > 0
+    interior = (~fixed) & (~touches_fixed) & (~nb_unagg) & (rowsum < 1e-12)
+    assert interior.sum() > 0.8 * (~fixed).sum()
+    ones = np.asarray(P0.sum(axis=1)).ravel()
+    assert np.max(np.abs(ones[interior] - 1.0)) <= 5e-7
+    # gentle coarsening below 512 rows: aggregates of at most 3 rows
+    small = [lev for lev in levels if lev["nc"] and lev["n"] <= 512]
+    assert small, [lev["n"] for lev in levels]
+    for lev in small:
+        sizes = np.bincount(lev["agg"][lev["agg"] >= 0], minlength=lev["nc"])
+        assert sizes.max() <= 3 + 2 and lev["nc"] >= lev["n"] // 4      # root + 2, plus leftovers that joined
+    big = [lev for lev in levels if lev["nc"] and lev["n"] > 512]
+    assert all(lev["nc"] <= lev["n"] // 4 for lev in big)
