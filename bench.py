@@ -179,58 +179,64 @@ def main():
     pr = problem()
     mesh = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
     smp = D.api.sample_ddpe(mesh, pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
-    # end to end through the C ABI with host buffers: mesh + coefficient uploads, setup, K steps, D2H of V,u,v
-    e2e = None
-    if not args.no_e2e:
-        # (measured FIRST, in the fresh process: this is the cold start a user sees; a session created after ~10 GB of
-        # cudaFree runs into a slow and erratic legacy allocation path, which would be timed as "setup")
-        # host buffers in the ABI's layout (= the memory layout of the reference's Julia arrays: nodes 2 x nq and elements
-        # 5 x nme column-major), pinned; the Mesh handed to the library is a zero-copy view of them
-        nodes = torch.from_numpy(np.ascontiguousarray(mesh.nodes.T)).pin_memory().numpy()
-        elems = torch.from_numpy(np.ascontiguousarray(mesh.elements.T)).pin_memory().numpy()
-        mesh_p = D.Mesh(nodes.T, mesh.edges, elems.T)
-        pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in smp.items()}
-        h2d = nodes.nbytes + elems.nbytes + sum(pinned[k].nbytes for k in ("lambda2", "mu_p", "mu_n", "C_mid")) + 3 * 16 * len(smp["n"])
-        d2h = 3 * 8 * mesh.nq
-        outs = tuple(torch.empty(mesh.nq, dtype=torch.float64).pin_memory().numpy() for _ in range(3))   # caller-owned outputs
-        if comm is None:
-            # one-time process initialisation is not part of the measurement: a tiny solve loads the library's kernels
-            # (lazy module loading) and creates the memory pool before the timed cold start of the real workload
-            mt = D.structured_mesh(64, 32, 0.0, 2.0, 0.0, 1.0)
-            with D.Session(local, **sopts) as sw:
-                sw.set_mesh(mt)
-                sw.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
-                sw.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
-                sw.ddpe_step(1)
-                sw.ddpe_fetch()
-        barrier()
-        t0 = time.perf_counter()
-        s2 = D.Session(local, comm=comm, **sopts) if comm is None else None
-        if s2 is None:   # multi-GPU: a communicator cannot be re-created from the same id; reuse a fresh one
-            ident2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                buf = (__import__("ctypes").c_char * 128)()
-                _lib.load().ddps_comm_unique_id(buf)
-                ident2 = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
-            dist.broadcast(ident2, 0)
-            s2 = D.Session(local, comm=(bytes(ident2.cpu().numpy().tobytes()), rank, world))
-        s2.set_mesh(mesh_p)
-        s2.upload_ddpe(pinned)
-        s2.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
-        s2.ddpe_step(args.steps)
-        s2.ddpe_fetch(out=outs)
-        barrier()
-        t_e2e = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        e2e = {"value": args.steps / t_e2e, "unit": "1/s", "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e,
-               "note": "cold start: mesh+coefficient H2D from pinned host buffers, pattern build"
-                       + (", multigrid hierarchy setup (device, greedy aggregation on the host)" if precond == "amg" else "") + ", first K Gummel iterations, D2H of V,u,v",
-               "setup_seconds": s2.stats()["t_setup_ms"] / 1000.0 + s2.stats()["t_amg_setup_ms"] / 1000.0}
-        s2.close()
+    def measure_e2e():
+        # end to end through the C ABI with host buffers: mesh + coefficient uploads, setup, K steps, D2H of V,u,v
+        e2e = None
+        if not args.no_e2e:
+            # (measured FIRST, in the fresh process: this is the cold start a user sees; a session created after ~10 GB of
+            # cudaFree runs into a slow and erratic legacy allocation path, which would be timed as "setup")
+            # host buffers in the ABI's layout (= the memory layout of the reference's Julia arrays: nodes 2 x nq and elements
+            # 5 x nme column-major), pinned; the Mesh handed to the library is a zero-copy view of them
+            nodes = torch.from_numpy(np.ascontiguousarray(mesh.nodes.T)).pin_memory().numpy()
+            elems = torch.from_numpy(np.ascontiguousarray(mesh.elements.T)).pin_memory().numpy()
+            mesh_p = D.Mesh(nodes.T, mesh.edges, elems.T)
+            pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in smp.items()}
+            h2d = nodes.nbytes + elems.nbytes + sum(pinned[k].nbytes for k in ("lambda2", "mu_p", "mu_n", "C_mid")) + 3 * 16 * len(smp["n"])
+            d2h = 3 * 8 * mesh.nq
+            outs = tuple(torch.empty(mesh.nq, dtype=torch.float64).pin_memory().numpy() for _ in range(3))   # caller-owned outputs
+            if comm is None:
+                # one-time process initialisation is not part of the measurement: a tiny solve loads the library's kernels
+                # (lazy module loading) and creates the memory pool before the timed cold start of the real workload
+                mt = D.structured_mesh(64, 32, 0.0, 2.0, 0.0, 1.0)
+                with D.Session(local, **sopts) as sw:
+                    sw.set_mesh(mt)
+                    sw.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
+                    sw.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+                    sw.ddpe_step(1)
+                    sw.ddpe_fetch()
+            barrier()
+            t0 = time.perf_counter()
+            s2 = D.Session(local, comm=comm, **sopts) if comm is None else None
+            if s2 is None:   # multi-GPU: a communicator cannot be re-created from the same id; reuse a fresh one
+                ident2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    buf = (__import__("ctypes").c_char * 128)()
+                    _lib.load().ddps_comm_unique_id(buf)
+                    ident2 = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+                dist.broadcast(ident2, 0)
+                s2 = D.Session(local, comm=(bytes(ident2.cpu().numpy().tobytes()), rank, world))
+            s2.set_mesh(mesh_p)
+            s2.upload_ddpe(pinned)
+            s2.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+            s2.ddpe_step(args.steps)
+            s2.ddpe_fetch(out=outs)
+            barrier()
+            t_e2e = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_e2e = float(t.item())
+            e2e = {"value": args.steps / t_e2e, "unit": "1/s", "h2d_bytes_per_step": h2d / args.steps,
+                   "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e,
+                   "note": "cold start: mesh+coefficient H2D from pinned host buffers, pattern build"
+                           + (", multigrid hierarchy setup (device, greedy aggregation on the host)" if precond == "amg" else "") + ", first K Gummel iterations, D2H of V,u,v",
+                   "setup_seconds": s2.stats()["t_setup_ms"] / 1000.0 + s2.stats()["t_amg_setup_ms"] / 1000.0}
+            s2.close()
+        return e2e
+
+    # single GPU: the cold start is measured FIRST, in the fresh process; with a communicator the validated order is kept
+    # (resident session first, then the end-to-end session with a second communicator)
+    e2e = measure_e2e() if comm is None else None
 
     s = D.Session(local, comm=comm, **sopts)
     if args.pcg_cap > 0:
@@ -286,6 +292,8 @@ def main():
                            "fine_spmv_share_of_iteration": 3 * ms_spmv / ms_it,
                            "t_hierarchy_setup_ms": st1["t_amg_setup_ms"]}
 
+    if comm is not None:
+        e2e = measure_e2e()
     s.close()
 
     cpu = None
