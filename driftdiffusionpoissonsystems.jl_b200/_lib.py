@@ -25,7 +25,8 @@ class SolverOpts(C.Structure):
     _fields_ = [("lin_rtol", C.c_double), ("newton_eta", C.c_double), ("lin_max_it", C.c_int64),
                 ("max_newton", C.c_int32), ("max_gummel", C.c_int32), ("check_every", C.c_int32),
                 ("warm_start", C.c_int32), ("verbose", C.c_int32), ("lin_cap_ok", C.c_int32), ("no_alt_traversal", C.c_int32), ("warm_start_v", C.c_int32),
-                ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("precond", C.c_int32), ("amg_no_lag", C.c_int32)]
+                ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("precond", C.c_int32), ("amg_no_lag", C.c_int32),
+                ("newton_damping", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -34,7 +35,7 @@ class Stats(C.Structure):
                 ("t_setup_ms", C.c_double), ("t_solve_ms", C.c_double), ("t_asm_ms", C.c_double),
                 ("t_pcg_ms", C.c_double), ("t_wall_ms", C.c_double), ("status", C.c_int32), ("n_negative_area", C.c_int32),
                 ("amg_levels", C.c_int32), ("amg_reuses", C.c_int32), ("t_amg_setup_ms", C.c_double),
-                ("reserved", C.c_int32 * 4)]
+                ("newton_halvings", C.c_int32), ("reserved", C.c_int32 * 3)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
@@ -57,6 +58,7 @@ SIGNATURES = {
     "ddps_dirichlet_set": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_double_p, C.c_int64]),
     "ddps_coeff_set": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int64]),
     "ddps_functor_set": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int]),
+    "ddps_coeff_functor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int]),
     "ddps_ddpe_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
     "ddps_ddpe_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.POINTER(C.c_int)]),
     "ddps_ddpe_fetch": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
@@ -68,6 +70,7 @@ SIGNATURES = {
     "ddps_get_csr_size": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),
     "ddps_get_csr": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_int64_p, c_double_p]),
     "ddps_get_vector": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int64]),
+    "ddps_get_coeff": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int64, c_int64_p]),
     "ddps_debug_assemble_base": (C.c_int, [C.c_void_p, C.c_int]),
     "ddps_debug_assemble_newton": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_double_p, c_double_p, c_double_p,
                                              c_double_p]),

@@ -20,7 +20,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .functors import FUNCTOR_POLY, FUNCTOR_SINH, PolyRHS, SinhRHS
+from .functors import FUNCTOR_POLY, FUNCTOR_SINH, PolyRHS, SinhRHS, SpatialFunctor
 from .mesh import Mesh
 
 FIELD_V, FIELD_U, FIELD_W, FIELD_SCALAR = 0, 1, 2, 3
@@ -40,10 +40,32 @@ class DDPSError(RuntimeError):
 # --------------------------------------------------------------------------------------------
 # host-side boundary preprocessing (src:162-218 and its inline copies src:532-544, 965-1013)
 # --------------------------------------------------------------------------------------------
+_SAMPLE_THREADS = max(1, min(16, (__import__("os").cpu_count() or 1)))
+_SAMPLE_CHUNK = 1 << 20
+
+
 def _sample2(fn, x, y):
-    """Evaluate a scalar closure (x,y)->value on arrays (Julia's ``map``/dot call)."""
+    """Evaluate a scalar closure (x,y)->value on arrays (Julia's ``map``/dot call).  Large arrays are cut into chunks
+    that a thread pool evaluates concurrently (vectorised closures spend their time in numpy ufuncs, which release the
+    GIL): the one-time host sampling of arbitrary closures uses all host cores."""
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
+    if x.size >= 4 * _SAMPLE_CHUNK and _SAMPLE_THREADS > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        xf, yf = x.reshape(-1), y.reshape(-1)
+        out = np.empty(xf.size)
+        cuts = list(range(0, xf.size, _SAMPLE_CHUNK))
+
+        def work(o):
+            out[o:o + _SAMPLE_CHUNK] = _sample2_serial(fn, xf[o:o + _SAMPLE_CHUNK], yf[o:o + _SAMPLE_CHUNK])
+
+        with ThreadPoolExecutor(_SAMPLE_THREADS) as ex:
+            list(ex.map(work, cuts))
+        return out.reshape(x.shape)
+    return _sample2_serial(fn, x, y)
+
+
+def _sample2_serial(fn, x, y):
     try:
         out = np.asarray(fn(x, y), dtype=np.float64)
         if out.shape == x.shape:
@@ -135,20 +157,31 @@ def _midpoints(mesh: Mesh):
     return mx, my
 
 
-def sample_ddpe(mesh: Mesh, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun):
+def sample_ddpe(mesh: Mesh, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun, device_functors=False):
     """One-time host setup of solve_ddpe: evaluate the spatial closures where the reference
-    evaluates them (boundary nodes, centroids, edge midpoints) and return plain arrays."""
+    evaluates them (boundary nodes, centroids, edge midpoints) and return plain arrays.
+    ``device_functors``: coefficient closures that are registered spatial functors (functors.SpatialFunctor) are NOT
+    sampled here; the entry holds the functor itself and ``Session.upload_ddpe`` lets the library sample it on the device."""
     _, _, gD, n = aquire_boundary(mesh, Vbddata)                             # src:640
     nu, gDu = dirichlet_nodes(mesh, ubddata)                                 # src:532-544
     nv, gDv = dirichlet_nodes(mesh, vbddata)
     if len(gDu) != len(n) or len(gDv) != len(n):
         raise ValueError("DimensionMismatch: the u/v bddata must mark the same segments 'D' as the V bddata (src:563)")
-    cx, cy = _centroids(mesh)
-    mx, my = _midpoints(mesh)
-    return dict(n=n, gD_V=gD, gD_u=gDu, gD_v=gDv,
-                lambda2=_sample2(lam, cx, cy) ** 2,                          # src:254
-                mu_p=_sample2(mu_p, cx, cy), mu_n=_sample2(mu_n, cx, cy),    # src:467
-                C_mid=np.ascontiguousarray(_sample2(Cfun, mx, my)))          # src:341-343
+    fns = dict(lambda2=lam, mu_p=mu_p, mu_n=mu_n, C_mid=Cfun)
+    host = {k: f for k, f in fns.items() if not (device_functors and isinstance(f, SpatialFunctor))}
+    out = dict(n=n, gD_V=gD, gD_u=gDu, gD_v=gDv)
+    out.update({k: f for k, f in fns.items() if k not in host})
+    if any(k in host for k in ("lambda2", "mu_p", "mu_n")):
+        cx, cy = _centroids(mesh)
+        if "lambda2" in host:
+            out["lambda2"] = _sample2(lam, cx, cy) ** 2                      # src:254
+        for k in ("mu_p", "mu_n"):
+            if k in host:
+                out[k] = _sample2(host[k], cx, cy)                           # src:467
+    if "C_mid" in host:
+        mx, my = _midpoints(mesh)
+        out["C_mid"] = np.ascontiguousarray(_sample2(Cfun, mx, my))          # src:341-343
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -222,13 +255,24 @@ class Session:
         arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
         self._check(self.lib.ddps_coeff_set(self.h, slot, _lib.dptr(arr), arr.size))
 
+    def set_coeff_functor(self, slot, fn: SpatialFunctor):
+        """Let the library sample a registered spatial functor on the device (no host sampling, no upload)."""
+        p = np.ascontiguousarray(fn.params(), dtype=np.float64)
+        self._check(self.lib.ddps_coeff_functor(self.h, slot, int(fn.kind), _lib.dptr(p), p.size))
+
+    def set_coeff_any(self, slot, arr_or_functor):
+        if isinstance(arr_or_functor, SpatialFunctor):
+            self.set_coeff_functor(slot, arr_or_functor)
+        else:
+            self.set_coeff(slot, arr_or_functor)
+
     def set_functor(self, kind, params):
         p = np.ascontiguousarray(params, dtype=np.float64)
         self._check(self.lib.ddps_functor_set(self.h, kind, _lib.dptr(p), p.size))
 
     # -- problem setup (host sampling of the spatial closures) --
-    def setup_ddpe(self, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun):
-        self.upload_ddpe(sample_ddpe(self.mesh, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun))
+    def setup_ddpe(self, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun, device_functors=True):
+        self.upload_ddpe(sample_ddpe(self.mesh, Vbddata, ubddata, vbddata, lam, mu_p, mu_n, Cfun, device_functors))
 
     def upload_ddpe(self, smp):
         """Hand the sampled arrays of ``sample_ddpe`` to the library (host buffers -> HBM)."""
@@ -236,10 +280,10 @@ class Session:
         self.set_dirichlet(FIELD_V, smp["n"], smp["gD_V"])
         self.set_dirichlet(FIELD_U, smp["n"], smp["gD_u"])
         self.set_dirichlet(FIELD_W, smp["n"], smp["gD_v"])
-        self.set_coeff(COEFF_LAMBDA2, smp["lambda2"])
-        self.set_coeff(COEFF_MU_P, smp["mu_p"])
-        self.set_coeff(COEFF_MU_N, smp["mu_n"])
-        self.set_coeff(COEFF_C_MID, smp["C_mid"])
+        self.set_coeff_any(COEFF_LAMBDA2, smp["lambda2"])   # arrays sampled on the host, or registered spatial functors
+        self.set_coeff_any(COEFF_MU_P, smp["mu_p"])         # (sampled by the library on the device)
+        self.set_coeff_any(COEFF_MU_N, smp["mu_n"])
+        self.set_coeff_any(COEFF_C_MID, smp["C_mid"])
         self._ddpe_n = smp["n"]
 
     def ddpe_begin(self, rec_mode, delta, tau_p, tau_n, tol):
@@ -341,6 +385,13 @@ class Session:
         self._check(self.lib.ddps_get_csr_size(self.h, C.byref(nr), None))
         out = np.zeros(nr.value)
         self._check(self.lib.ddps_get_vector(self.h, which, _lib.dptr(out), out.size))
+        return out
+
+    def get_coeff(self, slot):
+        n = C.c_int64(0)
+        self._check(self.lib.ddps_get_coeff(self.h, int(slot), None, 0, C.byref(n)))
+        out = np.zeros(n.value)
+        self._check(self.lib.ddps_get_coeff(self.h, int(slot), _lib.dptr(out), out.size, C.byref(n)))
         return out
 
     def debug_assemble_base(self, semlin=False):

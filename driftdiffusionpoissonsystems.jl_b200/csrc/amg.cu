@@ -539,6 +539,7 @@ __global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int
   scal->breakdown = 0;
   if (warm) scal->done = (scal->rr == 0.0) ? 1 : 0;
   else scal->done = (scal->rr <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
+  scal->conv = scal->done;   // every stop rule met (an exhausted iteration cap leaves it 0 -> DDPS_ERR_NOCONV)
 }
 
 // x += alpha p; r -= alpha q; the block that finishes last takes the convergence decision, so that the cycle
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, in
       // rz = r.Br of the residual BEFORE this update bounds the energy of the error after it (CG decreases it)
       const bool small_r = tot[0] <= scal->thresh2 || tot[1] <= scal->thresh_inf;
       const bool small_e = !scal->warm || rz <= scal->thresh_e;
+      if (small_r && small_e) scal->conv = 1;
       if ((small_r && small_e) || it + 1 >= max_it || !(tot[0] == tot[0])) scal->done = 1;
     }
   }
@@ -1078,6 +1080,72 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
 
 int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz) { return amg_vcycle_impl(ctx, r, z, dot_rz, false); }
 
+// Single kernels of the multigrid-preconditioned CG iteration, launched alone for ddps_time_kernel (ids 9..13), with the
+// ALGORITHMIC bytes of one launch (every input array read once, every output written once; the cycle's matrix values in
+// the width it stores them: fp32 on the large levels):
+//   9  finest-level residual t = b - A x          (k_amg_spmv<1,false,VT>)
+//   10 finest-level smoothing sweep + r.z         (k_amg_spmv<2,true,VT>)
+//   11 CG update x,r + first sweep                (k_apcg_update)
+//   12 restriction 0 -> 1 + coarse first sweep    (k_amg_restrict)
+//   13 prolongation 1 -> 0                        (k_amg_prolong)
+int amg_time_launch(Context* ctx, int which, int it, double* bytes) {
+  Amg& A = *ctx->amg;
+  AmgLevelDev& L = A.lv[0];
+  AmgLevelDev& C = A.lv[1];
+  const double n = L.n, nnz = (double)L.nnz, nc = L.nc, vw = L.cur32 ? 4.0 : 8.0;
+  L.b = ctx->r; L.x2 = A.z;
+  double nnzP = 0.0;
+  if (bytes) {
+    int last = 0;
+    cudaMemcpy(&last, L.Pptr + L.n, sizeof(int), cudaMemcpyDeviceToHost);
+    nnzP = last;
+  }
+  switch (which) {
+    case 9:
+      launch_amg_spmv<1, false>(ctx, L, L.x, L.b, A.omega, L.t);
+      if (bytes) *bytes = (vw + 4.0) * nnz + 4.0 * (n + 1) + 3 * 8.0 * n;
+      return 0;
+    case 10:
+      launch_amg_spmv<2, true>(ctx, L, L.x, L.b, A.omega, L.x2);
+      if (bytes) *bytes = (vw + 4.0) * nnz + 4.0 * (n + 1) + 4 * 8.0 * n;
+      return 0;
+    case 11:
+      k_apcg_update<<<amg_grid(ctx, L.n, kVecBlock), kVecBlock, 0, ctx->stream>>>(L.n, it & 1, it, 1 << 30, ctx->p, ctx->q, ctx->x, ctx->r, L.cur_dinv,
+                                                                                A.omega, L.x, ctx->partials, ctx->scal);
+      if (bytes) *bytes = 8 * 8.0 * n;
+      return 0;
+    case 12:
+      k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, ctx->stream>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, C.cur_dinv, A.omega, C.x, ctx->scal);
+      if (bytes) *bytes = 8.0 * nnzP + 4.0 * (nc + 1) + 8.0 * n + 3 * 8.0 * nc;
+      return 0;
+    case 13:
+      k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, ctx->stream>>>(L.n, L.Pptr, L.Pent, C.x2, L.x, ctx->scal);
+      if (bytes) *bytes = 8.0 * nnzP + 4.0 * (n + 1) + 8.0 * nc + 2 * 8.0 * n;
+      return 0;
+  }
+  return DDPS_ERR_ARG;
+}
+
+// algorithmic bytes of one whole multigrid-preconditioned CG iteration: the CG's own SpMV + vector kernels and, per level,
+// the two cycle SpMVs and the two transfers (same counting rules as above)
+double amg_iteration_bytes(Context* ctx) {
+  Amg& A = *ctx->amg;
+  const double n0 = A.lv[0].n;
+  double by = 12.0 * (double)A.lv[0].nnz + 4.0 * (n0 + 1) + 16.0 * n0;   // k_spmv<true>
+  by += 8 * 8.0 * n0 + 3 * 8.0 * n0;                                     // k_apcg_update, k_apcg_direction
+  for (int l = 0; l + 1 < A.nlev; ++l) {
+    const AmgLevelDev& L = A.lv[l];
+    const double n = L.n, nnz = (double)L.nnz, nc = L.nc, vw = L.cur32 ? 4.0 : 8.0;
+    int last = 0;
+    cudaMemcpy(&last, L.Pptr + L.n, sizeof(int), cudaMemcpyDeviceToHost);
+    by += 2 * ((vw + 4.0) * nnz + 4.0 * (n + 1)) + 7 * 8.0 * n;           // residual + smoothing sweep
+    by += 2 * 8.0 * (double)last + 4.0 * (nc + 1) + 4.0 * (n + 1) + 8.0 * n + 4 * 8.0 * nc + 2 * 8.0 * n;   // restrict + prolong
+  }
+  const double nL = A.lv[A.nlev - 1].n;
+  by += 8.0 * nL * nL;
+  return by;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // CG preconditioned with the V-cycle
 // ------------------------------------------------------------------------------------------------------------
@@ -1140,7 +1208,7 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
     ctx->fail(DDPS_ERR_BREAKDOWN, "PCG breakdown: p.Ap <= 0 (operator not SPD; u or v negative? SURVEY H3)");
     return DDPS_ERR_BREAKDOWN;
   }
-  if (!(S.rr <= S.thresh2 || S.rmax <= S.thresh_inf) && !ctx->opts.lin_cap_ok) {
+  if (!S.conv && !ctx->opts.lin_cap_ok) {   // residual rule AND (warm starts) the energy rule: a cap hit on either is reported
     ctx->fail(DDPS_ERR_NOCONV, "AMG-PCG hit the iteration cap (" + std::to_string(S.iters) + " its, relres " +
                                    std::to_string(S.bb > 0 ? sqrt(S.rr / S.bb) : 0.0) + ")");
     return DDPS_ERR_NOCONV;

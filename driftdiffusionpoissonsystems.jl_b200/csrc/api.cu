@@ -89,6 +89,43 @@ __global__ void k_check_finite(size_t n, const double* __restrict__ a, int* __re
   if (bad) *flag = 1;
 }
 
+// registered spatial functors (include/ddps.h: ddps_spatial_kind), evaluated where the reference evaluates its closures
+struct SpatialFn { int kind; int ntag; double p[16]; };
+__device__ __forceinline__ double eval_spatial(const SpatialFn& f, double x, double y, int tag) {
+  switch (f.kind) {
+    case DDPS_SPATIAL_CONST: return f.p[0];
+    case DDPS_SPATIAL_AFFINE: return (f.p[0] + f.p[1] * x) + f.p[2] * y;
+    case DDPS_SPATIAL_STEP_X: return x > f.p[0] ? f.p[2] : f.p[1];
+    case DDPS_SPATIAL_STEP_Y: return y > f.p[0] ? f.p[2] : f.p[1];
+    default: {
+      double v = f.p[0];
+      for (int k = 0; k < f.ntag; ++k) if ((double)tag == f.p[1 + 2 * k]) v = f.p[2 + 2 * k];
+      return v;
+    }
+  }
+}
+// where = 0: centroids ((x1+x2+x3)/3, src:250-251) -> out[nme]; 1: edge midpoints m12,m23,m31 ((xa+xb)/2, src:303-308) ->
+// out[3*nme]; square: store the square (lambda^2, src:254)
+__global__ void k_sample_elements(int nme, const int4* __restrict__ elem, const double2* __restrict__ xy, SpatialFn f, int where,
+                                  int square, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nme) return;
+  const int4 el = elem[e];
+  const double2 q1 = xy[el.x], q2 = xy[el.y], q3 = xy[el.z];
+  if (where == 0) {
+    const double v = eval_spatial(f, (q1.x + q2.x + q3.x) / 3.0, (q1.y + q2.y + q3.y) / 3.0, el.w);
+    out[e] = square ? v * v : v;
+  } else {
+    out[3 * (size_t)e + 0] = eval_spatial(f, (q1.x + q2.x) / 2.0, (q1.y + q2.y) / 2.0, el.w);
+    out[3 * (size_t)e + 1] = eval_spatial(f, (q2.x + q3.x) / 2.0, (q2.y + q3.y) / 2.0, el.w);
+    out[3 * (size_t)e + 2] = eval_spatial(f, (q3.x + q1.x) / 2.0, (q3.y + q1.y) / 2.0, el.w);
+  }
+}
+__global__ void k_sample_nodes(int n, const double2* __restrict__ xy, SpatialFn f, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = eval_spatial(f, xy[i].x, xy[i].y, 0);
+}
+
 __global__ void k_scatter_global(int n, const long long* __restrict__ glob, const double* __restrict__ src,
                                  double* __restrict__ dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,41 +416,79 @@ struct EventTimer {
   double ms() { float t = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&t, a, b); return t; }
 };
 
-// Vsolve (src:292-425): Newton from V=0 on MV*V = b(V) at frozen (u0,v0).
-int vsolve(Context* ctx) {
+// The Newton loop shared by Vsolve (src:368-423) and solve_semlin_poisson (src:1040-1095):
+//   assemble A = base - J0(V), b(V), F = base*V - b at the iterate;  stop when ||F||_inf <= tol;  V <- V - A^-1 F.
+// The assembly at the updated iterate is both the stop test of the reference's `while` and the next step's system.
+// opts.newton_damping = k > 0 (OPT-IN; the reference's update is undamped, src:394-395,1063-1064):
+// the step is halved, at most k times, until ||F||_inf decreases -- backtracking on the quantity the loop tests anyway.
+// on_res(res, it) sees the residual norm of every ACCEPTED iterate (it = 0: the initial one).
+template <class OnRes>
+int newton_loop(Context* ctx, bool semlin, double delta, double tol, const double* u, const double* v, OnRes&& on_res,
+                int* count_out) {
   int rc;
   const int n = ctx->n_own;
-  if (!(ctx->opts.warm_start_v && ctx->stats.outer_iters > 0))   // opt-in warm start keeps the previous V (SURVEY 8f-4)
-    DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:311
-  int newton = 0;
   const int cap = ctx->opts.max_newton > 0 ? ctx->opts.max_newton : 1000;
-  while (true) {
+  const int damp = std::max(0, ctx->opts.newton_damping);
+  const size_t bytes = (size_t)ctx->n_loc * sizeof(double);
+  auto assemble = [&](double* res) -> int {
     EventTimer ta(ctx, ctx->ev0, ctx->ev1);
-    if ((rc = assemble_newton(ctx, false, ctx->delta, ctx->V, ctx->U0, ctx->W0))) return rc;
+    int r = assemble_newton(ctx, semlin, delta, ctx->V, u, v);
+    if (r) return r;
     ta.stop();
-    double res;
-    if ((rc = fetch_resid_norm(ctx, &res))) return rc;
+    if ((r = fetch_resid_norm(ctx, res))) return r;
     ctx->stats.t_asm_ms += ta.ms();
-    if (!(res > ctx->tol)) break;                                                            // src:368
-    if (newton >= cap) {
+    return 0;
+  };
+  int count = 0;
+  double res = 0.0;
+  if ((rc = assemble(&res))) return rc;
+  on_res(res, 0);
+  while (res > tol) {                                                                        // src:368, 1040
+    if (count >= cap) {
       if (ctx->opts.lin_cap_ok) break;   // profiling runs only
-      ctx->fail(DDPS_ERR_NOCONV, "Vsolve: Newton iteration cap reached");
+      ctx->fail(DDPS_ERR_NOCONV, semlin ? "semlin: Newton iteration cap reached" : "Vsolve: Newton iteration cap reached");
+      *count_out = count;
       return DDPS_ERR_NOCONV;
     }
     EventTimer tp(ctx, ctx->ev2, ctx->ev3);
     // Newton correction: the linear residual only has to be below the Newton tolerance (so that, like the
     // reference's direct solve, a linear problem converges in one step); newton_eta is a relative floor.
-    ctx->amg_kind = newton == 0 ? 0 : 3;
-    rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * ctx->tol,
-                   ctx->opts.lin_max_it, nullptr, nullptr);
+    ctx->amg_kind = count == 0 ? 0 : 3;
+    rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
+                      ctx->opts.lin_max_it, nullptr, nullptr);                               // src:394, 1063
     ctx->amg_kind = -1;
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
     if (rc) return rc;
-    if ((rc = launch_axpy(ctx, -1.0, ctx->x, ctx->V, n))) return rc;                         // src:394-395
+    if (damp) DDPS_CUDA(cudaMemcpyAsync(ctx->Unew, ctx->V, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = launch_axpy(ctx, -1.0, ctx->x, ctx->V, n))) return rc;                         // src:395, 1064
     if ((rc = halo_exchange(ctx, ctx->V))) return rc;
-    ++newton;
+    double res_new = 0.0;
+    if ((rc = assemble(&res_new))) return rc;
+    double t = 1.0;
+    for (int k = 0; k < damp && !(res_new < res); ++k) {
+      t *= 0.5;
+      DDPS_CUDA(cudaMemcpyAsync(ctx->V, ctx->Unew, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      if ((rc = launch_axpy(ctx, -t, ctx->x, ctx->V, n))) return rc;
+      if ((rc = halo_exchange(ctx, ctx->V))) return rc;
+      if ((rc = assemble(&res_new))) return rc;
+      ctx->stats.newton_halvings++;
+    }
+    res = res_new;
+    ++count;
+    on_res(res, count);
   }
+  *count_out = count;
+  return 0;
+}
+
+// Vsolve (src:292-425): Newton from V=0 on MV*V = b(V) at frozen (u0,v0).
+int vsolve(Context* ctx) {
+  if (!(ctx->opts.warm_start_v && ctx->stats.outer_iters > 0))   // opt-in warm start keeps the previous V (SURVEY 8f-4)
+    DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:311
+  int newton = 0;
+  int rc = newton_loop(ctx, false, ctx->delta, ctx->tol, ctx->U0, ctx->W0, [](double, int) {}, &newton);
+  if (rc) return rc;
   ctx->stats.newton_total += newton;
   ctx->hist_newton.push_back((double)newton);
   return 0;
@@ -816,17 +891,21 @@ int ddps_dirichlet_set(ddps_ctx* ctx, int field, const int64_t* idx1, const doub
   return DDPS_OK;
 }
 
+static int coeff_slot_kind(int slot) {   // 0: [nme], 1: [3,nme], 2: [nq], -1: unknown
+  if (slot == DDPS_COEFF_C_MID || slot == DDPS_COEFF_H_MID || (slot >= DDPS_COEFF_POLY_MID0 && slot < DDPS_COEFF_POLY_MID0 + kMaxPoly)) return 1;
+  if (slot == DDPS_COEFF_NEUMANN || (slot >= DDPS_COEFF_POLY_NODE0 && slot < DDPS_COEFF_POLY_NODE0 + kMaxPoly)) return 2;
+  if (slot >= 0 && slot <= DDPS_COEFF_A22) return 0;
+  return -1;
+}
+
 int ddps_coeff_set(ddps_ctx* ctx, int slot, const double* data, int64_t len) {
   if (!ctx) return DDPS_ERR_ARG;
   cudaSetDevice(ctx->device);
   int rc;
   if ((rc = require_mesh(ctx))) return rc;
   if (slot < 0 || slot >= 64 || !data) { ctx->fail(DDPS_ERR_ARG, "bad coefficient slot"); return DDPS_ERR_ARG; }
-  int kind;  // 0: [nme], 1: [3,nme], 2: [nq]
-  if (slot == DDPS_COEFF_C_MID || slot == DDPS_COEFF_H_MID || (slot >= DDPS_COEFF_POLY_MID0 && slot < DDPS_COEFF_POLY_MID0 + kMaxPoly)) kind = 1;
-  else if (slot == DDPS_COEFF_NEUMANN || (slot >= DDPS_COEFF_POLY_NODE0 && slot < DDPS_COEFF_POLY_NODE0 + kMaxPoly)) kind = 2;
-  else if (slot <= DDPS_COEFF_A22) kind = 0;
-  else { ctx->fail(DDPS_ERR_ARG, "unknown coefficient slot"); return DDPS_ERR_ARG; }
+  const int kind = coeff_slot_kind(slot);  // 0: [nme], 1: [3,nme], 2: [nq]
+  if (kind < 0) { ctx->fail(DDPS_ERR_ARG, "unknown coefficient slot"); return DDPS_ERR_ARG; }
   int64_t want = kind == 0 ? ctx->nme_global : kind == 1 ? 3 * ctx->nme_global : ctx->nq_global;
   if (len != want) { ctx->fail(DDPS_ERR_ARG, "coefficient array has the wrong length"); return DDPS_ERR_ARG; }
   const bool direct = (kind == 2) ? ctx->loc2glob.empty() : ctx->elem_glob.empty();
@@ -861,6 +940,44 @@ int ddps_coeff_set(ddps_ctx* ctx, int slot, const double* data, int64_t len) {
     if ((rc = upload(ctx, ctx->coeff[slot], tmp.data(), nloc))) return rc;
     DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (slot == DDPS_COEFF_LAMBDA2 || slot == DDPS_COEFF_A11 || slot == DDPS_COEFF_A22) ctx->base_ready = false;
+  return DDPS_OK;
+}
+
+int ddps_coeff_functor(ddps_ctx* ctx, int slot, int kind, const double* params, int nparams) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  const int sk = coeff_slot_kind(slot);
+  if (sk < 0 || slot == DDPS_COEFF_NEUMANN) { ctx->fail(DDPS_ERR_ARG, "slot cannot be filled from a spatial functor"); return DDPS_ERR_ARG; }
+  static const int want[] = {0, 1, 3, 3, 3};
+  const bool by_tag = kind == DDPS_SPATIAL_BY_TAG;
+  if (kind < DDPS_SPATIAL_CONST || kind > DDPS_SPATIAL_BY_TAG || !params || (!by_tag && nparams != want[kind]) ||
+      (by_tag && (nparams < 1 || nparams > 15 || nparams % 2 == 0))) {
+    ctx->fail(DDPS_ERR_ARG, "unknown spatial functor or wrong parameter count (host-sample the closure and use ddps_coeff_set)");
+    return DDPS_ERR_ARG;
+  }
+  if (by_tag && sk == 2) { ctx->fail(DDPS_ERR_ARG, "BY_TAG functors exist per triangle only"); return DDPS_ERR_ARG; }
+  SpatialFn f;
+  memset(&f, 0, sizeof(f));
+  f.kind = kind;
+  f.ntag = by_tag ? (nparams - 1) / 2 : 0;
+  for (int i = 0; i < nparams; ++i) {
+    if (!std::isfinite(params[i])) { ctx->fail(DDPS_ERR_ARG, "spatial functor parameter is not finite"); return DDPS_ERR_ARG; }
+    f.p[i] = params[i];
+  }
+  const size_t nloc = sk == 0 ? (size_t)ctx->nme : sk == 1 ? (size_t)3 * ctx->nme : (size_t)ctx->n_loc;
+  if ((rc = dev_alloc(ctx, &ctx->coeff[slot], nloc))) return rc;
+  ctx->coeff_len[slot] = (int64_t)nloc;
+  if (sk == 2) {
+    if (ctx->n_loc) k_sample_nodes<<<(ctx->n_loc + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_loc, ctx->xy, f, ctx->coeff[slot]);
+  } else if (ctx->nme) {
+    k_sample_elements<<<(ctx->nme + 255) / 256, 256, 0, ctx->stream>>>(ctx->nme, ctx->elem, ctx->xy, f, sk, slot == DDPS_COEFF_LAMBDA2,
+                                                                      ctx->coeff[slot]);
+  }
+  DDPS_CUDA(cudaGetLastError());
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   if (slot == DDPS_COEFF_LAMBDA2 || slot == DDPS_COEFF_A11 || slot == DDPS_COEFF_A22) ctx->base_ready = false;
   return DDPS_OK;
@@ -990,32 +1107,14 @@ int ddps_solve_semlin(ddps_ctx* ctx, double tol, double* Vout, ddps_stats* stats
     ctx->stats.t_amg_setup_ms = now_ms() - ta;
   }
   DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, (size_t)ctx->n_loc * sizeof(double), ctx->stream));   // src:948
-  const int cap = ctx->opts.max_newton > 0 ? ctx->opts.max_newton : 1000;
   int count = 0;
-  while (true) {
-    EventTimer ta(ctx, ctx->ev0, ctx->ev1);
-    if ((rc = assemble_newton(ctx, true, 0.0, ctx->V, nullptr, nullptr))) break;
-    ta.stop();
-    double res;
-    if ((rc = fetch_resid_norm(ctx, &res))) break;
-    ctx->stats.t_asm_ms += ta.ms();
-    ctx->hist_outer.push_back(res);
-    ctx->stats.control = res;
-    if (count > 0 && ctx->opts.verbose) printf("iteration %d, tolerance: %.17g\n", count, res);   // src:1093
-    if (!(res > tol)) break;                                                                  // src:1040
-    if (count >= cap) { ctx->fail(DDPS_ERR_NOCONV, "semlin: Newton iteration cap reached"); rc = DDPS_ERR_NOCONV; break; }
-    EventTimer tp(ctx, ctx->ev2, ctx->ev3);
-    ctx->amg_kind = count == 0 ? 0 : 3;
-    rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
-                   ctx->opts.lin_max_it, nullptr, nullptr);                                   // src:1063
-    ctx->amg_kind = -1;
-    tp.stop();
-    ctx->stats.t_pcg_ms += tp.ms();
-    if (rc) break;
-    if ((rc = launch_axpy(ctx, -1.0, ctx->x, ctx->V, ctx->n_own))) break;                     // src:1064
-    if ((rc = halo_exchange(ctx, ctx->V))) break;
-    ++count;
-  }
+  rc = newton_loop(ctx, true, 0.0, tol, nullptr, nullptr,
+                   [&](double res, int it) {
+                     ctx->hist_outer.push_back(res);
+                     ctx->stats.control = res;
+                     if (it > 0 && ctx->opts.verbose) printf("iteration %d, tolerance: %.17g\n", it, res);   // src:1093
+                   },
+                   &count);
   ctx->stats.outer_iters = count;
   ctx->stats.newton_total = count;
   ctx->stats.status = rc;
@@ -1113,6 +1212,21 @@ int ddps_get_vector(ddps_ctx* ctx, int which, double* out, int64_t len) {
   if (ctx->nranks == 1) return download_owned(ctx, src, out);
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   DDPS_CUDA(cudaMemcpy(out, src, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost));
+  return DDPS_OK;
+}
+
+int ddps_get_coeff(ddps_ctx* ctx, int slot, double* out, int64_t cap, int64_t* len) {
+  if (!ctx || !len) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (slot < 0 || slot >= 64 || !ctx->coeff[slot]) { ctx->fail(DDPS_ERR_STATE, "coefficient slot is empty"); return DDPS_ERR_STATE; }
+  if (ctx->nranks != 1 || !ctx->loc2glob.empty()) { ctx->fail(DDPS_ERR_STATE, "debug exports are single-GPU, caller's numbering"); return DDPS_ERR_STATE; }
+  *len = ctx->coeff_len[slot];
+  if (!out) return DDPS_OK;
+  if (cap < *len) { ctx->fail(DDPS_ERR_ARG, "output buffer too small"); return DDPS_ERR_ARG; }
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  DDPS_CUDA(cudaMemcpy(out, ctx->coeff[slot], (size_t)*len * sizeof(double), cudaMemcpyDeviceToHost));
   return DDPS_OK;
 }
 
@@ -1250,6 +1364,7 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
       case 6: return amg_pcg_iteration_launch(ctx, ctx->x, it, 1 << 30);
       case 7: return amg_numeric(ctx, ctx->val_op, ctx->dinv, -1);
       case 8: return amg_vcycle(ctx, ctx->r, ctx->q, false);
+      case 9: case 10: case 11: case 12: case 13: return amg_time_launch(ctx, kernel, it, nullptr);
     }
     ctx->fail(DDPS_ERR_ARG, "unknown kernel id");
     return DDPS_ERR_ARG;
@@ -1264,7 +1379,7 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
     case 4: bytes = 12.0 * nme + 16.0 * nq + 8.0 * nme + 8.0 * nnz + 8.0 * nq; break;
     case 5: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq; break;
   }
-  if (kernel >= 6 && kernel <= 8) {
+  if (kernel >= 6 && kernel <= 13) {
     if (!amg_ready(ctx)) { ctx->fail(DDPS_ERR_STATE, "no multigrid hierarchy (opts.precond = DDPS_PRECOND_AMG and a base assembly first)"); return DDPS_ERR_STATE; }
     // fresh state on the last assembled system: one capped solve leaves r, p, z and the scalars consistent
     const int32_t keep = ctx->opts.lin_cap_ok;
@@ -1273,6 +1388,10 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
     ctx->opts.lin_cap_ok = keep;
     if (rc) return rc;
     DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
+    if (kernel == 6) bytes = amg_iteration_bytes(ctx);
+    if (kernel >= 9) {
+      if ((rc = amg_time_launch(ctx, kernel, 0, &bytes))) { ctx->fail(DDPS_ERR_ARG, "unknown kernel id"); return rc; }
+    }
   }
   if (kernel == 5) DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
   if (kernel == 2) {

@@ -94,7 +94,7 @@ struct PcgScalars {
   double thresh_e;  // stop only when r.Br <= thresh_e
   double xb;        // x0.rhs ~ ||x||_A^2
   int warm;
-  int pad1;
+  int conv;         // multigrid-preconditioned CG: 1 once every stop rule is met (0 after an exhausted iteration cap)
 };
 
 // ---- peer-memory (NVLink P2P via CUDA IPC) windows for the fused halo push + scalar allreduce ----
@@ -312,6 +312,8 @@ int amg_vcycle(Context* ctx, const double* r, double* z, bool dot_rz);
 int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const double* rhs, double* x, bool x0_nonzero,
                   double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out);
 int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it);
+int amg_time_launch(Context* ctx, int which, int it, double* bytes);   // single kernels of the iteration (ddps_time_kernel 9..13)
+double amg_iteration_bytes(Context* ctx);
 int amg_debug_levels(Context* ctx, int64_t* nlevels, int64_t* sizes, int cap);
 int amg_debug_get_values(Context* ctx, int level, double* val_csr, double* dinv);
 int amg_debug_get_level(Context* ctx, int level, int64_t* sizes, int64_t* rowptr, int64_t* col, int64_t* Pptr, int64_t* Pcol,

@@ -26,10 +26,13 @@ namespace ddps {
 // ambiguous; the data dependencies of CG (every rank needs every other rank's previous partial before it
 // can produce the next one) make single buffering safe.  A spin gives up after ~10 s and raises an error
 // flag instead of hanging the GPU.
-__device__ __forceinline__ bool spin_until(const volatile unsigned long long* flag, unsigned long long tag) {
+// `err` is the window's sticky error flag: once any wait of this solve has timed out, later waits give up at once
+// (a dead rank then costs one timeout, not one per kernel) and the solve ends with DDPS_ERR_COMM.
+__device__ __forceinline__ bool spin_until(const volatile unsigned long long* flag, unsigned long long tag, volatile int* err) {
   const long long t0 = clock64();
   while (*flag < tag) {
-    if (clock64() - t0 > 20000000000LL) return false;
+    if (*err) return false;
+    if (clock64() - t0 > 20000000000LL) { *err = 1; return false; }
   }
   return true;
 }
@@ -65,7 +68,7 @@ __device__ __forceinline__ bool p2p_gather(const P2PDev& pd, int phase, unsigned
 #pragma unroll
     for (int i = 0; i < NV; ++i) mine[i] = 0.0;
     if (r < pd.nranks) {
-      ok = spin_until(phase == 0 ? &W->redA_flag[r] : &W->redB_flag[r], tag);
+      ok = spin_until(phase == 0 ? &W->redA_flag[r] : &W->redB_flag[r], tag, &W->error);
       __threadfence();
       const volatile double* src = phase == 0 ? W->redA[r] : W->redB[r];
 #pragma unroll
@@ -86,7 +89,6 @@ __device__ __forceinline__ bool p2p_gather(const P2PDev& pd, int phase, unsigned
 #pragma unroll
       for (int i = 0; i < NV; ++i) sh[i] = acc[i];
       s_ok = ok ? 1 : 0;
-      if (!ok) W->error = 1;
     }
   }
   __syncthreads();
@@ -490,17 +492,26 @@ int launch_prep_semlin(Context* ctx, const double* V) {
 // ------------------------------------------------------------------------------------------------
 // SpMV (SELL-32) with fused dot, persistent grid-stride over slices
 // ------------------------------------------------------------------------------------------------
-template <bool DOT>
+// gather of x: the read-only path for columns this rank owns.  MR (fused peer-memory halo): the ghost block of x is
+// written by the peers over NVLink while this kernel may already be resident (it waits on the halo flags itself), so
+// ghost columns (c >= nrows) must not go through the non-coherent path: ld.global.cg reads them from L2.
+template <bool MR>
+__device__ __forceinline__ double ld_x(const double* __restrict__ x, int c, int nrows) {
+  if (MR && c >= nrows) return __ldcg(x + c);
+  return __ldg(x + c);
+}
+
+template <bool DOT, bool MR>
 __global__ void __launch_bounds__(kVecBlock, 8) k_spmv(int nrows, int nslices, const int* __restrict__ slice_ptr,
                                                     const int* __restrict__ col, const double* __restrict__ val,
                                                     const double* __restrict__ x, double* __restrict__ y,
                                                     double* partials, PcgScalars* scal, const P2PDev pd, const int rev) {
   __shared__ double sh_red[32];
   if (DOT && scal->done) return;
-  if (DOT && pd.nranks > 1) {   // the neighbours' halo pushes for this iteration must have landed
+  if (MR) {   // the neighbours' halo pushes for this iteration must have landed
     if (threadIdx.x < pd.nneigh) {
       P2PWin* W = pd.win[pd.rank];
-      if (!spin_until(&W->halo_flag[pd.neigh[threadIdx.x]], pd.tag_halo)) W->error = 1;
+      if (!spin_until(&W->halo_flag[pd.neigh[threadIdx.x]], pd.tag_halo, &W->error)) scal->breakdown = 2;   // -> DDPS_ERR_COMM
       __threadfence();
     }
     __syncthreads();
@@ -526,14 +537,14 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_spmv(int nrows, int nslices, c
                 c3 = ld_stream(col + idx + 96);
       const double v0 = ld_stream(val + idx), v1 = ld_stream(val + idx + 32), v2 = ld_stream(val + idx + 64),
                    v3 = ld_stream(val + idx + 96);
-      const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+      const double x0 = ld_x<MR>(x, c0, nrows), x1 = ld_x<MR>(x, c1, nrows), x2 = ld_x<MR>(x, c2, nrows), x3 = ld_x<MR>(x, c3, nrows);
       sum += v0 * x0; sum += v1 * x1; sum += v2 * x2; sum += v3 * x3;
       idx += 128;
     }
     for (; k < w; ++k) {
       const int c0 = ld_stream(col + idx);
       const double v0 = ld_stream(val + idx);
-      sum += v0 * __ldg(x + c0);
+      sum += v0 * ld_x<MR>(x, c0, nrows);
       idx += 32;
     }
     const int row = slice * 32 + lane;
@@ -546,7 +557,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_spmv(int nrows, int nslices, c
     double v[1] = {dot}, tot[1];
     if (grid_reduce<1, false>(v, partials, &scal->cnt[0], sh_red, tot)) {
       if (threadIdx.x == 0) {
-        if (pd.nranks > 1) p2p_publish<1>(pd, 0, pd.tagA, tot);
+        if (MR) p2p_publish<1>(pd, 0, pd.tagA, tot);
         else scal->sums[0] = tot[0];
       }
     }
@@ -564,7 +575,7 @@ int launch_spmv(Context* ctx, const double* val, const double* x, double* y) {
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
-  k_spmv<false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr, none, 0);
+  k_spmv<false, false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr, none, 0);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
@@ -576,7 +587,7 @@ int launch_spmv_dot(Context* ctx, const double* val, const double* x, double* y)
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
-  k_spmv<true><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal, none, 0);
+  k_spmv<true, false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal, none, 0);
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
@@ -714,9 +725,13 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_update(int n, int par, int
   double pq;
   if (pd.nranks > 1) {
     double t[1];
-    p2p_gather<1, 0u>(pd, 0, pd.tagA, t, sh_red);
+    const bool ok = p2p_gather<1, 0u>(pd, 0, pd.tagA, t, sh_red);
     pq = t[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) scal->sums[0] = pq;
+    if (!ok) {   // a peer's partial never arrived: alpha would be garbage -> stop, DDPS_ERR_COMM (raised by k_pcg_direction)
+      if (blockIdx.x == 0 && threadIdx.x == 0) scal->breakdown = 2;
+      return;
+    }
   } else {
     pq = scal->sums[0];
   }
@@ -757,7 +772,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, 
   __shared__ double sh_red[32];
   __shared__ bool s_last_dir;
   if (scal->done) return;
-  if (scal->breakdown) {
+  if (scal->breakdown) {   // (1: operator not SPD; 2: a peer-memory wait timed out -- every rank sees its own timeout)
     if (blockIdx.x == 0 && threadIdx.x == 0) { scal->done = 1; scal->iters = it; }
     return;
   }
@@ -912,8 +927,8 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
       ctx->stats.kernel_launches++;
     }
     pa.tag = pd.tagB + 1;           // = tag_halo of the next iteration
-    k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
-                                                    ctx->partials, ctx->scal, pd, r0);
+    k_spmv<true, true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
+                                                          ctx->partials, ctx->scal, pd, r0);
     k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r1, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
     k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd, pa,
                                                        ctx->halo.send_idx);
@@ -921,8 +936,8 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
     memset(&pd, 0, sizeof(pd));
     pd.nranks = 1;
     if ((rc = halo_exchange(ctx, ctx->p))) return rc;
-    k_spmv<true><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
-                                                    ctx->partials, ctx->scal, pd, r0);
+    k_spmv<true, false><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
+                                                           ctx->partials, ctx->scal, pd, r0);
     if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 1))) return rc;
     k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r1, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
     if ((rc = allreduce_sum(ctx, &ctx->scal->sums[1], 2))) return rc;
@@ -944,6 +959,8 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
   if (max_it > 2000000000LL) max_it = 2000000000LL;
   cudaStream_t st = ctx->stream;
   int g = vec_grid(ctx, std::max(n, 1), kVecBlock);
+  if (ctx->p2p.enabled)   // the sticky timeout flag of the peer-memory waits is per solve
+    DDPS_CUDA(cudaMemsetAsync(&ctx->p2p.win_local->error, 0, sizeof(int), st));
   if (x0_nonzero) {
     DDPS_CUDA(cudaMemcpyAsync(ctx->p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = halo_exchange(ctx, ctx->p))) return rc;

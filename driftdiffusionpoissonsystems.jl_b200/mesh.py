@@ -133,11 +133,13 @@ def structured_mesh(nx, ny, x0=0.0, x1=1.0, y0=0.0, y1=1.0) -> Mesh:
     tagged 1 bottom, 2 right, 3 top, 4 left."""
     xs = np.linspace(x0, x1, nx + 1)
     ys = np.linspace(y0, y1, ny + 1)
-    nodes = np.empty((2, (nx + 1) * (ny + 1)))
+    # stored like the reference's Julia arrays (column-major 2 x nq / 5 x nme = x,y interleaved per node, the five
+    # entries of a triangle adjacent): the (rows, count) views below are Fortran-ordered, and the C ABI takes them as is
+    nodes = np.empty(((nx + 1) * (ny + 1), 2)).T
     nodes[0] = np.tile(xs, ny + 1)
     nodes[1] = np.repeat(ys, nx + 1)
     cell = (np.arange(ny, dtype=np.int64)[:, None] * (nx + 1) + np.arange(nx, dtype=np.int64)[None, :]).ravel() + 1
-    el = np.empty((5, 2 * nx * ny), dtype=np.int64)
+    el = np.empty((2 * nx * ny, 5), dtype=np.int64).T
     el[0, 0::2] = cell
     el[1, 0::2] = cell + 1
     el[2, 0::2] = cell + nx + 2

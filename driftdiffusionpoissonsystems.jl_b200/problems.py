@@ -11,7 +11,7 @@ import math
 
 import numpy as np
 
-from .functors import SinhRHS
+from .functors import Const, SinhRHS, StepX
 
 
 def ddpe1(c: float = 1.0):
@@ -65,9 +65,9 @@ def pn_junction(dirichlet_tags, all_tags, x_junction=0.0, C0=1.0, U=0.3, lam=1.0
     pick = lambda f: [f if k == "D" else zero for k in kinds]
     return dict(rec_mode="shockley", Vbddata=[list(all_tags), kinds, pick(fV)],
                 ubddata=[list(all_tags), kinds, pick(fu)], vbddata=[list(all_tags), kinds, pick(fv)],
-                lam=lambda x, y: lam + 0 * np.asarray(x), delta=delta, tau_p=tau, tau_n=tau,
-                mu_p=lambda x, y: mu + 0 * np.asarray(x), mu_n=lambda x, y: mu + 0 * np.asarray(x),
-                C=lambda x, y: np.where(np.asarray(x) > x_junction, C0, -C0), tol=tol)
+                lam=Const(lam), delta=delta, tau_p=tau, tau_n=tau, mu_p=Const(mu), mu_n=Const(mu),
+                C=StepX(x_junction, -C0, C0), tol=tol)   # registered spatial functors: ordinary closures that the library
+                                                         # can also sample on the device (functors.py)
 
 
 def semlin_test(tags4=True):

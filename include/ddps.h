@@ -64,6 +64,19 @@ enum ddps_functor_kind {
   DDPS_FUNCTOR_POLY = 2  /* f = sum_k c_k u^k, g = sum_k k c_k u^(k-1); params {degree} */
 };
 
+/* ---- registered SPATIAL functors: coefficient closures the library samples ON THE DEVICE from the resident mesh, at
+ * the points where the reference evaluates them (centroids src:250-254,463-467; edge midpoints src:303-308,341-343;
+ * nodes), bitwise equal to host sampling of the same expression.  Anything else is sampled by the host shim and uploaded
+ * with ddps_coeff_set. */
+enum ddps_spatial_kind {
+  DDPS_SPATIAL_CONST = 1,  /* c                                  params {c} */
+  DDPS_SPATIAL_AFFINE = 2, /* (a + bx*x) + by*y                   params {a, bx, by} */
+  DDPS_SPATIAL_STEP_X = 3, /* x > x0 ? right : left               params {x0, left, right}   (pn doping, src:341) */
+  DDPS_SPATIAL_STEP_Y = 4, /* y > y0 ? above : below              params {y0, below, above} */
+  DDPS_SPATIAL_BY_TAG = 5  /* value of the triangle's geometric tag (Mesh.elements row 5, src:17); params
+                              {default, tag_1, value_1, ..., tag_k, value_k}, k <= 7; per-triangle slots only */
+};
+
 enum ddps_rec_mode { DDPS_REC_ZERO = 0 /* :zero src:520 */, DDPS_REC_SHOCKLEY = 1 /* :shockley src:516 */ };
 
 /* ---- matrices / vectors retrievable for parity tests -------------------------------------- */
@@ -105,6 +118,10 @@ typedef struct ddps_solver_opts {
                            they are reused while the operator of the same kind (first / later Newton system, u-, v-continuity
                            system) stays within 1 % (entries and row sums) of the one they were computed from -- the cycle is
                            only a preconditioner, the solutions are the same to solver tolerance */
+  int32_t newton_damping; /* OPT-IN, default 0 = the reference's undamped update (src:394-395,
+                           1063-1064).  k > 0: the Newton step of Vsolve / solve_semlin_poisson is halved, at most k times,
+                           until the residual max-norm ||M*V - b(V)||_inf (the quantity the loops test, src:368,1040) decreases.
+                           Changes the iteration history only when a full step would increase the residual */
 } ddps_solver_opts;
 
 #define DDPS_PRECOND_JACOBI 0
@@ -127,7 +144,8 @@ typedef struct ddps_stats {
   int32_t amg_levels;      /* multigrid levels in use (0: Jacobi-PCG) */
   int32_t amg_reuses;      /* solves that reused lagged coarse operators (opts.amg_no_lag = 0) */
   double t_amg_setup_ms;   /* host wall: one-time hierarchy setup (aggregation, prolongators, coarse patterns, uploads) */
-  int32_t reserved[4];
+  int32_t newton_halvings; /* step halvings taken by opts.newton_damping */
+  int32_t reserved[3];
 } ddps_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
@@ -168,6 +186,10 @@ int ddps_partition_plan(const double* nodes, int64_t nq, const int64_t* elements
 int ddps_dirichlet_set(ddps_ctx* ctx, int field, const int64_t* idx1, const double* val, int64_t nd);
 int ddps_coeff_set(ddps_ctx* ctx, int slot, const double* data, int64_t len);
 int ddps_functor_set(ddps_ctx* ctx, int kind, const double* params, int nparams);
+/* Fill a coefficient slot by evaluating a registered spatial functor on the device (replaces the reference's per-call
+ * `lambda.(cx,cy)`, `map(mu, ...)`, `C.(halfa_x, halfa_y)` broadcasts, src:254,467,341-343): no host sampling, no upload.
+ * DDPS_COEFF_LAMBDA2 stores the SQUARE of the functor's value (src:254). */
+int ddps_coeff_functor(ddps_ctx* ctx, int slot, int kind, const double* params, int nparams);
 
 /* ---- solve_ddpe (src:630-658) -------------------------------------------------------------
  * begin: MV_assemble once (src:643), zero state (src:635-637).
@@ -195,6 +217,9 @@ int ddps_get_csr_size(ddps_ctx* ctx, int64_t* nrows, int64_t* nnz);
 /* CSR of the fixed pattern, 0-based, columns sorted within each row, explicit zeros kept (Q5). */
 int ddps_get_csr(ddps_ctx* ctx, int which, int64_t* rowptr, int64_t* col, double* val);
 int ddps_get_vector(ddps_ctx* ctx, int which, double* out, int64_t len);
+/* The coefficient array a slot holds on the device (uploaded or device-sampled), in the layout ddps_coeff_set takes;
+ * *len receives its length (out may be NULL to query it). */
+int ddps_get_coeff(ddps_ctx* ctx, int slot, double* out, int64_t cap, int64_t* len);
 /* Assemble individual systems from host-supplied fields (each length nq), results retrievable with
  * ddps_get_csr(DDPS_MAT_OP)/ddps_get_vector(DDPS_VEC_RHS):
  *   base   : MV (src:229-287) from LAMBDA2, or semlin M (src:924-1028) from A11/A22 (use_semlin!=0)
@@ -217,7 +242,9 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
  * 2: one full PCG iteration; 3: Newton-system assembly (Vsolve, src:368-420); 4: base stiffness;
  * 5: the PCG's SpMV with the fused p.Ap dot; 6: one CG iteration preconditioned with the multigrid V-cycle
  * (opts.precond = DDPS_PRECOND_AMG); 7: the per-operator multigrid numeric phase (Galerkin products on all levels +
- * coarsest inverse); 8: one V-cycle alone.
+ * coarsest inverse); 8: one V-cycle alone; single kernels of the multigrid iteration on the finest level: 9 residual SpMV
+ * t = b - A x, 10 smoothing-sweep SpMV fused with r.z, 11 the CG update kernel (x, r, first sweep), 12 restriction to level 1,
+ * 13 prolongation from level 1 (kernel 6 reports the summed algorithmic bytes of the whole iteration).
  * Runs `reps` launches after `warm` untimed ones and returns the mean milliseconds per launch and
  * the algorithmic bytes of one launch (definition in DESIGN.md). */
 int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_per_launch, double* algo_bytes);

@@ -327,7 +327,23 @@ def _vec3(fn, x, y, u):
 # --------------------------------------------------------------------------------------------
 # Vsolve (src:292-425)
 # --------------------------------------------------------------------------------------------
-def Vsolve(mesh, u, v, delta, M, bdM, ar, n, gD, C, tol, linsolve="sparse", trace=None, max_newton=200):
+def _damped_update(V, dx, res, M, rhs, damping):
+    """NOT in the reference (its Newton update is undamped, src:394-395,1063-1064): restatement of the library's opt-in
+    ``opts.newton_damping`` so that the tests can check it -- halve the step (at most
+    ``damping`` times) until the residual max-norm decreases.  damping = 0 is the reference."""
+    t = 1.0
+    Vn = V - dx
+    bn = rhs(Vn)
+    k = 0
+    while k < damping and not np.max(np.abs(M @ Vn - bn)) < res:
+        t /= 2
+        Vn = V - t * dx
+        bn = rhs(Vn)
+        k += 1
+    return Vn, bn
+
+
+def Vsolve(mesh, u, v, delta, M, bdM, ar, n, gD, C, tol, linsolve="sparse", trace=None, max_newton=200, damping=0):
     nq = mesh.nodes.shape[1]
     a1, a2, a3 = (mesh.elements[k, :] - 1 for k in range(3))
     n0 = np.asarray(n) - 1
@@ -372,8 +388,7 @@ def Vsolve(mesh, u, v, delta, M, bdM, ar, n, gD, C, tol, linsolve="sparse", trac
         if trace is not None and "V_A_first" not in trace:
             trace["V_A_first"] = A.copy()
             trace["V_b_first"] = b.copy()
-        V = V - _solve(A, M @ V - b, linsolve)                                  # src:394-395
-        b = rhs(V)                                                              # src:397-420
+        V, b = _damped_update(V, _solve(A, M @ V - b, linsolve), res, M, rhs, damping)   # src:394-420 (damping=0)
         newton += 1
     if trace is not None:
         trace.setdefault("newton_counts", []).append(newton)
@@ -441,15 +456,15 @@ def uvsolve(mesh, rec_mode, V, bddata, tau_p, tau_n, mu, n, u0, v0, linsolve="sp
 # G and solve_ddpe (src:596-601, src:630-658)
 # --------------------------------------------------------------------------------------------
 def G(mesh, rec_mode, u0, v0, delta, tau_p, tau_n, mu_p, mu_n, gD, n, MV, bdMV, ar, ubddata, vbddata, C, tol,
-      linsolve="sparse", trace=None):
-    V = Vsolve(mesh, u0, v0, delta, MV, bdMV, ar, n, gD, C, tol, linsolve, trace)                      # src:597
+      linsolve="sparse", trace=None, damping=0):
+    V = Vsolve(mesh, u0, v0, delta, MV, bdMV, ar, n, gD, C, tol, linsolve, trace, damping=damping)     # src:597
     u = uvsolve(mesh, rec_mode, V, ubddata, tau_p, tau_n, mu_p, n, u0, v0, linsolve, trace, "_u")      # src:598
     v = uvsolve(mesh, rec_mode, -V, vbddata, tau_n, tau_p, mu_n, n, v0, u0, linsolve, trace, "_v")     # src:599 (old u0)
     return u, v, V
 
 
 def solve_ddpe(mesh, rec_mode, Vbddata, ubddata, vbddata, lam, delta, tau_p, tau_n, mu_p, mu_n, C, tol=1e-9,
-               linsolve="sparse", trace=None, max_gummel=200, verbose=False):
+               linsolve="sparse", trace=None, max_gummel=200, verbose=False, damping=0):
     nq = mesh.nodes.shape[1]
     u = np.zeros(nq)
     v = np.zeros(nq)
@@ -465,7 +480,7 @@ def solve_ddpe(mesh, rec_mode, Vbddata, ubddata, vbddata, lam, delta, tau_p, tau
     while control > tol and count < max_gummel:                                 # src:649
         u0, v0, V0 = u, v, V
         u, v, V = G(mesh, rec_mode, u0, v0, delta, tau_p, tau_n, mu_p, mu_n, gD, n, MV, bdMV, ar,
-                    ubddata, vbddata, C, tol, linsolve, trace)                  # src:651
+                    ubddata, vbddata, C, tol, linsolve, trace, damping)         # src:651
         control = max(np.max(np.abs(u - u0)), np.max(np.abs(v - v0)), np.max(np.abs(V - V0)))   # src:653
         count += 1
         if trace is not None:
@@ -479,7 +494,7 @@ def solve_ddpe(mesh, rec_mode, Vbddata, ubddata, vbddata, lam, delta, tau_p, tau
 # solve_semlin_poisson (src:895-1097)
 # --------------------------------------------------------------------------------------------
 def solve_semlin_poisson(mesh, A, bddata, f, g, tol=1e-14, linsolve="sparse", trace=None, max_newton=200,
-                         verbose=False):
+                         verbose=False, damping=0):
     nq = mesh.nodes.shape[1]
     gtag = mesh.elements[4, :].astype(np.float64)
     ph11 = np.array([float(A[0](t)) for t in gtag])                             # src:901
@@ -530,8 +545,7 @@ def solve_semlin_poisson(mesh, A, bddata, f, g, tol=1e-14, linsolve="sparse", tr
         Aop = M - J0
         if trace is not None and "A_first" not in trace:
             trace["A_first"] = Aop.copy()
-        V = V - _solve(Aop, M @ V - b, linsolve)                                # src:1063-1064
-        b = rhs(V)
+        V, b = _damped_update(V, _solve(Aop, M @ V - b, linsolve), res, M, rhs, damping)   # src:1063-1089 (damping=0)
         count += 1
         if verbose:
             print(f"iteration {count}, tolerance: {np.max(np.abs(M @ V - b))}")  # src:1091-1093
