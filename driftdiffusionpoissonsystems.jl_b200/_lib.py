@@ -26,7 +26,7 @@ class SolverOpts(C.Structure):
                 ("max_newton", C.c_int32), ("max_gummel", C.c_int32), ("check_every", C.c_int32),
                 ("warm_start", C.c_int32), ("verbose", C.c_int32), ("lin_cap_ok", C.c_int32), ("no_alt_traversal", C.c_int32), ("warm_start_v", C.c_int32),
                 ("no_sym_scaling", C.c_int32), ("renumber", C.c_int32), ("precond", C.c_int32), ("amg_no_lag", C.c_int32),
-                ("newton_damping", C.c_int32)]
+                ("newton_damping", C.c_int32), ("reserved0", C.c_int32), ("lin_etol", C.c_double)]
 
 
 class Stats(C.Structure):

@@ -530,14 +530,16 @@ __global__ void k_apcg_init(int n, const double* __restrict__ rhs, const double*
 // in addition bring the energy norm of the error, estimated by r.z = r.Br ~ e.Ae, below rtol^2 * ||x||_A^2 (~ x0.rhs):
 // the residual of a smooth error (the Gummel update of the previous outer iteration) is far below rtol*||rhs|| long
 // before the error itself is, and a solve that returns its initial guess would end the Gummel loop early.
-__global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int warm) {
+__global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int warm, double eps_e) {
   scal->thresh2 = rtol * rtol * scal->bb;
   scal->thresh_inf = atol_inf;
   scal->thresh_e = 0.0;
   scal->warm = warm;
+  scal->eps_e2 = eps_e * eps_e;
   scal->iters = 0;
   scal->breakdown = 0;
-  if (warm) scal->done = (scal->rr == 0.0) ? 1 : 0;
+  // with the energy rule armed nothing is known about the error yet: only an exactly zero residual ends the solve here
+  if (warm || eps_e > 0.0) scal->done = (scal->rr == 0.0) ? 1 : 0;
   else scal->done = (scal->rr <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
   scal->conv = scal->done;   // every stop rule met (an exhausted iteration cap leaves it 0 -> DDPS_ERR_NOCONV)
 }
@@ -582,9 +584,10 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, in
       scal->iters = it + 1;
       // rz = r.Br of the residual BEFORE this update bounds the energy of the error after it (CG decreases it)
       const bool small_r = tot[0] <= scal->thresh2 || tot[1] <= scal->thresh_inf;
-      const bool small_e = !scal->warm || rz <= scal->thresh_e;
-      if (small_r && small_e) scal->conv = 1;
-      if ((small_r && small_e) || it + 1 >= max_it || !(tot[0] == tot[0])) scal->done = 1;
+      const bool small_e = !(scal->warm || scal->eps_e2 > 0.0) || rz <= scal->thresh_e;
+      const bool conv = (small_r && small_e) || tot[0] == 0.0;
+      if (conv) scal->conv = 1;
+      if (conv || it + 1 >= max_it || !(tot[0] == tot[0])) scal->done = 1;
     }
   }
 }
@@ -598,7 +601,13 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_direction(int n, int par,
   const double beta = first ? 0.0 : rz_new / scal->rz[par];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     scal->rz[first ? 0 : (par ^ 1)] = rz_new;
-    if (first) scal->thresh_e = rtol * rtol * fmax(fabs(scal->xb), rz_new);
+    if (first) {
+      // r0.Br0 ~ the energy of what this solve adds to x0; E_ref carries the largest one across the corrections of a Newton loop
+      const double eref = fmax(scal->e_ref, rz_new);
+      scal->e_ref = eref;
+      const double e2 = scal->eps_e2 > 0.0 ? scal->eps_e2 : rtol * rtol;
+      scal->thresh_e = e2 * fmax(fabs(scal->xb), eref);
+    }
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     p[i] = first ? z[i] : z[i] + beta * p[i];
@@ -1182,7 +1191,7 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
     DDPS_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), st));
     k_apcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, nullptr, ctx->r, ctx->partials, ctx->scal);
   }
-  k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf, x0_nonzero ? 1 : 0);
+  k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf, x0_nonzero ? 1 : 0, ctx->eps_e);
   if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;
   k_apcg_direction<<<g, kVecBlock, 0, st>>>(n, 0, 1, rtol, A.z, ctx->p, ctx->scal);
   ctx->stats.kernel_launches += 3;

@@ -46,9 +46,7 @@ void free_mesh(Context* ctx) {
   dev_free(ctx->Unew); dev_free(ctx->EH); dev_free(ctx->EHi); dev_free(ctx->E3); dev_free(ctx->gw);
   dev_free(ctx->b); dev_free(ctx->resid); dev_free(ctx->dinv); dev_free(ctx->x); dev_free(ctx->r); dev_free(ctx->q);
   dev_free(ctx->p); dev_free(ctx->partials);
-  if (ctx->halo.send_idx) { cudaFree(ctx->halo.send_idx); ctx->halo.send_idx = nullptr; }
-  if (ctx->halo.send_buf) { cudaFree(ctx->halo.send_buf); ctx->halo.send_buf = nullptr; }
-  ctx->halo.nneigh = 0; ctx->halo.peer.clear(); ctx->halo.send_off.clear(); ctx->halo.recv_off.clear(); ctx->halo.nsend = 0;
+  plan_free(ctx->halo);
   ctx->loc2glob.clear(); ctx->elem_glob.clear(); ctx->Dset.clear();
   ctx->have_mesh = false; ctx->base_ready = false; ctx->ddpe_active = false;
 }
@@ -408,6 +406,16 @@ int assemble_uv(Context* ctx, int which, int rec_mode, double tau_p, double tau_
   return launch_assemble_uv(ctx, a, RHS_ZERO, false);
 }
 
+// Relative A-norm error every linear solve of a Newton / Gummel loop must reach (PcgScalars::eps_e2): two orders below the
+// outer tolerance (the outer loops test ABSOLUTE max-norms of updates / residuals of O(1) fields, src:368,653,1040), at most
+// opts.lin_etol, and never below 1e-13 (what FP64 CG can resolve).  The reference's direct solves are exact to rounding;
+// a residual-only rule leaves smooth error components of size ||A^-1|| * tol ~ tol / h^2 behind.
+double energy_tol(const Context* ctx, double outer_tol) {
+  if (ctx->opts.lin_etol < 0.0) return 0.0;   // A/B: residual rules only
+  const double cap = ctx->opts.lin_etol > 0.0 ? ctx->opts.lin_etol : 1e-10;
+  return std::max(1e-13, std::min(cap, 0.01 * outer_tol));
+}
+
 struct EventTimer {
   Context* ctx;
   cudaEvent_t a, b;
@@ -441,6 +449,9 @@ int newton_loop(Context* ctx, bool semlin, double delta, double tol, const doubl
   };
   int count = 0;
   double res = 0.0;
+  // error-based stop rule of the corrections: relative to the energy of the LARGEST correction of this loop (~ the iterate's)
+  DDPS_CUDA(cudaMemsetAsync(&ctx->scal->e_ref, 0, sizeof(double), ctx->stream));
+  const double eps_e = energy_tol(ctx, tol);
   if ((rc = assemble(&res))) return rc;
   on_res(res, 0);
   while (res > tol) {                                                                        // src:368, 1040
@@ -454,9 +465,11 @@ int newton_loop(Context* ctx, bool semlin, double delta, double tol, const doubl
     // Newton correction: the linear residual only has to be below the Newton tolerance (so that, like the
     // reference's direct solve, a linear problem converges in one step); newton_eta is a relative floor.
     ctx->amg_kind = count == 0 ? 0 : 3;
+    ctx->eps_e = eps_e;
     rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
                       ctx->opts.lin_max_it, nullptr, nullptr);                               // src:394, 1063
     ctx->amg_kind = -1;
+    ctx->eps_e = 0.0;
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
     if (rc) return rc;
@@ -502,9 +515,12 @@ int uvsolve(Context* ctx, int which) {
   double* field = (which == DDPS_FIELD_U) ? ctx->U : ctx->W;
   EventTimer tp(ctx, ctx->ev2, ctx->ev3);
   ctx->amg_kind = (which == DDPS_FIELD_U) ? 1 : 2;
+  DDPS_CUDA(cudaMemsetAsync(&ctx->scal->e_ref, 0, sizeof(double), ctx->stream));
+  ctx->eps_e = energy_tol(ctx, ctx->tol);
   rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->b, field, ctx->opts.warm_start != 0, ctx->opts.lin_rtol, 0.0,
                  ctx->opts.lin_max_it, nullptr, nullptr);                                     // src:588
   ctx->amg_kind = -1;
+  ctx->eps_e = 0.0;
   tp.stop();
   ctx->stats.t_pcg_ms += tp.ms();
   ctx->stats.t_asm_ms += ta.ms();
@@ -553,6 +569,7 @@ void ddps_default_opts(ddps_solver_opts* o) {
   o->check_every = 32;
   o->warm_start = 1;
   o->verbose = 0;
+  o->lin_etol = 1e-10;
 }
 
 int ddps_ctx_create(ddps_ctx** out, int device) {
@@ -743,6 +760,7 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
     HaloPlan& H = ctx->halo;
     H.nneigh = (int)L.peers.size(); H.peer = L.peers; H.send_off = L.send_off; H.recv_off = L.recv_off;
     H.nsend = (int)L.send_idx.size();
+    H.n_own = L.n_own; H.n_ghost = L.n_loc - L.n_own;
     if ((rc = dev_alloc(ctx, &H.send_idx, L.send_idx.size()))) return rc;
     if ((rc = dev_alloc(ctx, &H.send_buf, L.send_idx.size()))) return rc;
     if ((rc = upload(ctx, H.send_idx, L.send_idx.data(), L.send_idx.size()))) return rc;

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -94,17 +95,35 @@ struct PcgScalars {
   double thresh_e;  // stop only when r.Br <= thresh_e
   double xb;        // x0.rhs ~ ||x||_A^2
   int warm;
-  int conv;         // multigrid-preconditioned CG: 1 once every stop rule is met (0 after an exhausted iteration cap)
+  int conv;         // 1 once every stop rule is met (0 after an exhausted iteration cap)
+  // error-based stop rule (both preconditioners): the A-norm of the error must fall below eps_e * sqrt(E_ref), E_ref = the
+  // largest solution energy seen (x0.rhs of a warm start, the energy of the largest Newton correction of the running
+  // Newton loop).  Multigrid path: r.Br ~ e.Ae directly.  Jacobi path: Hestenes-Stiefel estimate, the energy the last
+  // hs_d updates added, sum alpha_j r_j.z_j (= ||x_k - x_{k-d}||_A^2 <= ||x - x_{k-d}||_A^2).
+  double eps_e2;    // eps_e^2 (0: rule off)
+  double e_ref;     // reference energy carried across the solves of one Newton loop
+  double hs_total;  // energy added so far in this solve
+  double hs_ring[32];
+  int hs_d;
+  int pad2;
 };
+constexpr int kHsDelay = 32;
 
-// ---- peer-memory (NVLink P2P via CUDA IPC) windows for the fused halo push + scalar allreduce ----
+// ---- peer-memory (NVLink P2P via CUDA IPC) windows ---------------------------------------------------------------------
+// Two users: (a) the Jacobi-PCG iteration pushes the halo of p and exchanges its dot products from INSIDE its three kernels
+// (halo_flag / redA / redB; kernels.cu); (b) the generic staged exchange every other vector of every multigrid level goes
+// through (xflag + the staging buffers) and the generic scalar allreduce (rflag / rval) -- one tiny kernel each, so no full
+// grid ever spins on a peer (comm.cu).
 constexpr int kMaxRanks = 8;
 struct P2PWin {                                  // one per rank, written by the peers
-  unsigned long long halo_flag[kMaxRanks];       // [src] tag of the last halo src pushed into my ghost block
+  unsigned long long halo_flag[kMaxRanks];       // [src] tag of the last halo src pushed into my ghost block (Jacobi path)
   unsigned long long redA_flag[kMaxRanks];       // [src] tag of src's p.Ap partial
   unsigned long long redB_flag[kMaxRanks];       // [src] tag of src's {r.z, r.r, max|r|} partials
   double redA[kMaxRanks][4];
   double redB[kMaxRanks][4];
+  unsigned long long xflag[kMaxRanks];           // [src] tag of the last staged halo block src wrote into my staging buffer
+  unsigned long long rflag[2][kMaxRanks];        // generic scalar allreduce, double-buffered by tag parity
+  double rval[2][kMaxRanks][4];
   int error;
   int pad;
 };
@@ -122,24 +141,40 @@ struct PushArgs {
   unsigned long long tag;
 };
 struct P2PHost {
-  bool enabled = false;
+  bool enabled = false;                          // (a) fused Jacobi-PCG path
+  bool xenabled = false;                         // (b) staged exchange + scalar allreduce
   P2PWin* win_local = nullptr;
   P2PWin* win_peer[kMaxRanks] = {nullptr};
   double* p_peer[kMaxRanks] = {nullptr};
+  double* stage_local = nullptr;                 // [2][stage_cap] receive staging, double-buffered by tag parity
+  double* stage_peer[kMaxRanks] = {nullptr};
+  size_t stage_cap = 0;
+  bool ipc = false;                              // peer pointers are IPC mappings (to be closed), not in-process pointers
   PushArgs push;
   P2PDev dev;
-  unsigned long long tag = 0;
+  unsigned long long tag = 0, xtag = 0, rtag = 0;
 };
 
+// halo plan of one level: owned entries first, ghosts grouped by owner; the send list to peer q is exactly q's ghost block
+// for me, in the same order
 struct HaloPlan {
+  int n_own = 0, n_ghost = 0;
   int nneigh = 0;
   std::vector<int> peer;        // neighbour ranks
   std::vector<int> send_off;    // [nneigh+1] offsets into send_idx
   std::vector<int> recv_off;    // [nneigh+1] offsets into the ghost block (relative to n_own)
+  std::vector<int> remote_off;  // [nneigh] offset of my block inside the peer's ghost block (= its staging offset)
   int* send_idx = nullptr;      // device: local owned ids to pack, grouped by neighbour
   double* send_buf = nullptr;   // device
   int nsend = 0;
+  bool p2p = false;             // staged peer-memory exchange usable for this plan (every rank agrees)
 };
+
+// communication backends: NCCL (one process per GPU) or an in-process group (ranks = host threads sharing one device; lets
+// the whole distributed logic run, and be tested, on a single GPU)
+struct LocalGroup;
+enum { COMM_SUM = 0, COMM_MAX = 1, COMM_MIN = 2 };
+struct CommMsg { int peer; const void* send; size_t send_bytes; void* recv; size_t recv_bytes; };
 
 struct Amg;   // amg.cu: device-side smoothed-aggregation hierarchy
 
@@ -158,6 +193,7 @@ struct Context {
 #ifdef DDPS_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
+  std::shared_ptr<LocalGroup> lgroup;   // in-process communicator (ddps_comm_init with a "LOCAL:<name>" id)
   HaloPlan halo;
   P2PHost p2p;
 
@@ -218,6 +254,7 @@ struct Context {
   std::vector<double> hist_outer, hist_newton, hist_pcg;
 
   // optional multigrid preconditioner (opts.precond == DDPS_PRECOND_AMG, single GPU)
+  double eps_e = 0.0;  // energy-norm stop tolerance of the NEXT solve_system call (0: residual rules only)
   Amg* amg = nullptr;
   int amg_kind = -1;   // which kind of operator the next solve_system call handles (amg_numeric: lagged coarse operators)
 
@@ -320,9 +357,24 @@ int amg_debug_get_level(Context* ctx, int level, int64_t* sizes, int64_t* rowptr
                         double* Pval);
 
 // ---- comm.cu ----
-int halo_exchange(Context* ctx, double* vec);            // fill ghost part of a [n_loc] vector
+int halo_exchange(Context* ctx, double* vec);            // fill ghost part of a [n_loc] vector (finest level's plan)
 int allreduce_sum(Context* ctx, double* dev, int count); // in place on the library stream
 int allreduce_max(Context* ctx, double* dev, int count);
+// backend primitives (NCCL or in-process): grouped point-to-point exchange of device buffers on the library stream, allreduce of
+// device doubles, allgather of small host structs (blocking)
+int comm_exchange(Context* ctx, const CommMsg* msgs, int n);
+int comm_allreduce(Context* ctx, double* dev, size_t count, int op);
+int comm_allgather_host(Context* ctx, const void* mine, size_t bytes, void* all);
+// halo exchange on any level's plan: staged peer-memory kernel when plan.p2p, else pack + comm_exchange.  check_done: the
+// kernel early-exits once the running solve's `done` flag is up (identical on all ranks)
+int halo_xchg(Context* ctx, HaloPlan& plan, double* vec, bool check_done);
+int halo_exchange_bytes(Context* ctx, const HaloPlan& plan, void* vec, size_t elem);   // setup: any element size, backend exchange
+// in-place allreduce of nsum sums followed by nmax maxima (nsum + nmax <= 4) living at `dev_vals`: one tiny peer-memory
+// kernel, or backend allreduces
+int scalar_allreduce(Context* ctx, double* dev_vals, int nsum, int nmax, bool check_done);
+int plan_finish(Context* ctx, HaloPlan& plan);   // collective: remote offsets + agree on peer-memory use
+void plan_free(HaloPlan& plan);
+int p2p_check_error(Context* ctx);               // raise DDPS_ERR_COMM if a peer-memory wait timed out since the last check
 int comm_init(Context* ctx, const char* id128, int rank, int nranks);
 int comm_unique_id(char* id128);
 void comm_destroy(Context* ctx);

@@ -678,12 +678,13 @@ int fetch_resid_norm(Context* ctx, double* host_out) { return launch_max_abs(ctx
 // Jacobi-preconditioned CG (K9), all control flow on the device
 // ------------------------------------------------------------------------------------------------
 // r = rhs - q (q = A*x0) or r = rhs;  p = dinv*r;  local sums {r.z, r.r, rhs.rhs}
+// (x0 = the initial guess when HAVE_Q: x0.rhs ~ ||x||_A^2 is the reference energy of the error-based stop rule)
 template <bool HAVE_Q>
-__global__ void k_pcg_init(int n, const double* __restrict__ rhs, const double* __restrict__ q,
+__global__ void k_pcg_init(int n, const double* __restrict__ rhs, const double* __restrict__ q, const double* __restrict__ x0,
                            const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
                            double* partials, PcgScalars* scal) {
   __shared__ double sh_red[32];
-  double s_rz = 0.0, s_rr = 0.0, s_bb = 0.0, s_max = 0.0;
+  double s_rz = 0.0, s_rr = 0.0, s_bb = 0.0, s_xb = 0.0, s_max = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double bi = rhs[i];
     const double ri = HAVE_Q ? bi - q[i] : bi;
@@ -691,27 +692,34 @@ __global__ void k_pcg_init(int n, const double* __restrict__ rhs, const double* 
     r[i] = ri;
     p[i] = zi;
     s_rz += ri * zi; s_rr += ri * ri; s_bb += bi * bi;
+    if (HAVE_Q) s_xb += x0[i] * bi;
     s_max = fmax(s_max, fabs(ri));
   }
-  double v[3] = {s_rz, s_rr, s_bb}, tot[3];
-  const bool last = grid_reduce<3, false>(v, partials, &scal->cnt[1], sh_red, tot);
-  if (last && threadIdx.x == 0) { scal->sums[0] = tot[0]; scal->sums[1] = tot[1]; scal->sums[2] = tot[2]; }
+  double v[4] = {s_rz, s_rr, s_bb, s_xb}, tot[4];
+  const bool last = grid_reduce<4, false>(v, partials, &scal->cnt[1], sh_red, tot);
+  if (last && threadIdx.x == 0) { scal->sums[0] = tot[0]; scal->sums[1] = tot[1]; scal->sums[2] = tot[2]; scal->sums[3] = tot[3]; }
   double vm[1] = {s_max}, totm[1];
-  if (grid_reduce<1, true>(vm, partials + 3 * gridDim.x, &scal->cnt[2], sh_red, totm)) {
+  if (grid_reduce<1, true>(vm, partials + 4 * gridDim.x, &scal->cnt[2], sh_red, totm)) {
     if (threadIdx.x == 0) scal->rmax = totm[0];
   }
 }
 
 // stop rule: ||r||_2 <= rtol*||rhs||_2  OR  ||r||_inf <= atol_inf
-__global__ void k_pcg_start(PcgScalars* scal, double rtol, double atol_inf) {
+__global__ void k_pcg_start(PcgScalars* scal, double rtol, double atol_inf, double eps_e) {
   scal->rz[0] = scal->sums[0];
   scal->rr = scal->sums[1];
   scal->bb = scal->sums[2];
+  scal->xb = scal->sums[3];
   scal->thresh2 = rtol * rtol * scal->sums[2];
   scal->thresh_inf = atol_inf;
+  scal->eps_e2 = eps_e * eps_e;
+  scal->hs_total = 0.0;
+  scal->hs_d = kHsDelay;
   scal->iters = 0;
   scal->breakdown = 0;
-  scal->done = (scal->sums[1] <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
+  if (eps_e > 0.0) scal->done = (scal->sums[1] == 0.0) ? 1 : 0;   // error rule armed: only a zero residual ends the solve here
+  else scal->done = (scal->sums[1] <= scal->thresh2 || scal->rmax <= atol_inf) ? 1 : 0;
+  scal->conv = scal->done;
 }
 
 // x += alpha p; r -= alpha q; partial sums {r.D^-1 r, r.r, max|r|}
@@ -786,13 +794,34 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, 
     rz_new = scal->sums[1]; rr = scal->sums[2]; rmax = scal->rmax;
   }
   const double rz_old = scal->rz[par];
-  const bool stop = (rr <= scal->thresh2) || (rmax <= scal->thresh_inf) || (it + 1 >= max_it) || !(rr == rr) || !comm_ok;
+  const bool small_r = (rr <= scal->thresh2) || (rmax <= scal->thresh_inf);
+  // error-based rule (Hestenes-Stiefel): the energy the last hs_d updates added, sum_j alpha_j r_j.z_j = ||x_k - x_{k-d}||_A^2,
+  // a lower bound of ||x - x_{k-d}||_A^2, must be below eps_e^2 * E_ref.  Every block evaluates it from the ring the earlier
+  // launches wrote + this iteration's own term (identical everywhere); block 0 alone stores.
+  bool small_e = true;
+  double hs_term = 0.0, hs_tot = 0.0;
+  if (scal->eps_e2 > 0.0) {
+    const int d = scal->hs_d;
+    hs_term = rz_old * (rz_old / scal->sums[0]);   // alpha * r.z, alpha = r.z / p.Ap
+    hs_tot = scal->hs_total + hs_term;
+    double est = hs_term;
+    for (int j = 1; j < d; ++j) est += (it - j >= 0) ? scal->hs_ring[(it - j) % d] : 0.0;
+    small_e = (it + 1 >= d) && est <= scal->eps_e2 * fmax(fmax(scal->e_ref, fabs(scal->xb)), hs_tot);
+  }
+  const bool conv = (small_r && small_e) || rr == 0.0;
+  const bool stop = conv || (it + 1 >= max_it) || !(rr == rr) || !comm_ok;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     scal->rz[par ^ 1] = rz_new;
     scal->rmax = rmax;
     if (!comm_ok) scal->breakdown = 2;
     scal->rr = rr;
     scal->iters = it + 1;
+    if (scal->eps_e2 > 0.0) {
+      scal->hs_ring[it % scal->hs_d] = hs_term;
+      scal->hs_total = hs_tot;
+      if (stop) scal->e_ref = fmax(scal->e_ref, hs_tot);   // later corrections of the same Newton loop refer to the largest one
+    }
+    if (conv) scal->conv = 1;
     if (stop) scal->done = 1;
   }
   if (stop) return;
@@ -965,14 +994,14 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
     DDPS_CUDA(cudaMemcpyAsync(ctx->p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = halo_exchange(ctx, ctx->p))) return rc;
     if ((rc = launch_spmv(ctx, val, ctx->p, ctx->q))) return rc;
-    k_pcg_init<true><<<g, kVecBlock, 0, st>>>(n, rhs, ctx->q, dinv, ctx->r, ctx->p, ctx->partials, ctx->scal);
+    k_pcg_init<true><<<g, kVecBlock, 0, st>>>(n, rhs, ctx->q, x, dinv, ctx->r, ctx->p, ctx->partials, ctx->scal);
   } else {
     DDPS_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), st));
-    k_pcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, dinv, ctx->r, ctx->p, ctx->partials, ctx->scal);
+    k_pcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, nullptr, dinv, ctx->r, ctx->p, ctx->partials, ctx->scal);
   }
-  if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 3))) return rc;
+  if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 4))) return rc;
   if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
-  k_pcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf);
+  k_pcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf, ctx->eps_e);
   ctx->stats.kernel_launches += 2;
   DDPS_CUDA(cudaGetLastError());
 
@@ -1002,7 +1031,7 @@ int pcg_solve(Context* ctx, const double* val, const double* dinv, const double*
     ctx->fail(DDPS_ERR_BREAKDOWN, "PCG breakdown: p.Ap <= 0 (operator not SPD; u or v negative? SURVEY H3)");
     return DDPS_ERR_BREAKDOWN;
   }
-  if (!(S.rr <= S.thresh2 || S.rmax <= S.thresh_inf) && !ctx->opts.lin_cap_ok) {
+  if (!S.conv && !ctx->opts.lin_cap_ok) {
     ctx->fail(DDPS_ERR_NOCONV, "PCG hit the iteration cap (" + std::to_string(S.iters) + " its, relres " +
                                    std::to_string(S.bb > 0 ? sqrt(S.rr / S.bb) : 0.0) + ")");
     return DDPS_ERR_NOCONV;

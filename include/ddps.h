@@ -122,6 +122,14 @@ typedef struct ddps_solver_opts {
                            1063-1064).  k > 0: the Newton step of Vsolve / solve_semlin_poisson is halved, at most k times,
                            until the residual max-norm ||M*V - b(V)||_inf (the quantity the loops test, src:368,1040) decreases.
                            Changes the iteration history only when a full step would increase the residual */
+  int32_t reserved0;
+  double lin_etol;      /* error-based stop rule of every linear solve inside the Newton / Gummel loops, on top of the residual
+                           rules above: the A-norm of the error (multigrid path: r.Br; Jacobi path: Hestenes-Stiefel estimate
+                           over the last 32 updates) must fall below eps * sqrt(E), E = the energy of the solution (x0.b of a
+                           warm start / the largest Newton correction of the running loop), eps = max(1e-13, min(lin_etol,
+                           0.01*tol)).  Default 1e-10; < 0 switches the rule off (residual rules only).  The reference's
+                           direct solves are exact to rounding; a residual-only rule leaves an error ~ tol/h^2 behind, which
+                           breaks the 1e-8 field parity on large meshes */
 } ddps_solver_opts;
 
 #define DDPS_PRECOND_JACOBI 0

@@ -60,7 +60,7 @@ def test_ddpe_diode_262k_triangles_vs_oracle(D, O):
             assert rel_l2(a, b) <= FIELD_TOL, (opts, name, rel_l2(a, b))
         assert st["outer_iters"] == len(tr["control"]), (opts, st["outer_iters"], len(tr["control"]))
         assert [int(k) for k in st["newton_per_vsolve"]] == tr["newton_counts"], opts
-        assert np.allclose(st["control_history"], tr["control"], rtol=1e-3, atol=1e-11), opts
+        assert np.allclose(st["control_history"], tr["control"], rtol=1e-2, atol=1e-11), opts
 
 
 def test_config4_16M_triangles_amg_vs_jacobi_to_tol(D):
