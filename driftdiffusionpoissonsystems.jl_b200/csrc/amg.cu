@@ -519,10 +519,8 @@ __global__ void k_apcg_init(int n, const double* __restrict__ rhs, const double*
   }
   double v[4] = {s_rr, s_bb, s_xb, s_max}, tot[4];
   if (grid_reduce_mixed<4, 8u>(v, partials, &scal->cnt[1], sh_red, tot)) {
-    if (threadIdx.x == 0) {
-      scal->rr = tot[0]; scal->bb = tot[1]; scal->xb = tot[2]; scal->rmax = tot[3];
-      scal->sums[2] = tot[0];
-    }
+    if (threadIdx.x == 0) { scal->sums[0] = tot[0]; scal->sums[1] = tot[1]; scal->sums[2] = tot[2]; scal->sums[3] = tot[3]; }
+    // (this rank's part; multi-rank contexts allreduce sums[0..3] -- three sums and a maximum -- before k_apcg_start)
   }
 }
 
@@ -531,6 +529,7 @@ __global__ void k_apcg_init(int n, const double* __restrict__ rhs, const double*
 // the residual of a smooth error (the Gummel update of the previous outer iteration) is far below rtol*||rhs|| long
 // before the error itself is, and a solve that returns its initial guess would end the Gummel loop early.
 __global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int warm, double eps_e) {
+  scal->rr = scal->sums[0]; scal->bb = scal->sums[1]; scal->xb = scal->sums[2]; scal->rmax = scal->sums[3];
   scal->thresh2 = rtol * rtol * scal->bb;
   scal->thresh_inf = atol_inf;
   scal->thresh_e = 0.0;
@@ -547,6 +546,25 @@ __global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int
 // x += alpha p; r -= alpha q; the block that finishes last takes the convergence decision, so that the cycle
 // kernels behind it exit immediately once the residual is small enough.
 // Fused: xs = om * dinv * r, the first damped-Jacobi sweep of the V-cycle on the finest level (saves a pass over r).
+// The convergence decision from the (global) sums {r.r, max|r|}: by the last block of k_apcg_update on one rank, by the
+// one-thread kernel k_apcg_decide after the allreduce in multi-rank contexts (identical on every rank).
+__device__ __forceinline__ void apcg_decide(PcgScalars* scal, double rr, double rmax, double rz, int it, int max_it) {
+  scal->rr = rr;
+  scal->rmax = rmax;
+  scal->iters = it + 1;
+  // rz = r.Br of the residual BEFORE this update bounds the energy of the error after it (CG decreases it)
+  const bool small_r = rr <= scal->thresh2 || rmax <= scal->thresh_inf;
+  const bool small_e = !(scal->warm || scal->eps_e2 > 0.0) || rz <= scal->thresh_e;
+  const bool conv = (small_r && small_e) || rr == 0.0;
+  if (conv) scal->conv = 1;
+  if (conv || it + 1 >= max_it || !(rr == rr)) scal->done = 1;
+}
+__global__ void k_apcg_decide(PcgScalars* scal, int par, int it, int max_it) {
+  if (scal->done) return;
+  apcg_decide(scal, scal->sums[2], scal->sums[3], scal->rz[par], it, max_it);
+}
+
+template <bool DECIDE>
 __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, int it, int max_it,
                                                            const double* __restrict__ p, const double* __restrict__ q,
                                                            double* __restrict__ x, double* __restrict__ r,
@@ -579,15 +597,8 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, in
   double v[2] = {s_rr, s_max}, tot[2];
   if (grid_reduce_mixed<2, 2u>(v, partials, &scal->cnt[1], sh_red, tot)) {
     if (threadIdx.x == 0) {
-      scal->rr = tot[0];
-      scal->rmax = tot[1];
-      scal->iters = it + 1;
-      // rz = r.Br of the residual BEFORE this update bounds the energy of the error after it (CG decreases it)
-      const bool small_r = tot[0] <= scal->thresh2 || tot[1] <= scal->thresh_inf;
-      const bool small_e = !(scal->warm || scal->eps_e2 > 0.0) || rz <= scal->thresh_e;
-      const bool conv = (small_r && small_e) || tot[0] == 0.0;
-      if (conv) scal->conv = 1;
-      if (conv || it + 1 >= max_it || !(tot[0] == tot[0])) scal->done = 1;
+      if (DECIDE) apcg_decide(scal, tot[0], tot[1], rz, it, max_it);
+      else { scal->sums[2] = tot[0]; scal->sums[3] = tot[1]; }
     }
   }
 }
@@ -629,6 +640,9 @@ void amg_free(Context* ctx) {
     amg_release(L.Rptr); amg_release(L.Rent);
     if (l > 0) { amg_release(L.b); amg_release(L.x2); }
     amg_release(L.x); amg_release(L.t);
+    amg_release(L.glob); amg_release(L.ap_send_pos); amg_release(L.ap_send_buf);
+    if (L.owns_plan && L.plan) { plan_free(*L.plan); delete L.plan; }
+    L.plan = nullptr;
   }
   amg_release(A->dense);
   amg_release(A->z);
@@ -643,10 +657,11 @@ void amg_free(Context* ctx) {
 }
 
 // upload helpers of the host-built part of the hierarchy
-static int amg_install_pattern(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL) {
+int amg_install_pattern(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL) {
   int rc;
   L = AmgLevelDev();
   L.n = HL.n;
+  L.n_loc = HL.n;
   L.nnz = (int64_t)HL.col.size();
   // SELL-32 layout of the coarse pattern (same convention as the fine pattern: padding = value 0, own column)
   L.nslices = (HL.n + 31) / 32;
@@ -678,7 +693,7 @@ static int amg_install_pattern(Context* ctx, AmgLevelDev& L, const AmgHostLevel&
   return 0;
 }
 
-static int amg_install_transfers(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL) {
+int amg_install_transfers(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL) {
   int rc;
   L.nc = HL.nc;
   std::vector<int2> pe(HL.Pcol.size()), re(HL.Rrow.size());
@@ -700,9 +715,57 @@ static int amg_install_transfers(Context* ctx, AmgLevelDev& L, const AmgHostLeve
 // coarsened on the device (amg_setup.cu: only the strong-neighbour lists travel to the host for the greedy
 // aggregation); the small rest of the hierarchy is built by the host reference implementation (amg_host.cu) and
 // uploaded.  DDPS_AMG_HOST_SETUP=1 forces the host path for every level (A/B and fallback).
+static int amg_finish_setup(Context* ctx, Amg* A, int nlev, double t0);
+
+// Multi-rank contexts: distributed coarsening (amg_setup.cu: amg_dist_coarsen) while the level has more than DDPS_AMG_TAIL
+// rows in total (default 200000), then the transition to the replicated rest of the hierarchy (amg_dist_transition).
+static int amg_setup_dist(Context* ctx) {
+  const double t0 = wall_ms();
+  const Pattern& P = ctx->pat;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  AmgParams prm;
+  const long long tail = getenv("DDPS_AMG_TAIL") ? atoll(getenv("DDPS_AMG_TAIL")) : 200000;
+  const bool timing = getenv("DDPS_AMG_TIMING") != nullptr;
+  Amg* A = new Amg();
+  ctx->amg = A;
+  A->omega = prm.omega;
+  int rc;
+  {
+    AmgLevelDev& L = A->lv[0];
+    L.n = P.nrows; L.n_loc = ctx->n_loc; L.nnz = P.nnz; L.nslices = P.nslices; L.nentries = P.nentries; L.wmax = P.max_row_len;
+    L.slice_ptr = P.slice_ptr; L.col = P.col; L.rowptr = P.rowptr; L.owns = false;
+    L.cur_val = ctx->val_base;
+    L.plan = &ctx->halo; L.owns_plan = false;
+  }
+  long long ng = ctx->nq_global;
+  int l = 0, nlev = 0;
+  while (true) {
+    if (ng > tail && l + 2 < prm.max_levels) {
+      long long ncg = 0;
+      const double ta = wall_ms();
+      rc = amg_dist_coarsen(ctx, A, l, prm, &ncg);
+      if (rc < 0) return rc;
+      if (rc > 0 || ncg == 0) { amg_free(ctx); return 0; }   // does not apply / stalled: Jacobi-PCG stays (same decision on all ranks)
+      if (timing && ctx->rank == 0)
+        fprintf(stderr, "[ddps amg] distributed level %d: %lld -> %lld rows (rank 0: %d -> %d owned, %d ghost columns): %.1f ms\n", l, ng, ncg,
+                A->lv[l].n, A->lv[l + 1].n, A->lv[l + 1].n_loc - A->lv[l + 1].n, wall_ms() - ta);
+      ng = ncg;
+      ++l;
+      continue;
+    }
+    const double ta = wall_ms();
+    if ((rc = amg_dist_transition(ctx, A, l, prm, &nlev))) return rc;
+    if (timing && ctx->rank == 0) fprintf(stderr, "[ddps amg] transition at level %d (%lld rows gathered), %d levels in all: %.1f ms\n", l, ng, nlev, wall_ms() - ta);
+    break;
+  }
+  if (nlev < 2 || A->lv[nlev - 1].n > kAmgDenseMax) { amg_free(ctx); return 0; }
+  return amg_finish_setup(ctx, A, nlev, t0);
+}
+
 int amg_setup(Context* ctx) {
   amg_free(ctx);
-  if (ctx->nranks != 1 || !ctx->base_ready) return 0;   // multi-GPU: the Jacobi path stays in charge
+  if (!ctx->base_ready) return 0;
+  if (ctx->nranks != 1) return amg_setup_dist(ctx);
   const double t0 = wall_ms();
   const Pattern& P = ctx->pat;
   const int n = P.nrows;
@@ -782,26 +845,40 @@ int amg_setup(Context* ctx) {
   }
   const double t2 = wall_ms();
   if (nlev < 2 || A->lv[nlev - 1].n > kAmgDenseMax) { amg_free(ctx); return 0; }   // no hierarchy: Jacobi-PCG stays
+  return amg_finish_setup(ctx, A, nlev, t0);
+}
+
+// cycle vectors, fp32 copies, coarsest inverse (vectors of distributed levels carry their ghost entries)
+static int amg_finish_setup(Context* ctx, Amg* A, int nlev, double t0) {
+  int rc;
   A->nlev = nlev;
   const bool cycle_fp32 = getenv("DDPS_AMG_FP64_CYCLE") == nullptr;   // A/B switch: keep the cycle's matrices in FP64
   const int fp32_min = getenv("DDPS_AMG_FP32_MIN") ? atoi(getenv("DDPS_AMG_FP32_MIN")) : 50000;   // (tests lower it)
   for (int l = 0; l < nlev; ++l) {
     AmgLevelDev& L = A->lv[l];
+    if (L.n_loc < L.n) L.n_loc = L.n;
     if (cycle_fp32 && L.n > fp32_min && (rc = amg_alloc(ctx, &L.val32, (size_t)L.nentries))) return rc;
-    if ((rc = amg_alloc(ctx, &L.x, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.t, (size_t)L.n))) return rc;
-    if (l >= 1 && ((rc = amg_alloc(ctx, &L.b, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.x2, (size_t)L.n)))) return rc;
+    if ((rc = amg_alloc(ctx, &L.x, (size_t)L.n_loc)) || (rc = amg_alloc(ctx, &L.t, (size_t)L.n_loc))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(L.x, 0, std::max<size_t>((size_t)L.n_loc, 1) * sizeof(double), ctx->stream));
+    DDPS_CUDA(cudaMemsetAsync(L.t, 0, std::max<size_t>((size_t)L.n_loc, 1) * sizeof(double), ctx->stream));
+    if (l >= 1) {
+      if ((rc = amg_alloc(ctx, &L.b, (size_t)L.n)) || (rc = amg_alloc(ctx, &L.x2, (size_t)L.n_loc))) return rc;
+      DDPS_CUDA(cudaMemsetAsync(L.x2, 0, std::max<size_t>((size_t)L.n_loc, 1) * sizeof(double), ctx->stream));
+    }
   }
   const int nL = A->lv[nlev - 1].n;
   if ((rc = amg_alloc(ctx, &A->dense, (size_t)nL * nL))) return rc;
   DDPS_CUDA(cudaFuncSetAttribute(k_amg_dense_inverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kAmgDenseShared * kAmgDenseShared * (int)sizeof(double)));
-  if ((rc = amg_alloc(ctx, &A->z, (size_t)n))) return rc;
+  if ((rc = amg_alloc(ctx, &A->z, (size_t)A->lv[0].n))) return rc;
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   A->ready = true;
   A->setup_ms = wall_ms() - t0;
-  if (timing)
-    fprintf(stderr, "[ddps amg] setup %.1f ms: device levels %.1f (%d), host levels + uploads %.1f, vectors %.1f\n", A->setup_ms, t1 - t0,
-            ld, t2 - t1, wall_ms() - t2);
+  if (getenv("DDPS_AMG_TIMING") && ctx->rank == 0) {
+    fprintf(stderr, "[ddps amg] setup %.1f ms, levels (rows owned by rank 0):", A->setup_ms);
+    for (int l = 0; l < nlev; ++l) fprintf(stderr, " %d%s", A->lv[l].n, A->lv[l].dist == 1 ? "d" : A->lv[l].dist == 2 ? "t" : "");
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 
@@ -897,9 +974,40 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_amg_change(int nrows, int nsli
   }
 }
 
-void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv) {
+// inverse diagonal from the (completed) values of a level
+__global__ void k_amg_dinv(int n, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                           const double* __restrict__ val, double* __restrict__ dinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int len = rowptr[i + 1] - rowptr[i];
+  const int base = slice_ptr[i >> 5] + (i & 31);
+  for (int k = 0; k < len; ++k)
+    if (col[base + 32 * k] == i) dinv[i] = 1.0 / val[base + 32 * k];
+}
+
+static int amg_launch_rap_impl(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv);
+
+int amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv) {
+  int rc = amg_launch_rap_impl(ctx, F, f_val, C, out_val, out_dinv);
+  if (rc) return rc;
+  if (F.dist == 2) {
+    // transition level: every rank summed over ITS fine rows only; the replicated coarse operator is the sum over the ranks
+    if ((rc = comm_allreduce(ctx, out_val, (size_t)C.nentries, COMM_SUM))) return rc;
+    k_amg_dinv<<<(C.n + 255) / 256, 256, 0, ctx->stream>>>(C.n, C.rowptr, C.slice_ptr, C.col, out_val, out_dinv);
+    ctx->stats.kernel_launches++;
+  }
+  return 0;
+}
+
+static int amg_launch_rap_impl(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv) {
   if (F.APptr) {   // two-stage product
-    k_amg_ap<<<(F.n + 127) / 128, 128, 0, ctx->stream>>>(F.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.APptr, F.APcol, F.APval);
+    if (F.n) k_amg_ap<<<(F.n + 127) / 128, 128, 0, ctx->stream>>>(F.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.APptr, F.APcol, F.APval);
+    // distributed level: the A*P rows of the neighbours' boundary rows (my ghost rows) arrive by one exchange of values
+    if (F.dist == 1) {
+      int rc = amg_dist_ap_halo(ctx, const_cast<AmgLevelDev&>(F));
+      if (rc) return rc;
+    }
+    if (C.n == 0) { ctx->stats.kernel_launches++; return 0; }
     if (C.wmax <= 16) {
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 6));
       k_amg_rap_ap<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.Rptr, F.Rent, F.APptr, F.APcol, F.APval, C.rowptr, C.slice_ptr, C.col, out_val,
@@ -914,8 +1022,9 @@ void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, con
                                                         out_dinv);
     }
     ctx->stats.kernel_launches += 2;
-    return;
+    return 0;
   }
+  if (F.dist) { ctx->fail(DDPS_ERR_STATE, "distributed multigrid level without an A*P pattern"); return DDPS_ERR_STATE; }
   if (C.wmax <= 16) {   // short coarse rows: small private tables, more resident warps per SM
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)C.n + 7) / 8, (int64_t)ctx->num_sms * 5));
     k_amg_rap2<16, 8><<<grid, 256, 0, ctx->stream>>>(C.n, F.slice_ptr, F.col, f_val, F.Pptr, F.Pent, F.Rptr, F.Rent, C.rowptr,
@@ -930,6 +1039,7 @@ void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, con
                                                     C.slice_ptr, C.col, out_val, out_dinv);
   }
   ctx->stats.kernel_launches++;
+  return 0;
 }
 
 // The per-kind copies come from the stream-ordered pool (only the library stream touches them): when lagging is armed, a
@@ -973,6 +1083,7 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind) {
     k_amg_change<<<amg_grid(ctx, (int64_t)L0.nslices * 32, kVecBlock), kVecBlock, 0, ctx->stream>>>(L0.n, L0.nslices, L0.slice_ptr, val, S->snap,
                                                                                                ctx->partials, ctx->scal);
     ctx->stats.kernel_launches++;
+    if ((rc = scalar_allreduce(ctx, ctx->scal->sums, 0, 4, false))) return rc;   // every rank takes the same decision
     DDPS_CUDA(cudaMemcpyAsync(ctx->scal_host, ctx->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
     DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
     const double* m = ctx->scal_host->sums;
@@ -990,7 +1101,7 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind) {
     for (int l = 0; l + 1 < A.nlev; ++l) {
       const AmgLevelDev& F = A.lv[l];
       const AmgLevelDev& C = A.lv[l + 1];
-      amg_launch_rap(ctx, F, F.cur_val, C, const_cast<double*>(C.cur_val), const_cast<double*>(C.cur_dinv));
+      if ((rc = amg_launch_rap(ctx, F, F.cur_val, C, const_cast<double*>(C.cur_val), const_cast<double*>(C.cur_dinv)))) return rc;
     }
     for (int l = 1; l < A.nlev; ++l) {   // fp32 copies of the large coarse levels' values for the cycle's SpMVs
       AmgLevelDev& L = A.lv[l];
@@ -1048,10 +1159,15 @@ static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x,
 }
 
 // z = B r: one V(1,1) cycle from the zero initial guess.  dot_rz: also leave r.z in scal->sums[1].
+// Distributed levels (multi-rank contexts): the level's x, t, x2 carry ghost entries that are refreshed right before the
+// kernel that gathers them -- x before the residual and before the smoothing sweep, t before the restriction, the coarse
+// correction before the prolongation (amg_dist_prototype.py messages 5-8); on the transition level restriction sums over
+// the owned fine rows only and one allreduce completes the replicated right-hand side.
 static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz, bool have_first_sweep) {
   Amg& A = *ctx->amg;
   const double om = A.omega;
   cudaStream_t st = ctx->stream;
+  int rc;
   A.lv[0].b = const_cast<double*>(r);
   A.lv[0].x2 = z;
   for (int l = 0; l + 1 < A.nlev; ++l) {
@@ -1060,16 +1176,26 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
       k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);   // level; coarser
       ctx->stats.kernel_launches++;                                                                    // levels: fused in restrict)
     }
+    if (L.dist && (rc = halo_xchg(ctx, *L.plan, L.x, true))) return rc;
     launch_amg_spmv<1, false>(ctx, L, L.x, L.b, om, L.t);
+    if (L.dist == 1 && (rc = halo_xchg(ctx, *L.plan, L.t, true))) return rc;
     AmgLevelDev& C = A.lv[l + 1];
     const bool coarsest = (l + 2 == A.nlev);
+    const bool fuse_sweep = !coarsest && L.dist != 2;   // transition: the sweep needs the COMPLETED right-hand side
     if (L.nc <= kAmgSmallLevel)
-      k_amg_restrict_wpr<<<amg_grid(ctx, (int64_t)L.nc * 32, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, coarsest ? nullptr : C.cur_dinv,
+      k_amg_restrict_wpr<<<amg_grid(ctx, (int64_t)L.nc * 32, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr,
                                                                                 om, C.x, ctx->scal);
     else
-      k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, coarsest ? nullptr : C.cur_dinv, om, C.x,
+      k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr, om, C.x,
                                                               ctx->scal);
     ctx->stats.kernel_launches++;
+    if (L.dist == 2) {
+      if ((rc = comm_allreduce(ctx, C.b, (size_t)C.n, COMM_SUM))) return rc;
+      if (!coarsest) {
+        k_amg_jac0<<<amg_grid(ctx, C.n, 256), 256, 0, st>>>(C.n, om, C.cur_dinv, C.b, C.x, ctx->scal);
+        ctx->stats.kernel_launches++;
+      }
+    }
   }
   {
     AmgLevelDev& L = A.lv[A.nlev - 1];
@@ -1078,8 +1204,11 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
   }
   for (int l = A.nlev - 2; l >= 0; --l) {
     AmgLevelDev& L = A.lv[l];
-    k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pent, A.lv[l + 1].x2, L.x, ctx->scal);
+    AmgLevelDev& C = A.lv[l + 1];
+    if (L.dist == 1 && (rc = halo_xchg(ctx, *C.plan, C.x2, true))) return rc;
+    k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pent, C.x2, L.x, ctx->scal);
     ctx->stats.kernel_launches++;
+    if (L.dist && (rc = halo_xchg(ctx, *L.plan, L.x, true))) return rc;
     if (l == 0 && dot_rz) launch_amg_spmv<2, true>(ctx, L, L.x, L.b, om, L.x2);
     else launch_amg_spmv<2, false>(ctx, L, L.x, L.b, om, L.x2);
   }
@@ -1119,7 +1248,7 @@ int amg_time_launch(Context* ctx, int which, int it, double* bytes) {
       if (bytes) *bytes = (vw + 4.0) * nnz + 4.0 * (n + 1) + 4 * 8.0 * n;
       return 0;
     case 11:
-      k_apcg_update<<<amg_grid(ctx, L.n, kVecBlock), kVecBlock, 0, ctx->stream>>>(L.n, it & 1, it, 1 << 30, ctx->p, ctx->q, ctx->x, ctx->r, L.cur_dinv,
+      k_apcg_update<true><<<amg_grid(ctx, L.n, kVecBlock), kVecBlock, 0, ctx->stream>>>(L.n, it & 1, it, 1 << 30, ctx->p, ctx->q, ctx->x, ctx->r, L.cur_dinv,
                                                                                 A.omega, L.x, ctx->partials, ctx->scal);
       if (bytes) *bytes = 8 * 8.0 * n;
       return 0;
@@ -1162,12 +1291,24 @@ int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it) {
   Amg& A = *ctx->amg;
   const int n = ctx->n_own;
   const int par = it & 1;
+  const bool mr = ctx->nranks > 1;
   int rc;
   const int g2 = amg_grid(ctx, n, kVecBlock);
+  if (mr && (rc = halo_xchg(ctx, ctx->halo, ctx->p, true))) return rc;              // ghost entries of the search direction
   if ((rc = launch_spmv_dot(ctx, A.lv[0].cur_val, ctx->p, ctx->q))) return rc;    // q = A p, p.q -> sums[0]
-  k_apcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
-                                                   A.lv[0].x, ctx->partials, ctx->scal);
+  if (mr) {
+    if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[0], 1, 0, true))) return rc;
+    k_apcg_update<false><<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
+                                                            A.lv[0].x, ctx->partials, ctx->scal);
+    if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[2], 1, 1, true))) return rc;   // {r.r, max|r|}
+    k_apcg_decide<<<1, 1, 0, ctx->stream>>>(ctx->scal, par, it, max_it);
+    ctx->stats.kernel_launches++;
+  } else {
+    k_apcg_update<true><<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
+                                                           A.lv[0].x, ctx->partials, ctx->scal);
+  }
   if ((rc = amg_vcycle_impl(ctx, ctx->r, A.z, true, true))) return rc;             // z = B r, r.z -> sums[1]
+  if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[1], 1, 0, true))) return rc;
   k_apcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, 0, 0.0, A.z, ctx->p, ctx->scal);
   ctx->stats.kernel_launches += 2;
   return 0;
@@ -1177,22 +1318,27 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
                   double rtol, double atol_inf, int64_t max_it, int64_t* iters_out, double* relres_out) {
   Amg& A = *ctx->amg;
   const int n = ctx->n_own;
+  const bool mr = ctx->nranks > 1;
   int rc;
   if (max_it <= 0) max_it = 200000;
   if (max_it > 2000000000LL) max_it = 2000000000LL;
   cudaStream_t st = ctx->stream;
+  if (ctx->p2p.win_local) DDPS_CUDA(cudaMemsetAsync(&ctx->p2p.win_local->error, 0, sizeof(int), st));
   if ((rc = amg_numeric(ctx, val, dinv, ctx->amg_kind))) return rc;
   const int g = amg_grid(ctx, std::max(n, 1), kVecBlock);
   if (x0_nonzero) {
     DDPS_CUDA(cudaMemcpyAsync(ctx->p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (mr && (rc = halo_xchg(ctx, ctx->halo, ctx->p, false))) return rc;
     if ((rc = launch_spmv(ctx, val, ctx->p, ctx->q))) return rc;
     k_apcg_init<true><<<g, kVecBlock, 0, st>>>(n, rhs, ctx->q, ctx->p, ctx->r, ctx->partials, ctx->scal);
   } else {
     DDPS_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), st));
     k_apcg_init<false><<<g, kVecBlock, 0, st>>>(n, rhs, nullptr, nullptr, ctx->r, ctx->partials, ctx->scal);
   }
+  if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[0], 3, 1, false))) return rc;   // {r.r, b.b, x0.b, max|r|}
   k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf, x0_nonzero ? 1 : 0, ctx->eps_e);
   if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;
+  if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[1], 1, 0, true))) return rc;
   k_apcg_direction<<<g, kVecBlock, 0, st>>>(n, 0, 1, rtol, A.z, ctx->p, ctx->scal);
   ctx->stats.kernel_launches += 3;
   DDPS_CUDA(cudaGetLastError());
@@ -1213,6 +1359,10 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
   if (relres_out) *relres_out = (S.bb > 0) ? sqrt(S.rr / S.bb) : 0.0;
   ctx->stats.pcg_total += S.iters;
   ctx->hist_pcg.push_back((double)S.iters);
+  if (S.breakdown == 2) {
+    ctx->fail(DDPS_ERR_COMM, "peer-memory exchange timed out (a rank stopped participating)");
+    return DDPS_ERR_COMM;
+  }
   if (S.breakdown) {
     ctx->fail(DDPS_ERR_BREAKDOWN, "PCG breakdown: p.Ap <= 0 (operator not SPD; u or v negative? SURVEY H3)");
     return DDPS_ERR_BREAKDOWN;

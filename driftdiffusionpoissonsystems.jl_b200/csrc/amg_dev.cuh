@@ -35,6 +35,26 @@ struct AmgLevelDev {
   double* APval = nullptr;
   int64_t nAP = 0;
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
+  // ---- distributed levels (multi-rank contexts).  Rows = the level's rows this rank owns (n of them, global id goff + i),
+  // columns = local ids: owned first, then ghosts grouped by owner (n_loc in all); vectors x, t, x2 have n_loc entries, their
+  // ghost parts are refreshed over `plan`.
+  //   dist == 1: the next level is distributed too (rank-local aggregates, ghost prolongator rows and A*P rows of the
+  //              neighbours' boundary rows come by one exchange each);
+  //   dist == 2: "transition": the next level (and everything below) is REPLICATED on every rank -- restriction and the
+  //              Galerkin product give partial sums over the owned fine rows that one allreduce completes;
+  //   dist == 0: single-rank context or replicated level.
+  int dist = 0;
+  int n_loc = 0;
+  long long goff = 0;
+  HaloPlan* plan = nullptr;
+  bool owns_plan = false;
+  int* glob = nullptr;               // [n_loc] global row id of every local column
+  // A*P values of the boundary rows travel to the neighbours once per operator (dist == 1)
+  int ap_nsend = 0;
+  int* ap_send_pos = nullptr;        // positions in APval of the entries to pack, grouped by neighbour
+  double* ap_send_buf = nullptr;
+  std::vector<int> ap_send_off, ap_recv_off;   // [nneigh+1] entry offsets per neighbour (send buffer / ghost part of APval)
+  int ap_ghost_base = 0;             // APptr[n]: the ghost rows' entries start here
 };
 
 // Galerkin values of one KIND of operator (first Newton system of a Vsolve / later Newton systems / u- / v-continuity
@@ -65,10 +85,19 @@ struct Amg {
 
 
 // amg.cu: Galerkin product of the fine matrix values `f_val` (SELL order of level F) into level C (values + inverse diagonal)
-void amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv);
+int amg_launch_rap(Context* ctx, const AmgLevelDev& F, const double* f_val, const AmgLevelDev& C, double* out_val, double* out_dinv);
 // amg_setup.cu: build transfers of level l and the pattern + base values of level l+1 on the device.
 // Returns 0 on success with *nc_out = rows of the next level (0: coarsening stalled, nothing installed), <0 on error,
 // >0 when the device path does not apply (caller falls back to the host path).
 int amg_dev_coarsen(Context* ctx, Amg* A, int l, const unsigned char* d_fixed, const AmgParams& prm, int* nc_out);
+// amg_setup.cu, multi-rank contexts.  Distributed coarsening of level l (collective): *ncg_out = global rows of level l+1
+// (0: coarsening stalled on the whole, nothing installed).  Transition: gather level l, build the replicated rest of the
+// hierarchy on the host, install it; *nlev_out = total number of levels (0: no coarsening possible).
+int amg_dist_coarsen(Context* ctx, Amg* A, int l, const AmgParams& prm, long long* ncg_out);
+int amg_dist_transition(Context* ctx, Amg* A, int l, const AmgParams& prm, int* nlev_out);
+int amg_dist_ap_halo(Context* ctx, AmgLevelDev& F);   // numeric phase: A*P values of the neighbours' boundary rows
+// amg.cu: upload helpers of host-built levels
+int amg_install_pattern(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL);
+int amg_install_transfers(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL);
 
 }  // namespace ddps

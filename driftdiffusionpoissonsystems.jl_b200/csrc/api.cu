@@ -339,8 +339,7 @@ int assemble_base(Context* ctx, bool semlin) {
 int maybe_amg_setup(Context* ctx) {
   ctx->stats.amg_levels = 0;
   if (ctx->opts.precond != DDPS_PRECOND_AMG) { amg_free(ctx); return 0; }
-  if (ctx->nranks != 1) return 0;
-  int rc = amg_setup(ctx);
+  int rc = amg_setup(ctx);   // (multi-rank contexts: distributed hierarchy, collective)
   if (rc) return rc;
   int64_t nl = 0;
   amg_debug_levels(ctx, &nl, nullptr, 0);
@@ -1073,6 +1072,7 @@ int ddps_ddpe_step(ddps_ctx* ctx, int nsteps, int stop_at_tol, double* control, 
   ctx->stats.t_solve_ms += dev_ms;                 // CUDA events on the library stream
   ctx->stats.t_wall_ms += now_ms() - t0;           // host wall clock around the same region
   if (steps_done) *steps_done = done;
+  if (!rc) rc = p2p_check_error(ctx);
   ctx->stats.status = rc;
   return rc;
 }
@@ -1356,6 +1356,7 @@ int ddps_amg_apply(ddps_ctx* ctx, const double* r, double* z) {
   int rc;
   if ((rc = require_mesh(ctx))) return rc;
   if (!amg_ready(ctx)) { ctx->fail(DDPS_ERR_STATE, "no multigrid hierarchy"); return DDPS_ERR_STATE; }
+  if (ctx->nranks != 1) { ctx->fail(DDPS_ERR_STATE, "debug exports are single-GPU"); return DDPS_ERR_STATE; }
   if ((rc = upload_owned(ctx, ctx->r, r))) return rc;
   DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
   if ((rc = amg_vcycle(ctx, ctx->r, ctx->q, false))) return rc;

@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_update(int n, int par, int
   if (grid_reduce_mixed<3, 4u>(v, partials, &scal->cnt[1], sh_red, tot)) {
     if (threadIdx.x == 0) {
       if (pd.nranks > 1) p2p_publish<3>(pd, 1, pd.tagB, tot);
-      else { scal->sums[1] = tot[0]; scal->sums[2] = tot[1]; scal->rmax = tot[2]; }
+      else { scal->sums[1] = tot[0]; scal->sums[2] = tot[1]; scal->sums[3] = tot[2]; }
     }
   }
 }
@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, 
     comm_ok = p2p_gather<3, 4u>(pd, 1, pd.tagB, t, sh_red);
     rz_new = t[0]; rr = t[1]; rmax = t[2];
   } else {
-    rz_new = scal->sums[1]; rr = scal->sums[2]; rmax = scal->rmax;
+    rz_new = scal->sums[1]; rr = scal->sums[2]; rmax = scal->sums[3];
   }
   const double rz_old = scal->rz[par];
   const bool small_r = (rr <= scal->thresh2) || (rmax <= scal->thresh_inf);
@@ -964,13 +964,12 @@ int pcg_iteration_launch(Context* ctx, const double* val, const double* dinv, do
   } else {
     memset(&pd, 0, sizeof(pd));
     pd.nranks = 1;
-    if ((rc = halo_exchange(ctx, ctx->p))) return rc;
+    if ((rc = halo_xchg(ctx, ctx->halo, ctx->p, true))) return rc;
     k_spmv<true, false><<<g1, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, ctx->p, ctx->q,
                                                            ctx->partials, ctx->scal, pd, r0);
-    if ((rc = allreduce_sum(ctx, &ctx->scal->sums[0], 1))) return rc;
+    if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[0], 1, 0, true))) return rc;
     k_pcg_update<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r1, ctx->p, ctx->q, dinv, x, ctx->r, ctx->partials, ctx->scal, pd);
-    if ((rc = allreduce_sum(ctx, &ctx->scal->sums[1], 2))) return rc;
-    if ((rc = allreduce_max(ctx, &ctx->scal->rmax, 1))) return rc;
+    if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[1], 2, 1, true))) return rc;
     PushArgs none;
     memset(&none, 0, sizeof(none));
     k_pcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, r0, it, max_it, ctx->r, dinv, ctx->p, ctx->scal, pd, none, nullptr);

@@ -113,7 +113,8 @@ typedef struct ddps_solver_opts {
                            the Jacobi-PCG the north star names.  DDPS_PRECOND_AMG (1): smoothed-aggregation multigrid
                            V(1,1) cycle (frozen prolongators from the base stiffness, Galerkin operators of every assembled
                            M - J0 recomputed on the device); same stop rules, same solutions to solver tolerance.
-                           Single-GPU contexts only; with a communicator the Jacobi path stays in charge */
+                           With a communicator the hierarchy is distributed: rank-local aggregates, halo exchanges of the
+                           cycle vectors over peer memory on the large levels, a replicated tail below ~200k rows */
   int32_t amg_no_lag;   /* multigrid path: 1 = recompute the coarse (Galerkin) operators for every assembled operator.  Default 0:
                            they are reused while the operator of the same kind (first / later Newton system, u-, v-continuity
                            system) stays within 1 % (entries and row sums) of the one they were computed from -- the cycle is
@@ -166,7 +167,10 @@ int ddps_set_opts(ddps_ctx* ctx, const ddps_solver_opts* opts);
 
 /* ---- multi-GPU (one process per GPU; node-partitioned by coordinate bisection) ------------ */
 /* The reference has no communication at all; these are new.  id is an ncclUniqueId (128 bytes)
- * produced on rank 0 and broadcast by the host's own plumbing (torch.distributed / MPI / files). */
+ * produced on rank 0 and broadcast by the host's own plumbing (torch.distributed / MPI / files).
+ * An id that starts with "LOCAL:" selects the in-process backend instead: the ranks are THREADS of one process sharing one
+ * device (each with its own ctx), exchanges are device-to-device copies -- the whole distributed path (partition, ghost
+ * layers, distributed multigrid) runs on a single GPU; this is what the single-GPU test-suite drives. */
 int ddps_comm_unique_id(char id128[128]);
 int ddps_comm_init(ddps_ctx* ctx, const char id128[128], int rank, int nranks);
 

@@ -1,0 +1,101 @@
+"""Node-partitioned solves with the ranks running as threads on ONE GPU (in-process communicator): N-rank results against the
+single-rank result and the golden fixtures, for both transports of the hot exchanges (staged peer-memory kernels / backend
+exchange) and both preconditioners.  The same checks run with one process per GPU in tests/test_multigpu.py."""
+import numpy as np
+import pytest
+
+from localranks import run_ranks
+from util import KEYS, golden, gpu_mesh, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D():
+    import ddps_b200
+    return ddps_b200
+
+
+def _solve_ddpe(D, mesh, pr, comm=None, **opts):
+    with D.Session(0, comm=comm, **opts) as s:
+        V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+    return V, u, v, st
+
+
+@pytest.mark.parametrize("p2p", ["1", "0"])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_jacobi_path_local_ranks(D, nranks, p2p, monkeypatch):
+    monkeypatch.setenv("DDPS_P2P", p2p)
+    mesh = D.structured_mesh(96, 48, 0.0, 2.0, 0.0, 1.0)
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0)
+    ref = _solve_ddpe(D, mesh, pr)
+    res = run_ranks(nranks, lambda r, comm: _solve_ddpe(D, mesh, pr, comm=comm))
+    for V, u, v, st in res:
+        for a, b in ((V, ref[0]), (u, ref[1]), (v, ref[2])):
+            assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)
+        assert st["outer_iters"] == ref[3]["outer_iters"]
+        assert list(st["newton_per_vsolve"]) == list(ref[3]["newton_per_vsolve"])
+    # every rank returns the same full fields
+    assert np.array_equal(res[0][0], res[-1][0])
+
+
+def test_semlin_and_golden_local_ranks(D):
+    mesh = gpu_mesh("F1")
+    pr = D.problems.semlin_test(True)
+
+    def semlin(r, comm):
+        with D.Session(0, comm=comm) as s:
+            return D.solve_semlin_poisson(mesh, pr["A"], pr["bddata"], pr["f"], pr["g"], pr["tol"], session=s, return_stats=True, verbose=False)
+
+    z = golden("semlin_F1")
+    for V, st in run_ranks(3, semlin):
+        assert rel_l2(V, z["V"]) <= 1e-8
+        assert st["outer_iters"] == 5
+    mesh2 = gpu_mesh("F2")
+    pr2 = D.problems.ddpe2()
+    z = golden("ddpe2_F2")
+    for V, u, v, st in run_ranks(2, lambda r, comm: _solve_ddpe(D, mesh2, pr2, comm=comm)):
+        for a, k in ((V, "V"), (u, "u"), (v, "v")):
+            assert rel_l2(a, z[k]) <= 1e-8, (k, rel_l2(a, z[k]))
+        assert st["outer_iters"] == len(z["control"])
+
+
+@pytest.mark.parametrize("p2p", ["1", "0"])
+@pytest.mark.parametrize("nranks,tail,cells", [(2, 300, (96, 48)), (3, 300, (96, 48)), (2, 200000, (96, 48)), (4, 1500, (192, 96))])
+def test_distributed_multigrid_local_ranks(D, nranks, tail, cells, p2p, monkeypatch):
+    """The distributed multigrid hierarchy (rank-local aggregates, ghost prolongator / A*P rows, halo exchanges of the cycle
+    vectors, replicated tail below DDPS_AMG_TAIL rows) against the single-GPU hierarchy on the same problem: fields <= 1e-10,
+    the same Gummel and Newton counts, and at most 3 more CG iterations in any linear solve."""
+    monkeypatch.setenv("DDPS_P2P", p2p)
+    monkeypatch.setenv("DDPS_AMG_TAIL", str(tail))
+    mesh = D.structured_mesh(cells[0], cells[1], 0.0, 2.0, 0.0, 1.0)
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0)
+    ref = _solve_ddpe(D, mesh, pr, precond=1)
+    assert ref[3]["amg_levels"] >= 2
+    res = run_ranks(nranks, lambda r, comm: _solve_ddpe(D, mesh, pr, comm=comm, precond=1))
+    for V, u, v, st in res:
+        assert st["amg_levels"] >= 2, "distributed hierarchy was not built (fell back to Jacobi-PCG)"
+        for a, b in ((V, ref[0]), (u, ref[1]), (v, ref[2])):
+            assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)
+        assert st["outer_iters"] == ref[3]["outer_iters"]
+        assert list(st["newton_per_vsolve"]) == list(ref[3]["newton_per_vsolve"])
+        its, its_ref = np.array(st["pcg_per_solve"]), np.array(ref[3]["pcg_per_solve"])
+        assert its.shape == its_ref.shape
+        assert np.all(its <= its_ref + 3), (its.tolist(), its_ref.tolist())
+    assert np.array_equal(res[0][0], res[-1][0])
+
+
+def test_distributed_multigrid_semlin_local_ranks(D, monkeypatch):
+    monkeypatch.setenv("DDPS_AMG_TAIL", "400")
+    mesh = gpu_mesh("F1")
+    pr = D.problems.semlin_test(True)
+
+    def semlin(r, comm):
+        with D.Session(0, comm=comm, precond=1) as s:
+            return D.solve_semlin_poisson(mesh, pr["A"], pr["bddata"], pr["f"], pr["g"], pr["tol"], session=s, return_stats=True, verbose=False)
+
+    z = golden("semlin_F1")
+    for V, st in run_ranks(3, semlin):
+        assert st["amg_levels"] >= 2
+        assert rel_l2(V, z["V"]) <= 1e-8
+        assert st["outer_iters"] == 5
