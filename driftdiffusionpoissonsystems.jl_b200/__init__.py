@@ -7,7 +7,8 @@ Public surface (mirrors the reference's exports, ``src:6-7``):
     Mesh, read_mesh, construct_mesh4, construct_mesh8, construct_mesh, structured_mesh,
     solve_ddpe, solve_semlin_poisson, aquire_boundary, SinhRHS, PolyRHS, Session
 """
-from .mesh import Mesh, read_mesh, construct_mesh4, construct_mesh8, construct_mesh, structured_mesh
+from .mesh import (Mesh, read_mesh, construct_mesh4, construct_mesh8, construct_mesh, structured_mesh, structured_mesh_part,
+                   structured_boundary)
 from .functors import SinhRHS, PolyRHS, Const, Affine, StepX, StepY
 from . import functors
 from .api import (Session, DDPSError, solve_ddpe, solve_semlin_poisson, aquire_boundary, dirichlet_nodes,
@@ -16,7 +17,7 @@ from .postprocess import aquire_boundary_separate_edges, get_gradients, calculat
 from . import problems
 from . import amg
 
-__all__ = ["Mesh", "read_mesh", "construct_mesh4", "construct_mesh8", "construct_mesh", "structured_mesh",
+__all__ = ["Mesh", "read_mesh", "construct_mesh4", "construct_mesh8", "construct_mesh", "structured_mesh", "structured_mesh_part", "structured_boundary",
            "solve_ddpe", "solve_semlin_poisson", "aquire_boundary", "SinhRHS", "PolyRHS", "Const", "Affine", "StepX", "StepY", "functors", "Session", "DDPSError",
            "problems", "amg", "dirichlet_nodes", "neumann_edges", "aquire_boundary_separate_edges", "get_gradients",
            "calculate_current", "current_from_fields"]

@@ -52,6 +52,9 @@ SIGNATURES = {
     "ddps_comm_unique_id": (C.c_int, [C.c_char_p]),
     "ddps_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "ddps_mesh_set": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_int64_p, C.c_int64]),
+    "ddps_mesh_set_local": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int64, c_int64_p, c_int32_p, c_int64_p, C.c_int64, c_int64_p,
+                                      C.c_int64, C.c_int64]),
+    "ddps_ddpe_fetch_owned": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_int64]),
     "ddps_partition_nodes": (C.c_int, [c_double_p, C.c_int64, C.c_int, c_int32_p]),
     "ddps_partition_plan": (C.c_int, [c_double_p, C.c_int64, c_int64_p, C.c_int64, C.c_int, C.c_int, c_int64_p, c_int64_p,
                                       c_int32_p, c_int64_p, c_int64_p, c_int64_p]),

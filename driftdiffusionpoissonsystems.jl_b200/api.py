@@ -246,6 +246,28 @@ class Session:
                                            elements.shape[0]))
         self.mesh = mesh
 
+    def set_mesh_local(self, part, with_elem_glob=True):
+        """Per-rank mesh ingest (``ddps_mesh_set_local``): ``part`` as returned by ``mesh.structured_mesh_part`` -- nobody
+        holds the global mesh.  ``self.mesh`` becomes the boundary-only Mesh the host preprocessing needs."""
+        nodes = np.ascontiguousarray(part["nodes"], dtype=np.float64)
+        el = np.ascontiguousarray(part["elements"], dtype=np.int64)
+        ng = part["n_loc"] - part["n_own"]
+        go = part["ghost_owner"]
+        eg = part.get("elem_glob") if with_elem_glob else None
+        self._check(self.lib.ddps_mesh_set_local(
+            self.h, _lib.dptr(nodes), int(part["n_own"]), int(part["n_loc"]), _lib.iptr(part["node_glob"]),
+            go.ctypes.data_as(_lib.c_int32_p) if ng else None, _lib.iptr(el), el.shape[0],
+            _lib.iptr(eg) if eg is not None else None, int(part["nq_global"]), int(part["nme_global"])))
+        self.mesh = part["boundary"]
+        self._part = part
+
+    def ddpe_fetch_owned(self):
+        """V, u, v of the nodes this rank owns (order of ``part['own_glob']``)."""
+        n = self._part["n_own"]
+        V, u, v = np.empty(n), np.empty(n), np.empty(n)
+        self._check(self.lib.ddps_ddpe_fetch_owned(self.h, _lib.dptr(V), _lib.dptr(u), _lib.dptr(v), n))
+        return V, u, v
+
     def set_dirichlet(self, field, n, gD):
         n = np.ascontiguousarray(n, dtype=np.int64)
         gD = np.ascontiguousarray(gD, dtype=np.float64)

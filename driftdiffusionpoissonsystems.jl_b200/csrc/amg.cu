@@ -724,7 +724,8 @@ static int amg_setup_dist(Context* ctx) {
   const Pattern& P = ctx->pat;
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   AmgParams prm;
-  const long long tail = getenv("DDPS_AMG_TAIL") ? atoll(getenv("DDPS_AMG_TAIL")) : 200000;
+  // (at least 8 x coarse_max rows: the replicated part must still coarsen once, the coarsest level is solved directly)
+  const long long tail = std::max<long long>(8LL * prm.coarse_max, getenv("DDPS_AMG_TAIL") ? atoll(getenv("DDPS_AMG_TAIL")) : 200000);
   const bool timing = getenv("DDPS_AMG_TIMING") != nullptr;
   Amg* A = new Amg();
   ctx->amg = A;
@@ -745,7 +746,12 @@ static int amg_setup_dist(Context* ctx) {
       const double ta = wall_ms();
       rc = amg_dist_coarsen(ctx, A, l, prm, &ncg);
       if (rc < 0) return rc;
-      if (rc > 0 || ncg == 0) { amg_free(ctx); return 0; }   // does not apply / stalled: Jacobi-PCG stays (same decision on all ranks)
+      if (rc > 0 || ncg == 0) {   // does not apply / stalled: Jacobi-PCG stays (same decision on all ranks)
+        if (timing) fprintf(stderr, "[ddps amg] rank %d: distributed coarsening of level %d (%lld rows) %s -> no hierarchy\n", ctx->rank, l, ng,
+                            rc > 0 ? "does not apply" : "stalled");
+        amg_free(ctx);
+        return 0;
+      }
       if (timing && ctx->rank == 0)
         fprintf(stderr, "[ddps amg] distributed level %d: %lld -> %lld rows (rank 0: %d -> %d owned, %d ghost columns): %.1f ms\n", l, ng, ncg,
                 A->lv[l].n, A->lv[l + 1].n, A->lv[l + 1].n_loc - A->lv[l + 1].n, wall_ms() - ta);
@@ -758,7 +764,11 @@ static int amg_setup_dist(Context* ctx) {
     if (timing && ctx->rank == 0) fprintf(stderr, "[ddps amg] transition at level %d (%lld rows gathered), %d levels in all: %.1f ms\n", l, ng, nlev, wall_ms() - ta);
     break;
   }
-  if (nlev < 2 || A->lv[nlev - 1].n > kAmgDenseMax) { amg_free(ctx); return 0; }
+  if (nlev < 2 || A->lv[nlev - 1].n > kAmgDenseMax) {
+    if (timing) fprintf(stderr, "[ddps amg] rank %d: %d levels, coarsest %d rows -> no hierarchy\n", ctx->rank, nlev, nlev ? A->lv[nlev - 1].n : 0);
+    amg_free(ctx);
+    return 0;
+  }
   return amg_finish_setup(ctx, A, nlev, t0);
 }
 

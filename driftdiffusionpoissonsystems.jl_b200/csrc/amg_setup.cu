@@ -801,6 +801,8 @@ int amg_dist_coarsen(Context* ctx, Amg* A, int l, const AmgParams& prm, long lon
   long long nfg = 0;
   for (int r = 0; r < nr; ++r) { coff[r + 1] = coff[r] + cnt_all[2 * r]; nfg += cnt_all[2 * r + 1]; }
   const long long ncg = coff[nr];
+  if (getenv("DDPS_AMG_TIMING")) fprintf(stderr, "[ddps amg] rank %d level %d: %d owned rows (%d local columns), %d strong couplings, %d aggregates; %lld of %lld in total\n",
+                                         me, l, n, nl, ns, nc, ncg, nfg);
   if (ncg <= 0 || ncg > 0.7 * (double)nfg) return 0;   // coarsening stalled (same decision on every rank)
   if (ncg >= (1LL << 31) - 2) { ctx->fail(DDPS_ERR_ARG, "multigrid level too large for 32-bit global ids"); return DDPS_ERR_ARG; }
   const int off = (int)coff[me];

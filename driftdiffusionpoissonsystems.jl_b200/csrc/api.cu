@@ -48,7 +48,7 @@ void free_mesh(Context* ctx) {
   dev_free(ctx->p); dev_free(ctx->partials);
   plan_free(ctx->halo);
   ctx->loc2glob.clear(); ctx->elem_glob.clear(); ctx->Dset.clear();
-  ctx->have_mesh = false; ctx->base_ready = false; ctx->ddpe_active = false;
+  ctx->have_mesh = false; ctx->base_ready = false; ctx->ddpe_active = false; ctx->local_ingest = false;
 }
 
 __global__ void k_count_negative(const int4* __restrict__ elem, const double2* __restrict__ xy, int nme, int* out) {
@@ -670,6 +670,65 @@ int ddps_partition_plan(const double* nodes, int64_t nq, const int64_t* elements
   return DDPS_OK;
 }
 
+// common tail of ddps_mesh_set / ddps_mesh_set_local: orientation report, pattern build, work arrays, peer-memory setup
+static int finish_mesh(ddps_ctx* ctx, double t0) {
+  int rc;
+  // orientation report (Q2: the mass weights use the SIGNED area, src:375)
+  {
+    int* d_neg = nullptr;
+    DDPS_CUDA(cudaMalloc(&d_neg, sizeof(int)));
+    cudaMemsetAsync(d_neg, 0, sizeof(int), ctx->stream);
+    if (ctx->nme) k_count_negative<<<(ctx->nme + 255) / 256, 256, 0, ctx->stream>>>(ctx->elem, ctx->xy, ctx->nme, d_neg);
+    int neg = 0;
+    cudaMemcpyAsync(&neg, d_neg, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_neg);
+    ctx->stats.n_negative_area = neg;
+  }
+  const double t_up = now_ms();
+  if ((rc = build_pattern(ctx))) { free_mesh(ctx); return rc; }
+  const double t_pat = now_ms();
+
+  const size_t nl = ctx->n_loc, no = ctx->n_own, ne = (size_t)ctx->pat.nentries;
+  if ((rc = dev_alloc(ctx, &ctx->isD, nl))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(ctx->isD, 0, nl, ctx->stream));
+  for (int f = 0; f < 4; ++f) {
+    if ((rc = dev_alloc(ctx, &ctx->gD[f], nl))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(ctx->gD[f], 0, nl * sizeof(double), ctx->stream));
+  }
+  double** nodal[] = {&ctx->V, &ctx->U, &ctx->W, &ctx->V0, &ctx->U0, &ctx->W0, &ctx->Unew, &ctx->EH, &ctx->EHi, &ctx->E3,
+                      &ctx->gw, &ctx->p};
+  for (double** pp : nodal) {
+    if ((rc = dev_alloc(ctx, pp, nl))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(*pp, 0, nl * sizeof(double), ctx->stream));
+  }
+  double** owned[] = {&ctx->b, &ctx->resid, &ctx->dinv, &ctx->x, &ctx->r, &ctx->q, &ctx->lift};
+  for (double** pp : owned) {
+    if ((rc = dev_alloc(ctx, pp, no))) return rc;
+    DDPS_CUDA(cudaMemsetAsync(*pp, 0, no * sizeof(double), ctx->stream));
+  }
+  if ((rc = dev_alloc(ctx, &ctx->val_base, ne))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->val_op, ne))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->val_s, ne))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->sc, nl))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->bs, no))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(ctx->val_s, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
+  DDPS_CUDA(cudaMemsetAsync(ctx->sc, 0, std::max<size_t>(nl, 1) * sizeof(double), ctx->stream));
+  DDPS_CUDA(cudaMemsetAsync(ctx->val_base, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
+  DDPS_CUDA(cudaMemsetAsync(ctx->val_op, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
+  int asm_blocks = (ctx->pat.nslices * 32 + kAsmBlock - 1) / kAsmBlock;
+  ctx->partial_cap = std::max(asm_blocks, 4 * ctx->num_sms * 16) + 64;
+  if ((rc = dev_alloc(ctx, &ctx->partials, (size_t)ctx->partial_cap))) return rc;
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if ((rc = p2p_setup(ctx))) return rc;
+  ctx->have_mesh = true;
+  ctx->stats.t_setup_ms = now_ms() - t0;
+  if (getenv("DDPS_AMG_TIMING"))
+    fprintf(stderr, "[ddps] mesh_set %.1f ms: uploads + conversion %.1f, pattern build %.1f, allocations %.1f\n", ctx->stats.t_setup_ms,
+            t_up - t0, t_pat - t_up, now_ms() - t_pat);
+  return DDPS_OK;
+}
+
 int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t* elements, int64_t nme) {
   if (!ctx) return DDPS_ERR_ARG;
   cudaSetDevice(ctx->device);
@@ -784,59 +843,129 @@ int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t*
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   hel.clear(); hel.shrink_to_fit();
 
-  // orientation report (Q2: the mass weights use the SIGNED area, src:375)
-  {
-    int* d_neg = nullptr;
-    DDPS_CUDA(cudaMalloc(&d_neg, sizeof(int)));
-    cudaMemsetAsync(d_neg, 0, sizeof(int), ctx->stream);
-    if (ctx->nme) k_count_negative<<<(ctx->nme + 255) / 256, 256, 0, ctx->stream>>>(ctx->elem, ctx->xy, ctx->nme, d_neg);
-    int neg = 0;
-    cudaMemcpyAsync(&neg, d_neg, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_neg);
-    ctx->stats.n_negative_area = neg;
-  }
-  const double t_up = now_ms();
-  if ((rc = build_pattern(ctx))) { free_mesh(ctx); return rc; }
-  const double t_pat = now_ms();
+  return finish_mesh(ctx, t0);
+}
 
-  const size_t nl = ctx->n_loc, no = ctx->n_own, ne = (size_t)ctx->pat.nentries;
-  if ((rc = dev_alloc(ctx, &ctx->isD, nl))) return rc;
-  DDPS_CUDA(cudaMemsetAsync(ctx->isD, 0, nl, ctx->stream));
-  for (int f = 0; f < 4; ++f) {
-    if ((rc = dev_alloc(ctx, &ctx->gD[f], nl))) return rc;
-    DDPS_CUDA(cudaMemsetAsync(ctx->gD[f], 0, nl * sizeof(double), ctx->stream));
+// Per-rank mesh ingest: nobody holds the global mesh.  The halo plan follows from the local
+// triangles alone: my send list to peer q = my owned corners of triangles that also have a q-owned corner, in increasing
+// global id -- exactly q's ghost block for me (q holds every triangle touching one of its nodes, so it sees the same ones).
+int ddps_mesh_set_local(ddps_ctx* ctx, const double* nodes, int64_t n_own, int64_t n_loc, const int64_t* node_glob,
+                        const int32_t* ghost_owner, const int64_t* elements, int64_t nme_loc, const int64_t* elem_glob,
+                        int64_t nq_global, int64_t nme_global) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (!nodes || !node_glob || !elements || n_own < 0 || n_loc < n_own || n_loc <= 0 || nme_loc <= 0 || (n_loc > n_own && !ghost_owner)) {
+    ctx->fail(DDPS_ERR_ARG, "empty or inconsistent local mesh");
+    return DDPS_ERR_ARG;
   }
-  double** nodal[] = {&ctx->V, &ctx->U, &ctx->W, &ctx->V0, &ctx->U0, &ctx->W0, &ctx->Unew, &ctx->EH, &ctx->EHi, &ctx->E3,
-                      &ctx->gw, &ctx->p};
-  for (double** pp : nodal) {
-    if ((rc = dev_alloc(ctx, pp, nl))) return rc;
-    DDPS_CUDA(cudaMemsetAsync(*pp, 0, nl * sizeof(double), ctx->stream));
+  if (n_loc >= (1LL << 31) - 64 || nme_loc >= (1LL << 29) || nq_global >= (1LL << 31) - 64) { ctx->fail(DDPS_ERR_ARG, "local mesh too large for one GPU"); return DDPS_ERR_ARG; }
+  if (ctx->opts.renumber) { ctx->fail(DDPS_ERR_ARG, "opts.renumber is not available with ddps_mesh_set_local (number the local nodes as you like)"); return DDPS_ERR_ARG; }
+  const double t0 = now_ms();
+  free_mesh(ctx);
+  ctx->nq_global = nq_global; ctx->nme_global = nme_global;
+  const int me = ctx->rank, nr = ctx->nranks;
+  int rc;
+  for (int64_t i = 1; i < n_own; ++i)
+    if (node_glob[i] <= node_glob[i - 1]) { ctx->fail(DDPS_ERR_ARG, "owned nodes must come in increasing global id"); return DDPS_ERR_ARG; }
+  for (int64_t g = 0; g < n_loc - n_own; ++g) {
+    const int o = ghost_owner[g];
+    if (o < 0 || o >= nr || o == me) { ctx->fail(DDPS_ERR_ARG, "bad ghost owner"); return DDPS_ERR_ARG; }
+    if (g > 0 && (o < ghost_owner[g - 1] || (o == ghost_owner[g - 1] && node_glob[n_own + g] <= node_glob[n_own + g - 1]))) {
+      ctx->fail(DDPS_ERR_ARG, "ghost nodes must be sorted by (owner, global id)");
+      return DDPS_ERR_ARG;
+    }
   }
-  double** owned[] = {&ctx->b, &ctx->resid, &ctx->dinv, &ctx->x, &ctx->r, &ctx->q, &ctx->lift};
-  for (double** pp : owned) {
-    if ((rc = dev_alloc(ctx, pp, no))) return rc;
-    DDPS_CUDA(cudaMemsetAsync(*pp, 0, no * sizeof(double), ctx->stream));
+  ctx->n_own = (int)n_own; ctx->n_loc = (int)n_loc; ctx->nme = (int)nme_loc;
+  ctx->loc2glob.resize(n_loc);
+  for (int64_t i = 0; i < n_loc; ++i) {
+    ctx->loc2glob[i] = node_glob[i] - 1;
+    if (ctx->loc2glob[i] < 0 || ctx->loc2glob[i] >= nq_global) { ctx->fail(DDPS_ERR_ARG, "global node id outside 1..nq_global"); return DDPS_ERR_ARG; }
   }
-  if ((rc = dev_alloc(ctx, &ctx->val_base, ne))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->val_op, ne))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->val_s, ne))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->sc, nl))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->bs, no))) return rc;
-  DDPS_CUDA(cudaMemsetAsync(ctx->val_s, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
-  DDPS_CUDA(cudaMemsetAsync(ctx->sc, 0, std::max<size_t>(nl, 1) * sizeof(double), ctx->stream));
-  DDPS_CUDA(cudaMemsetAsync(ctx->val_base, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
-  DDPS_CUDA(cudaMemsetAsync(ctx->val_op, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
-  int asm_blocks = (ctx->pat.nslices * 32 + kAsmBlock - 1) / kAsmBlock;
-  ctx->partial_cap = std::max(asm_blocks, 4 * ctx->num_sms * 16) + 64;
-  if ((rc = dev_alloc(ctx, &ctx->partials, (size_t)ctx->partial_cap))) return rc;
+  if (elem_glob) {
+    ctx->elem_glob.resize(nme_loc);
+    for (int64_t e = 0; e < nme_loc; ++e) ctx->elem_glob[e] = elem_glob[e] - 1;
+  }
+  // triangles: local 1-based ids -> packed records (device), validated on the device like ddps_mesh_set does
+  {
+    long long* d_el = nullptr;
+    int* d_bad = nullptr;
+    DDPS_CUDA(cudaMallocAsync(&d_el, (size_t)5 * nme_loc * sizeof(long long), ctx->stream));
+    if ((rc = dev_alloc(ctx, &ctx->elem, (size_t)nme_loc)) || (rc = dev_alloc(ctx, &ctx->xy, (size_t)n_loc))) { cudaFreeAsync(d_el, ctx->stream); return rc; }
+    cudaMalloc(&d_bad, sizeof(int));
+    cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+    cudaMemcpyAsync(d_el, elements, (size_t)5 * nme_loc * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->xy, nodes, (size_t)2 * n_loc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    k_convert_elements<<<(unsigned)((nme_loc + 255) / 256), 256, 0, ctx->stream>>>(d_el, (int)nme_loc, (long long)n_loc, ctx->elem, d_bad);
+    int bad = 0;
+    cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaFreeAsync(d_el, ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_bad);
+    if (ce != cudaSuccess) { ctx->fail(DDPS_ERR_CUDA, cudaGetErrorString(ce)); return DDPS_ERR_CUDA; }
+    if (bad) { ctx->fail(DDPS_ERR_ARG, "local element " + std::to_string(bad) + " references a node outside 1..n_loc"); return DDPS_ERR_ARG; }
+  }
+  // halo plan
+  HaloPlan& H = ctx->halo;
+  H.n_own = (int)n_own; H.n_ghost = (int)(n_loc - n_own);
+  if (nr > 1) {
+    std::vector<std::pair<int, int>> sends;   // (peer, local owned id); owned ids ascend with the global id
+    for (int64_t e = 0; e < nme_loc; ++e) {
+      const int64_t* c = elements + 5 * e;
+      int o[3];
+      for (int k = 0; k < 3; ++k) o[k] = c[k] - 1 < n_own ? me : ghost_owner[c[k] - 1 - n_own];
+      if (o[0] == me && o[1] == me && o[2] == me) continue;
+      for (int k = 0; k < 3; ++k)
+        if (o[k] == me)
+          for (int j = 0; j < 3; ++j)
+            if (o[j] != me) sends.emplace_back(o[j], (int)(c[k] - 1));
+    }
+    std::sort(sends.begin(), sends.end());
+    sends.erase(std::unique(sends.begin(), sends.end()), sends.end());
+    std::vector<int> peers;
+    for (int64_t g = 0; g < n_loc - n_own; ++g) peers.push_back(ghost_owner[g]);
+    for (auto& pr : sends) peers.push_back(pr.first);
+    std::sort(peers.begin(), peers.end());
+    peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+    const int nn = (int)peers.size();
+    std::vector<int> send_idx;
+    H.nneigh = nn; H.peer = peers;
+    H.send_off.assign(nn + 1, 0); H.recv_off.assign(nn + 1, 0);
+    for (int j = 0; j < nn; ++j) {
+      for (auto& pr : sends) if (pr.first == peers[j]) send_idx.push_back(pr.second);
+      H.send_off[j + 1] = (int)send_idx.size();
+      int cnt = 0;
+      for (int64_t g = 0; g < n_loc - n_own; ++g) if (ghost_owner[g] == peers[j]) ++cnt;
+      H.recv_off[j + 1] = H.recv_off[j] + cnt;
+    }
+    H.nsend = (int)send_idx.size();
+    if ((rc = dev_alloc(ctx, &H.send_idx, send_idx.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &H.send_buf, send_idx.size()))) return rc;
+    if ((rc = upload(ctx, H.send_idx, send_idx.data(), send_idx.size()))) return rc;
+    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if ((rc = dev_alloc(ctx, &ctx->d_own_glob, (size_t)n_own))) return rc;
+  {
+    std::vector<long long> og(ctx->loc2glob.begin(), ctx->loc2glob.begin() + n_own);
+    if ((rc = upload(ctx, ctx->d_own_glob, og.data(), og.size()))) return rc;
+    DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->local_ingest = true;
+  return finish_mesh(ctx, t0);
+}
+
+// V, u, v of the nodes this rank OWNS (n_own each, in the order of ddps_mesh_set_local's owned nodes / increasing global
+// id): no global gather -- the natural output of a partitioned solve
+int ddps_ddpe_fetch_owned(ddps_ctx* ctx, double* V, double* u, double* v, int64_t cap) {
+  if (!ctx) return DDPS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = require_mesh(ctx))) return rc;
+  if (cap < ctx->n_own) { ctx->fail(DDPS_ERR_ARG, "output buffers too small"); return DDPS_ERR_ARG; }
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
-  if ((rc = p2p_setup(ctx))) return rc;
-  ctx->have_mesh = true;
-  ctx->stats.t_setup_ms = now_ms() - t0;
-  if (getenv("DDPS_AMG_TIMING"))
-    fprintf(stderr, "[ddps] mesh_set %.1f ms: uploads + conversion %.1f, pattern build %.1f, allocations %.1f\n", ctx->stats.t_setup_ms,
-            t_up - t0, t_pat - t_up, now_ms() - t_pat);
+  const size_t b = (size_t)ctx->n_own * sizeof(double);
+  if (V) DDPS_CUDA(cudaMemcpy(V, ctx->V, b, cudaMemcpyDeviceToHost));
+  if (u) DDPS_CUDA(cudaMemcpy(u, ctx->U, b, cudaMemcpyDeviceToHost));
+  if (v) DDPS_CUDA(cudaMemcpy(v, ctx->W, b, cudaMemcpyDeviceToHost));
   return DDPS_OK;
 }
 
@@ -891,14 +1020,33 @@ int ddps_dirichlet_set(ddps_ctx* ctx, int field, const int64_t* idx1, const doub
     ctx->base_ready = false;
     return DDPS_OK;
   }
-  std::vector<double> gl(ctx->nq_global, 0.0);
-  std::vector<unsigned char> fl(ctx->nq_global, 0);
-  for (int64_t i = 0; i < nd; ++i) { gl[ids[i]] = val[i]; fl[ids[i]] = 1; }
-  std::vector<unsigned char> lfl(ctx->n_loc);
-  std::vector<double> lg(ctx->n_loc);
-  for (int i = 0; i < ctx->n_loc; ++i) {
-    int64_t g = ctx->loc2glob.empty() ? i : ctx->loc2glob[i];
-    lfl[i] = fl[g]; lg[i] = gl[g];
+  // local copies of the flags / values: every listed node this rank holds (owned or ghost), found by binary search in
+  // the sorted runs of loc2glob (owned nodes ascending, then one ascending run per ghost owner) -- no global array
+  std::vector<unsigned char> lfl(ctx->n_loc, 0);
+  std::vector<double> lg(ctx->n_loc, 0.0);
+  {
+    const std::vector<int64_t>& G = ctx->loc2glob;
+    std::vector<std::pair<int, int>> runs;   // [begin, end) ascending runs
+    int b0 = 0;
+    for (int i = 1; i <= ctx->n_loc; ++i)
+      if (i == ctx->n_loc || i == ctx->n_own || G[i] < G[i - 1]) { if (i > b0) runs.emplace_back(b0, i); b0 = i; }
+    std::vector<std::pair<int64_t, int>> lookup;   // internally renumbered meshes have no long sorted runs: sort once
+    if (runs.size() > 64) {
+      lookup.resize(ctx->n_loc);
+      for (int i = 0; i < ctx->n_loc; ++i) lookup[i] = {G[i], i};
+      std::sort(lookup.begin(), lookup.end());
+    }
+    for (int64_t k = 0; k < nd; ++k) {
+      if (!lookup.empty()) {
+        auto it = std::lower_bound(lookup.begin(), lookup.end(), std::make_pair(ids[k], -1));
+        for (; it != lookup.end() && it->first == ids[k]; ++it) { lfl[it->second] = 1; lg[it->second] = val[k]; }
+        continue;
+      }
+      for (auto& rn : runs) {
+        auto it = std::lower_bound(G.begin() + rn.first, G.begin() + rn.second, ids[k]);
+        if (it != G.begin() + rn.second && *it == ids[k]) { const int i = (int)(it - G.begin()); lfl[i] = 1; lg[i] = val[k]; }
+      }
+    }
   }
   if ((rc = upload(ctx, ctx->isD, lfl.data(), lfl.size()))) return rc;
   if ((rc = upload(ctx, ctx->gD[field], lg.data(), lg.size()))) return rc;

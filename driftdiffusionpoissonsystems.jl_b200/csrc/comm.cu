@@ -12,6 +12,7 @@
 // involvement inside the iteration (k_halo_xchg, k_p2p_allreduce below).  The Jacobi-PCG iteration additionally has its
 // exchanges fused into its three kernels (kernels.cu).
 #include <chrono>
+#include <cstdio>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -300,7 +301,11 @@ __global__ void __launch_bounds__(256) k_halo_xchg(const XchgArgs A, const int* 
   __syncthreads();
   if (threadIdx.x == 0) {
     *(volatile unsigned long long*)A.rflag[j] = A.tag;
-    if (!xspin(A.lflag[j], A.tag, A.err)) { scal->breakdown = 2; scal->done = 1; }
+    if (!xspin(A.lflag[j], A.tag, A.err)) {
+      printf("[ddps] staged halo exchange timed out: tag %llu, block %d of %d, flag seen %llu, n_own %d\n", A.tag, j, A.nneigh,
+             *(volatile const unsigned long long*)A.lflag[j], A.n_own);
+      scal->breakdown = 2; scal->done = 1;
+    }
     __threadfence_system();
   }
   __syncthreads();
@@ -342,6 +347,9 @@ __global__ void k_p2p_allreduce(const RedArgs A, double* vals, PcgScalars* scal,
       if (q == 0) acc[i] = t;
       else acc[i] = ((A.maxmask >> i) & 1) ? fmax(acc[i], t) : acc[i] + t;
     }
+  if (lane < A.nranks && !ok)
+    printf("[ddps] scalar allreduce timed out: rank %d waits for rank %d, tag %llu, flag seen %llu\n", A.rank, lane, A.tag,
+           *(volatile unsigned long long*)&me->rflag[par][lane]);
   if (lane == 0) {
     for (int i = 0; i < A.nv; ++i) vals[i] = acc[i];
     if (!ok) { scal->breakdown = 2; scal->done = 1; }
@@ -351,6 +359,10 @@ __global__ void k_p2p_allreduce(const RedArgs A, double* vals, PcgScalars* scal,
 int halo_xchg(Context* ctx, HaloPlan& H, double* vec, bool check_done) {
   if (ctx->nranks == 1) return 0;
   if (H.p2p && ctx->p2p.xenabled) {
+    // In-process group: the ranks share one device, and with it the copy engines -- a rank whose host runs ahead can park a
+    // device-to-host copy behind a kernel that spins on a peer whose host is itself waiting for a copy queued behind that
+    // one.  A host barrier in front of every spinning kernel keeps the partner's launch unblocked (test transport only).
+    if (ctx->lgroup && !ctx->lgroup->barrier()) return local_fail(ctx);
     if (H.nneigh == 0) return 0;
     P2PHost& P = ctx->p2p;
     XchgArgs A;
@@ -386,6 +398,7 @@ int halo_exchange(Context* ctx, double* vec) { return halo_xchg(ctx, ctx->halo, 
 int scalar_allreduce(Context* ctx, double* dev_vals, int nsum, int nmax, bool check_done) {
   if (ctx->nranks == 1) return 0;
   if (ctx->p2p.xenabled) {
+    if (ctx->lgroup && !ctx->lgroup->barrier()) return local_fail(ctx);   // (see halo_xchg)
     P2PHost& P = ctx->p2p;
     RedArgs A;
     memset(&A, 0, sizeof(A));

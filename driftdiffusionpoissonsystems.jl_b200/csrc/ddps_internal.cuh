@@ -199,6 +199,7 @@ struct Context {
 
   // mesh (local part)
   bool have_mesh = false;
+  bool local_ingest = false;          // mesh came through ddps_mesh_set_local (no rank holds the global mesh)
   int64_t nq_global = 0, nme_global = 0;
   int n_own = 0, n_loc = 0, nme = 0;
   double2* xy = nullptr;

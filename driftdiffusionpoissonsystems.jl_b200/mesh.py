@@ -155,3 +155,92 @@ def structured_mesh(nx, ny, x0=0.0, x1=1.0, y0=0.0, y1=1.0) -> Mesh:
     top = np.vstack([ny * (nx + 1) + nx + 1 - i, ny * (nx + 1) + nx - i, *one(nx, 3)])
     left = np.vstack([(ny - j) * (nx + 1) + 1, (ny - j - 1) * (nx + 1) + 1, *one(ny, 4)])
     return Mesh(nodes, np.ascontiguousarray(np.hstack([bottom, right, top, left])), el)
+
+
+# --------------------------------------------------------------------------------------------
+# Per-rank parts of a structured mesh (multi-GPU runs where no process holds the global mesh;
+# C ABI: ddps_mesh_set_local)
+# --------------------------------------------------------------------------------------------
+class _StructuredNodes:
+    """Lazy stand-in for ``Mesh.nodes`` of a structured mesh: ``nodes[k, ids]`` (k = 0: x, 1: y; ids = 0-based node ids)
+    computes the coordinates instead of storing 2 x nq doubles.  Same values as ``structured_mesh`` bit for bit."""
+
+    def __init__(self, nx, ny, x0, x1, y0, y1):
+        self.nx, self.xs, self.ys = nx, np.linspace(x0, x1, nx + 1), np.linspace(y0, y1, ny + 1)
+        self.shape = (2, (nx + 1) * (ny + 1))
+
+    def __getitem__(self, key):
+        k, ids = key
+        ids = np.asarray(ids, dtype=np.int64)
+        return self.xs[ids % (self.nx + 1)] if k == 0 else self.ys[ids // (self.nx + 1)]
+
+
+def structured_boundary(nx, ny, x0=0.0, x1=1.0, y0=0.0, y1=1.0) -> Mesh:
+    """The boundary of ``structured_mesh``: its edges (tags 1 bottom, 2 right, 3 top, 4 left) and lazily computed node
+    coordinates -- all that the host-side boundary preprocessing (``dirichlet_nodes``, src:162-218) reads."""
+    i = np.arange(nx, dtype=np.int64)
+    j = np.arange(ny, dtype=np.int64)
+    one = lambda n, t: (np.full(n, 1, dtype=np.int64), np.full(n, t, dtype=np.int64))
+    bottom = np.vstack([i + 1, i + 2, *one(nx, 1)])
+    right = np.vstack([j * (nx + 1) + nx + 1, (j + 1) * (nx + 1) + nx + 1, *one(ny, 2)])
+    top = np.vstack([ny * (nx + 1) + nx + 1 - i, ny * (nx + 1) + nx - i, *one(nx, 3)])
+    left = np.vstack([(ny - j) * (nx + 1) + 1, (ny - j - 1) * (nx + 1) + 1, *one(ny, 4)])
+    return Mesh(_StructuredNodes(nx, ny, x0, x1, y0, y1), np.ascontiguousarray(np.hstack([bottom, right, top, left])), None)
+
+
+def structured_mesh_part(nx, ny, x0, x1, y0, y1, rank, nranks):
+    """Rank ``rank``'s part of ``structured_mesh(nx, ny, ...)`` under a partition of the node COLUMNS into ``nranks``
+    vertical strips, built directly (the global mesh is never formed), in the layout ``ddps_mesh_set_local`` takes:
+    owned nodes in increasing global id, ghost nodes (the two neighbouring node columns) sorted by (owner, global id),
+    every triangle touching an owned node in increasing global triangle id with LOCAL 1-based node ids."""
+    ncol = nx + 1
+    cut = [r * ncol // nranks for r in range(nranks + 1)]
+    i0, i1 = cut[rank], cut[rank + 1]
+    if i1 - i0 < 2 and nranks > 1:
+        raise ValueError("strips narrower than two node columns are not supported")
+    xs, ys = np.linspace(x0, x1, nx + 1), np.linspace(y0, y1, ny + 1)
+    jj = np.arange(ny + 1, dtype=np.int64)
+    own_i = np.arange(i0, i1, dtype=np.int64)
+    own_glob = (jj[:, None] * ncol + own_i[None, :]).ravel()                 # increasing global id (j-major)
+    ghost_cols, ghost_owner_of_col = [], []
+    if i0 > 0:
+        ghost_cols.append(i0 - 1); ghost_owner_of_col.append(rank - 1)
+    if i1 < ncol:
+        ghost_cols.append(i1); ghost_owner_of_col.append(rank + 1)
+    n_own = own_glob.size
+    ghost_glob = [jj * ncol + c for c in ghost_cols]                          # per owner: increasing global id
+    node_glob = np.concatenate([own_glob] + ghost_glob) + 1
+    ghost_owner = np.concatenate([np.full(ny + 1, o, dtype=np.int32) for o in ghost_owner_of_col]) if ghost_cols else np.zeros(0, np.int32)
+    n_loc = node_glob.size
+    nodes = np.empty((n_loc, 2))
+    g0 = node_glob - 1
+    nodes[:, 0] = xs[g0 % ncol]
+    nodes[:, 1] = ys[g0 // ncol]
+    # local id of a node (column i, row j): owned -> j*(i1-i0) + (i-i0); ghost column k -> n_own + k*(ny+1) + j
+    w = i1 - i0
+
+    def local_id(i, j):
+        out = j * w + (i - i0)
+        for k, c in enumerate(ghost_cols):
+            out = np.where(i == c, n_own + k * (ny + 1) + j, out)
+        return out + 1
+
+    ci0, ci1 = max(i0 - 1, 0), min(i1, nx)                                    # cell columns [ci0, ci1) touch an owned node column
+    ci = np.arange(ci0, ci1, dtype=np.int64)
+    cj = np.arange(ny, dtype=np.int64)
+    I = np.broadcast_to(ci[None, :], (ny, ci.size)).ravel()
+    J = np.broadcast_to(cj[:, None], (ny, ci.size)).ravel()
+    n00, n10, n11, n01 = local_id(I, J), local_id(I + 1, J), local_id(I + 1, J + 1), local_id(I, J + 1)
+    nme_loc = 2 * I.size
+    el = np.empty((nme_loc, 5), dtype=np.int64)
+    el[0::2, 0], el[0::2, 1], el[0::2, 2] = n00, n10, n11
+    el[1::2, 0], el[1::2, 1], el[1::2, 2] = n00, n11, n01
+    el[:, 3:] = 2
+    elem_glob = np.empty(nme_loc, dtype=np.int64)
+    cell = J * nx + I
+    elem_glob[0::2] = 2 * cell + 1
+    elem_glob[1::2] = 2 * cell + 2
+    return dict(nodes=nodes, n_own=int(n_own), n_loc=int(n_loc), node_glob=np.ascontiguousarray(node_glob, dtype=np.int64),
+                ghost_owner=np.ascontiguousarray(ghost_owner, dtype=np.int32), elements=el, elem_glob=elem_glob,
+                nq_global=(nx + 1) * (ny + 1), nme_global=2 * nx * ny, own_glob=own_glob,
+                boundary=structured_boundary(nx, ny, x0, x1, y0, y1))

@@ -181,6 +181,22 @@ int ddps_comm_init(ddps_ctx* ctx, const char id128[128], int rank, int nranks);
  * call, src:275,284,361,391,...).  With a communicator every rank passes the SAME global mesh. */
 int ddps_mesh_set(ddps_ctx* ctx, const double* nodes, int64_t nq, const int64_t* elements, int64_t nme);
 
+/* Per-rank mesh ingest for multi-GPU runs: every rank passes ONLY its part, nobody holds the global mesh (at 268M triangles
+ * the global arrays are 13 GB per process).  Any node partition is accepted.
+ *   nodes      f64 [2,n_loc]   the n_own nodes this rank owns first, in increasing global id, then its ghost nodes (= every
+ *                              other node of a triangle that touches an owned node), sorted by (owner rank, global id)
+ *   node_glob  i64 [n_loc]     1-based global id of every local node
+ *   ghost_owner i32 [n_loc-n_own]  rank that owns each ghost node
+ *   elements   i64 [5,nme_loc] EVERY triangle that touches an owned node, LOCAL 1-based node ids, increasing global
+ *                              triangle id (= the reference's summation order per matrix entry)
+ *   elem_glob  i64 [nme_loc]   1-based global triangle ids, or NULL (then coefficient slots can only be filled by
+ *                              ddps_coeff_functor, not from global arrays)
+ * Dirichlet sets keep GLOBAL node ids (every rank passes the full, small boundary list).  Results: ddps_ddpe_fetch_owned. */
+int ddps_mesh_set_local(ddps_ctx* ctx, const double* nodes, int64_t n_own, int64_t n_loc, const int64_t* node_glob,
+                        const int32_t* ghost_owner, const int64_t* elements, int64_t nme_loc, const int64_t* elem_glob,
+                        int64_t nq_global, int64_t nme_global);
+int ddps_ddpe_fetch_owned(ddps_ctx* ctx, double* V, double* u, double* v, int64_t cap);
+
 /* Host-only partition query (runs without a GPU context's kernels; used by the CPU tests):
  * owner[nq] <- rank owning each node under recursive coordinate bisection into nparts parts. */
 int ddps_partition_nodes(const double* nodes, int64_t nq, int nparts, int32_t* owner);

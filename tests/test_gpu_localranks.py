@@ -61,7 +61,7 @@ def test_semlin_and_golden_local_ranks(D):
 
 
 @pytest.mark.parametrize("p2p", ["1", "0"])
-@pytest.mark.parametrize("nranks,tail,cells", [(2, 300, (96, 48)), (3, 300, (96, 48)), (2, 200000, (96, 48)), (4, 1500, (192, 96))])
+@pytest.mark.parametrize("nranks,tail,cells", [(2, 1100, (96, 48)), (3, 1100, (128, 64)), (2, 200000, (96, 48)), (4, 1100, (192, 96))])
 def test_distributed_multigrid_local_ranks(D, nranks, tail, cells, p2p, monkeypatch):
     """The distributed multigrid hierarchy (rank-local aggregates, ghost prolongator / A*P rows, halo exchanges of the cycle
     vectors, replicated tail below DDPS_AMG_TAIL rows) against the single-GPU hierarchy on the same problem: fields <= 1e-10,
@@ -99,3 +99,35 @@ def test_distributed_multigrid_semlin_local_ranks(D, monkeypatch):
         assert st["amg_levels"] >= 2
         assert rel_l2(V, z["V"]) <= 1e-8
         assert st["outer_iters"] == 5
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_per_rank_mesh_ingest_local_ranks(D, precond, monkeypatch):
+    """ddps_mesh_set_local: every rank passes only its strip of the structured mesh (nobody holds the global mesh) and
+    fetches only the nodes it owns; the assembled fields equal the single-GPU solve of the global mesh."""
+    monkeypatch.setenv("DDPS_AMG_TAIL", "500")
+    nx, ny, nr = 96, 48, 3
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0)
+    mesh = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
+    ref = _solve_ddpe(D, mesh, pr, precond=precond)
+
+    def work(r, comm):
+        part = D.structured_mesh_part(nx, ny, 0.0, 2.0, 0.0, 1.0, r, nr)
+        with D.Session(0, comm=comm, precond=precond) as s:
+            s.set_mesh_local(part, with_elem_glob=(r % 2 == 0))
+            s.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
+            s.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+            ctrl = []
+            while not ctrl or ctrl[-1] > pr["tol"]:
+                ctrl += list(s.ddpe_step(1, stop_at_tol=True))
+            V, u, v = s.ddpe_fetch_owned()
+            return part["own_glob"], V, u, v, len(ctrl), s.stats()
+
+    out = run_ranks(nr, work)
+    V, u, v = np.zeros(mesh.nq), np.zeros(mesh.nq), np.zeros(mesh.nq)
+    for g, Vr, ur, vr, nit, st in out:
+        V[g], u[g], v[g] = Vr, ur, vr
+        assert nit == ref[3]["outer_iters"]
+        assert (st["amg_levels"] >= 2) == bool(precond)
+    for a, b in ((V, ref[0]), (u, ref[1]), (v, ref[2])):
+        assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)

@@ -191,3 +191,35 @@ def test_terminal_current_postprocessing_matches_oracle(D, O):
     I1ref = O.calculate_current(om, "zero", E, pr1["Vbddata"], pr1["ubddata"], pr1["vbddata"], pr1["lam"], 1.0, 0.0, 0.0,
                                 pr1["mu_p"], pr1["mu_n"], pr1["C"], 1e-12, fields=(z1["V"], z1["u"], z1["v"]))[0]
     assert abs(I1 - I1ref) <= 1e-11 * max(1.0, abs(I1ref))
+
+
+def test_structured_mesh_parts_tile_the_global_mesh():
+    """Per-rank mesh parts (ddps_mesh_set_local input): owned nodes partition the nodes, every triangle touching an owned
+    node is present in increasing global id with consistent local ids, ghosts are exactly the other corners of those
+    triangles, coordinates equal the global mesh's bit for bit, and the boundary-only mesh gives the same Dirichlet lists."""
+    import ddps_b200 as D
+    nx, ny = 12, 5
+    m = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
+    for nr in (1, 2, 3, 4):
+        seen = np.zeros(m.nq, int)
+        for r in range(nr):
+            p = D.structured_mesh_part(nx, ny, 0.0, 2.0, 0.0, 1.0, r, nr)
+            g = p["node_glob"] - 1
+            assert np.array_equal(p["nodes"][:, 0], m.nodes[0, g]) and np.array_equal(p["nodes"][:, 1], m.nodes[1, g])
+            assert np.all(np.diff(g[:p["n_own"]]) > 0)
+            seen[g[:p["n_own"]]] += 1
+            eg = p["elem_glob"] - 1
+            assert np.array_equal(g[p["elements"][:, :3] - 1] + 1, m.elements[:3, eg].T)
+            owned = np.zeros(m.nq, bool)
+            owned[g[:p["n_own"]]] = True
+            assert np.array_equal(np.nonzero(owned[m.elements[:3] - 1].any(axis=0))[0], eg)
+            assert set(np.unique(m.elements[:3, eg] - 1).tolist()) == set(g.tolist())
+            if nr > 1:
+                go = p["ghost_owner"]
+                key = go.astype(np.int64) * m.nq + g[p["n_own"]:]
+                assert np.all(np.diff(key) > 0)
+        assert np.all(seen == 1)
+        bd = [[2, 4], ["D", "D"], [lambda x, y: x + 2 * y] * 2]
+        n1, v1 = D.dirichlet_nodes(p["boundary"], bd)
+        n2, v2 = D.dirichlet_nodes(m, bd)
+        assert np.array_equal(n1, n2) and np.array_equal(v1, v2)
