@@ -239,6 +239,9 @@ def main():
     ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"],
                     help="preconditioner of the hand-written CG: amg = smoothed-aggregation multigrid V-cycle (default), "
                          "jacobi = the diagonal preconditioner the north star names")
+    ap.add_argument("--digest", default="", help="after the timed solves run one more whole solve and write every 997th node's V,u,v "
+                                                 "(global ids) of this rank to <digest>_n<N>_r<rank>.npz: cross-checks between runs")
+    ap.add_argument("--no-lag", action="store_true", help="opts.amg_no_lag=1 (saves the per-kind operator copies: memory)")
     ap.add_argument("--pcg-cap", type=int, default=0,
                     help="PROFILING ONLY: cap every PCG solve at this many iterations (keeps an ncu launch list short); "
                          "the printed value is then not a benchmark number")
@@ -273,40 +276,73 @@ def main():
 
     precond = args.precond
     sopts = dict(precond=1) if precond == "amg" else {}
+    if args.no_lag:
+        sopts["amg_no_lag"] = 1
     pr = problem()
-    mesh0 = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
-    # the caller's arrays in pinned host memory, in the ABI's layout (= the reference's Julia arrays: nodes 2 x nq and
-    # elements 5 x nme column-major); the Mesh handed to the library is a zero-copy view of them
-    nodes = torch.from_numpy(np.ascontiguousarray(mesh0.nodes.T)).pin_memory().numpy()
-    elems = torch.from_numpy(np.ascontiguousarray(mesh0.elements.T)).pin_memory().numpy()
-    mesh = D.Mesh(nodes.T, mesh0.edges, elems.T)
-    del mesh0
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    if world == 1:
+        mesh0 = D.structured_mesh(nx, ny, 0.0, 2.0, 0.0, 1.0)
+        # the caller's arrays in pinned host memory, in the ABI's layout (= the reference's Julia arrays: nodes 2 x nq and
+        # elements 5 x nme column-major); the Mesh handed to the library is a zero-copy view of them
+        nodes, elems = pin(mesh0.nodes.T), pin(mesh0.elements.T)
+        mesh = D.Mesh(nodes.T, mesh0.edges, elems.T)
+        nq = mesh.nq
+        del mesh0
+        part = None
+        h2d_mesh = nodes.nbytes + elems.nbytes
+    else:
+        # multi-GPU: per-rank mesh ingest -- every rank builds and uploads ONLY its strip of the mesh (ddps_mesh_set_local);
+        # nobody holds the global arrays (13 GB per process at 268M triangles)
+        part = D.structured_mesh_part(nx, ny, 0.0, 2.0, 0.0, 1.0, rank, world)
+        for k in ("nodes", "elements", "node_glob"):
+            part[k] = pin(part[k])
+        part["elem_glob"] = None     # coefficients are sampled on the device: no global triangle ids needed
+        mesh = None
+        nq = part["nq_global"]
+        h2d_mesh = part["nodes"].nbytes + part["elements"].nbytes + part["node_glob"].nbytes
 
     def fresh_session():
         return D.Session(local, comm=new_comm(torch, dist, rank, world) if dist is not None else None, **sopts)
+
+    def load(s):
+        if part is None:
+            s.set_mesh(mesh)
+        else:
+            s.set_mesh_local(part)
+        s.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
 
     # ---- e2e FIRST (cold): D.solve_ddpe(mesh, closures..., tol) -> (V,u,v) -----------------------------------------
     e2e = None
     if not args.no_e2e and args.pcg_cap == 0:
         # one-time PROCESS initialisation is not part of the measurement: a tiny solve creates the CUDA context, loads the
         # library's kernels (lazy module loading) and creates the memory pool
-        with fresh_session() as sw:
+        with D.Session(local, **sopts) as sw:
             D.solve_ddpe(D.structured_mesh(64, 32, 0.0, 2.0, 0.0, 1.0), *[pr[k] for k in KEYS], session=sw, verbose=False)
         barrier()
         t0 = time.perf_counter()
         s2 = fresh_session()
-        V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s2, return_stats=True, verbose=False)
+        if part is None:
+            V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s2, return_stats=True, verbose=False)
+            iters = int(st["outer_iters"])
+        else:
+            # the same call sequence solve_ddpe makes, on this rank's part of the mesh; every rank fetches the nodes it owns
+            load(s2)
+            s2.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+            iters = len(s2.ddpe_step(1000, stop_at_tol=True))
+            V, u, v = s2.ddpe_fetch_owned()
+            st = s2.stats()
         barrier()
         t_e2e = allmax(time.perf_counter() - t0)
-        iters = int(st["outer_iters"])
-        nd = len(D.dirichlet_nodes(mesh, pr["Vbddata"])[0])
-        h2d = nodes.nbytes + elems.nbytes + 3 * 16 * nd      # mesh + three Dirichlet (node,value) lists; coefficients sampled on the device
-        d2h = 3 * 8 * mesh.nq
+        nd = len(D.dirichlet_nodes(mesh if part is None else part["boundary"], pr["Vbddata"])[0])
+        h2d = h2d_mesh + 3 * 16 * nd      # mesh + three Dirichlet (node,value) lists; coefficients sampled on the device
+        d2h = 3 * 8 * (nq if part is None else part["n_own"])
         e2e = {"value": iters / t_e2e, "unit": "1/s", "h2d_bytes_per_step": h2d / iters, "d2h_bytes_per_step": d2h / iters,
                "seconds": t_e2e, "gummel_iters_to_tol": iters,
-               "what": "cold D.solve_ddpe(mesh, closures..., tol) -> (V,u,v): context creation, mesh H2D from pinned host arrays, pattern "
-                       "build, boundary preprocessing on the host, coefficient closures (registered spatial functors) sampled on the "
-                       "device, base stiffness + multigrid hierarchy setup, Gummel to tol, D2H of V,u,v",
+               "what": ("cold D.solve_ddpe(mesh, closures..., tol) -> (V,u,v): " if part is None else
+                        "cold solve_ddpe call sequence on per-rank mesh parts (bytes: this rank's), every rank fetches its owned nodes: ")
+                       + "context creation, mesh H2D from pinned host arrays, pattern build, boundary preprocessing on the host, "
+                         "coefficient closures (registered spatial functors) sampled on the device, base stiffness + multigrid "
+                         "hierarchy setup, Gummel to tol, D2H of V,u,v",
                "setup_seconds": st["t_setup_ms"] / 1000.0 + st["t_amg_setup_ms"] / 1000.0, "final_control": float(st["control"])}
         s2.close()
         del V, u, v
@@ -315,8 +351,7 @@ def main():
     s = fresh_session()
     if args.pcg_cap > 0:
         s.set_opts(lin_max_it=args.pcg_cap, lin_cap_ok=1, max_newton=3)
-    s.set_mesh(mesh)
-    s.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
+    load(s)
     timed_solves(s, pr, args.warmup, barrier, allmax)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -325,6 +360,20 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = args.steps / (R["ms"] / 1000.0)
     levels = s.amg_levels() if precond == "amg" else []
+    amg_built = s.stats()["amg_levels"]
+    if args.digest:
+        s.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+        nit = len(s.ddpe_step(1000, stop_at_tol=True))
+        if part is None:
+            Vd, ud, vd = s.ddpe_fetch()
+            gid = np.arange(nq, dtype=np.int64)
+        else:
+            Vd, ud, vd = s.ddpe_fetch_owned()
+            gid = part["own_glob"]
+        pick = (gid % 997) == 0
+        np.savez(f"{args.digest}_n{world}_r{rank}.npz", gid=gid[pick], V=Vd[pick], u=ud[pick], v=vd[pick], iters=nit,
+                 sums=np.array([Vd.sum(), ud.sum(), vd.sum(), (Vd * Vd).sum(), (ud * ud).sum(), (vd * vd).sum()]))
+        del Vd, ud, vd
 
     # ---- roofline: every kernel of the benchmarked iteration, timed live in this process (CUDA events on the library
     #      stream, ddps_time_kernel); share = launches per step x ms per launch / ms per step -------------------------------
@@ -410,7 +459,8 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(nx, ny),
                            "l2": "inputs larger than L2 (CSR values+columns 705 MB at s16); no flush needed",
-                           "parallelism": f"node-partitioned x{world}" if world > 1 else "single GPU",
+                           "parallelism": (f"node-partitioned x{world} (vertical strips, one process per GPU, per-rank mesh ingest; distributed "
+                                           f"multigrid hierarchy: {amg_built} levels, rows owned by rank 0 per level {levels})") if world > 1 else "single GPU",
                            "solver": ("hand-written CG preconditioned with a smoothed-aggregation multigrid V(1,1) cycle "
                                       "(opts.precond=1; SURVEY 8f rank 1), lin_rtol 1e-13, Newton corrections to 0.1*tol"
                                       if precond == "amg" else "Jacobi-PCG, lin_rtol 1e-13, Newton corrections to 0.1*tol"),

@@ -58,6 +58,44 @@ double wall_ms() {
 
 }  // namespace
 
+// ---- iteration timeline (DDPS_PROFILE_ITER) ----
+static inline void prof_mark(Context* ctx, const char* name) {
+  AmgProf& P = ctx->amg->prof;
+  if (!P.armed || P.n >= 96) return;
+  P.name[P.n] = name;
+  cudaEventRecord(P.ev[P.n++], ctx->stream);
+}
+static void prof_begin(Context* ctx) {
+  AmgProf& P = ctx->amg->prof;
+  if (!P.on) return;
+  if (!P.have_ev) { for (int i = 0; i < 96; ++i) cudaEventCreate(&P.ev[i]); P.have_ev = true; }
+  P.armed = true;
+  P.n = 0;
+  prof_mark(ctx, "start");
+}
+static void prof_end(Context* ctx) {
+  AmgProf& P = ctx->amg->prof;
+  if (!P.armed) return;
+  P.armed = false;
+  cudaEventSynchronize(P.ev[P.n - 1]);
+  for (int i = 1; i < P.n; ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, P.ev[i - 1], P.ev[i]);
+    P.acc[i] += ms;
+  }
+  P.samples++;
+}
+static void prof_report(Context* ctx) {
+  AmgProf& P = ctx->amg->prof;
+  if (!P.on || !P.samples) return;
+  double tot = 0;
+  for (int i = 1; i < P.n; ++i) tot += P.acc[i];
+  fprintf(stderr, "[ddps prof] rank %d: one CG iteration = %.1f us (mean of %d sampled iterations)\n", ctx->rank, 1e3 * tot / P.samples, P.samples);
+  for (int i = 1; i < P.n; ++i) fprintf(stderr, "[ddps prof] rank %d   %-28s %7.1f us\n", ctx->rank, P.name[i], 1e3 * P.acc[i] / P.samples);
+  if (P.have_ev) for (int i = 0; i < 96; ++i) cudaEventDestroy(P.ev[i]);
+  P.have_ev = false;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------------------
@@ -632,6 +670,7 @@ bool amg_ready(const Context* ctx) { return ctx->amg && ctx->amg->ready; }
 void amg_free(Context* ctx) {
   Amg* A = ctx->amg;
   if (!A) return;
+  prof_report(ctx);
   for (int l = 0; l < kAmgMaxLevels; ++l) {
     AmgLevelDev& L = A->lv[l];
     if (L.owns) { amg_release(L.slice_ptr); amg_release(L.col); amg_release(L.rowptr); }
@@ -730,6 +769,7 @@ static int amg_setup_dist(Context* ctx) {
   Amg* A = new Amg();
   ctx->amg = A;
   A->omega = prm.omega;
+  A->prof.on = getenv("DDPS_PROFILE_ITER") != nullptr;
   int rc;
   {
     AmgLevelDev& L = A->lv[0];
@@ -789,6 +829,7 @@ int amg_setup(Context* ctx) {
   Amg* A = new Amg();
   ctx->amg = A;
   A->omega = prm.omega;
+  A->prof.on = getenv("DDPS_PROFILE_ITER") != nullptr;
   int rc;
   {
     AmgLevelDev& L = A->lv[0];
@@ -1187,8 +1228,11 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
       ctx->stats.kernel_launches++;                                                                    // levels: fused in restrict)
     }
     if (L.dist && (rc = halo_xchg(ctx, *L.plan, L.x, true))) return rc;
+    if (L.dist) prof_mark(ctx, l == 0 ? "L0 halo(x)" : "L>0 halo(x)");
     launch_amg_spmv<1, false>(ctx, L, L.x, L.b, om, L.t);
+    prof_mark(ctx, l == 0 ? "L0 residual spmv" : l == 1 ? "L1 residual spmv" : "L>1 residual spmv");
     if (L.dist == 1 && (rc = halo_xchg(ctx, *L.plan, L.t, true))) return rc;
+    if (L.dist == 1) prof_mark(ctx, l == 0 ? "L0 halo(t)" : "L>0 halo(t)");
     AmgLevelDev& C = A.lv[l + 1];
     const bool coarsest = (l + 2 == A.nlev);
     const bool fuse_sweep = !coarsest && L.dist != 2;   // transition: the sweep needs the COMPLETED right-hand side
@@ -1199,28 +1243,35 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
       k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr, om, C.x,
                                                               ctx->scal);
     ctx->stats.kernel_launches++;
+    prof_mark(ctx, l == 0 ? "L0 restrict" : l == 1 ? "L1 restrict" : "L>1 restrict");
     if (L.dist == 2) {
       if ((rc = comm_allreduce(ctx, C.b, (size_t)C.n, COMM_SUM))) return rc;
       if (!coarsest) {
         k_amg_jac0<<<amg_grid(ctx, C.n, 256), 256, 0, st>>>(C.n, om, C.cur_dinv, C.b, C.x, ctx->scal);
         ctx->stats.kernel_launches++;
       }
+      prof_mark(ctx, "tail allreduce + sweep");
     }
   }
   {
     AmgLevelDev& L = A.lv[A.nlev - 1];
     k_amg_dense_apply<<<1, 1024, 0, st>>>(L.n, A.cur_dense, L.b, L.x2, ctx->scal);
     ctx->stats.kernel_launches++;
+    prof_mark(ctx, "coarsest solve");
   }
   for (int l = A.nlev - 2; l >= 0; --l) {
     AmgLevelDev& L = A.lv[l];
     AmgLevelDev& C = A.lv[l + 1];
     if (L.dist == 1 && (rc = halo_xchg(ctx, *C.plan, C.x2, true))) return rc;
+    if (L.dist == 1) prof_mark(ctx, l == 0 ? "L0 halo(xc)" : "L>0 halo(xc)");
     k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pent, C.x2, L.x, ctx->scal);
     ctx->stats.kernel_launches++;
+    prof_mark(ctx, l == 0 ? "L0 prolong" : l == 1 ? "L1 prolong" : "L>1 prolong");
     if (L.dist && (rc = halo_xchg(ctx, *L.plan, L.x, true))) return rc;
+    if (L.dist) prof_mark(ctx, l == 0 ? "L0 halo(x) 2" : "L>0 halo(x) 2");
     if (l == 0 && dot_rz) launch_amg_spmv<2, true>(ctx, L, L.x, L.b, om, L.x2);
     else launch_amg_spmv<2, false>(ctx, L, L.x, L.b, om, L.x2);
+    prof_mark(ctx, l == 0 ? "L0 smoothing spmv" : l == 1 ? "L1 smoothing spmv" : "L>1 smoothing spmv");
   }
   DDPS_CUDA(cudaGetLastError());
   return 0;
@@ -1304,23 +1355,31 @@ int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it) {
   const bool mr = ctx->nranks > 1;
   int rc;
   const int g2 = amg_grid(ctx, n, kVecBlock);
+  if (it == 3) prof_begin(ctx);
   if (mr && (rc = halo_xchg(ctx, ctx->halo, ctx->p, true))) return rc;              // ghost entries of the search direction
+  if (mr) prof_mark(ctx, "halo(p)");
   if ((rc = launch_spmv_dot(ctx, A.lv[0].cur_val, ctx->p, ctx->q))) return rc;    // q = A p, p.q -> sums[0]
+  prof_mark(ctx, "CG spmv + p.Ap");
   if (mr) {
     if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[0], 1, 0, true))) return rc;
+    prof_mark(ctx, "allreduce p.Ap");
     k_apcg_update<false><<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
                                                             A.lv[0].x, ctx->partials, ctx->scal);
     if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[2], 1, 1, true))) return rc;   // {r.r, max|r|}
     k_apcg_decide<<<1, 1, 0, ctx->stream>>>(ctx->scal, par, it, max_it);
     ctx->stats.kernel_launches++;
+    prof_mark(ctx, "update + allreduce + decide");
   } else {
     k_apcg_update<true><<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
                                                            A.lv[0].x, ctx->partials, ctx->scal);
+    prof_mark(ctx, "update");
   }
   if ((rc = amg_vcycle_impl(ctx, ctx->r, A.z, true, true))) return rc;             // z = B r, r.z -> sums[1]
   if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[1], 1, 0, true))) return rc;
   k_apcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, 0, 0.0, A.z, ctx->p, ctx->scal);
+  prof_mark(ctx, mr ? "allreduce r.z + direction" : "direction");
   ctx->stats.kernel_launches += 2;
+  if (it == 3) prof_end(ctx);
   return 0;
 }
 

@@ -70,8 +70,20 @@ struct AmgOpSet {
   double* dense = nullptr;
 };
 
+// DDPS_PROFILE_ITER=1: CUDA-event timeline of ONE CG iteration per solve (the 4th), accumulated per phase and printed when the
+// hierarchy is freed -- where the iteration's time goes, including the exchanges (no profiler needed, works on every rank)
+struct AmgProf {
+  bool on = false, armed = false;
+  int n = 0, samples = 0;
+  cudaEvent_t ev[96];
+  const char* name[96];
+  double acc[96] = {0};
+  bool have_ev = false;
+};
+
 struct Amg {
   bool ready = false;
+  AmgProf prof;
   int nlev = 0;
   AmgLevelDev lv[kAmgMaxLevels];
   double* dense = nullptr;   // [n_coarsest^2] inverse of the coarsest operator

@@ -64,6 +64,40 @@ def main():
     for a, b in ((Vn, V1), (un, u1), (vn, v1)):
         assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)
     assert stn["outer_iters"] == st1["outer_iters"]
+    # 4. the DISTRIBUTED multigrid hierarchy (opts.precond = 1) against the single-GPU hierarchy: fields <= 1e-10, equal Gummel
+    #    and Newton counts, at most 3 more CG iterations in any solve; forced to build distributed levels on this small mesh
+    os.environ["DDPS_AMG_TAIL"] = "1100"
+    mesh = D.structured_mesh(192, 96, 0.0, 2.0, 0.0, 1.0)
+    with D.Session(local, comm=new_comm(rank, world), precond=1) as s:
+        Vn, un, vn, stn = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+    assert stn["amg_levels"] >= 3, stn["amg_levels"]
+    with D.Session(local, precond=1) as s:
+        V1, u1, v1, st1 = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+    for a, b in ((Vn, V1), (un, u1), (vn, v1)):
+        assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)
+    assert stn["outer_iters"] == st1["outer_iters"] and list(stn["newton_per_vsolve"]) == list(st1["newton_per_vsolve"])
+    assert np.all(np.array(stn["pcg_per_solve"]) <= np.array(st1["pcg_per_solve"]) + 3), (stn["pcg_per_solve"], st1["pcg_per_solve"])
+    # 5. per-rank mesh ingest (ddps_mesh_set_local) + owned-node fetch, multigrid path, vs the same single-GPU solve
+    part = D.structured_mesh_part(192, 96, 0.0, 2.0, 0.0, 1.0, rank, world)
+    with D.Session(local, comm=new_comm(rank, world), precond=1) as s:
+        s.set_mesh_local(part)
+        s.setup_ddpe(pr["Vbddata"], pr["ubddata"], pr["vbddata"], pr["lam"], pr["mu_p"], pr["mu_n"], pr["C"])
+        s.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
+        ctrl = []
+        while not ctrl or ctrl[-1] > pr["tol"]:
+            ctrl += list(s.ddpe_step(1, stop_at_tol=True))
+        Vo, uo, vo = s.ddpe_fetch_owned()
+    g = part["own_glob"]
+    assert len(ctrl) == st1["outer_iters"]
+    for a, b in ((Vo, V1[g]), (uo, u1[g]), (vo, v1[g])):
+        assert np.linalg.norm(a - b) <= 1e-10 * np.linalg.norm(b)
+    # 6. the same with the NCCL transport instead of the peer-memory kernels
+    os.environ["DDPS_P2P"] = "0"
+    with D.Session(local, comm=new_comm(rank, world), precond=1) as s:
+        Vq, uq, vq, stq = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+    del os.environ["DDPS_P2P"]
+    for a, b in ((Vq, V1), (uq, u1), (vq, v1)):
+        assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)
     dist.barrier()
     if rank == 0:
         print(f"MGPU_OK world={world}")
