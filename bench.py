@@ -361,6 +361,8 @@ def main():
     value = args.steps / (R["ms"] / 1000.0)
     levels = s.amg_levels() if precond == "amg" else []
     amg_built = s.stats()["amg_levels"]
+    free_b, total_b = torch.cuda.mem_get_info()
+    mem_used_gb = allmax((total_b - free_b) / 2 ** 30)
     if args.digest:
         s.ddpe_begin(pr["rec_mode"], pr["delta"], pr["tau_p"], pr["tau_n"], pr["tol"])
         nit = len(s.ddpe_step(1000, stop_at_tol=True))
@@ -472,7 +474,7 @@ def main():
                                          if precond == "amg" else "f64 throughout")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": R["launches"], "pcg_iterations": R["pcg"],
                 "gummel_iters_to_tol": R["per_solve"][0] if R["per_solve"] else None, "solves_timed": R["nsolves"],
-                "setup_ms_per_solve": R["setup_ms"] / R["nsolves"], "amg_levels": levels,
+                "setup_ms_per_solve": R["setup_ms"] / R["nsolves"], "amg_levels": levels, "gpu_mem_used_gb_max_over_ranks": mem_used_gb,
                 "control": R["control"], "roofline": roofline, "cpu_baseline": cpu, "same_size_pair": pair}
         if args.pcg_cap > 0:
             line["invalid"] = f"profiling run: PCG capped at {args.pcg_cap} iterations per solve"

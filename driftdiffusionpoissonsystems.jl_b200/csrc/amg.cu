@@ -244,7 +244,7 @@ __global__ void k_amg_prolong(int n, const int* __restrict__ Pptr, const int2* _
 #pragma unroll 1   // rows hold 2-4 entries: a 16x unrolled body would never run
     for (int m = Pptr[i]; m < e; ++m) {
       const int2 en = Pent[m];
-      s += (double)__int_as_float(en.y) * __ldg(xc + en.x);
+      if (en.x >= 0) s += (double)__int_as_float(en.y) * __ldg(xc + en.x);
     }
     x[i] += s;
   }
@@ -1264,11 +1264,13 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
     AmgLevelDev& C = A.lv[l + 1];
     if (L.dist == 1 && (rc = halo_xchg(ctx, *C.plan, C.x2, true))) return rc;
     if (L.dist == 1) prof_mark(ctx, l == 0 ? "L0 halo(xc)" : "L>0 halo(xc)");
-    k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, L.Pptr, L.Pent, C.x2, L.x, ctx->scal);
+    // distributed levels: the ghost rows are prolonged too (their prolongator rows came from their owners at setup, their
+    // pre-smoothed x from the exchange on the way down): same numbers in the same order as on the owner, so x needs no
+    // exchange before the smoothing sweep
+    const int np = L.dist ? L.n_loc : L.n;
+    k_amg_prolong<<<amg_grid(ctx, np, 256), 256, 0, st>>>(np, L.Pptr, L.Pent, C.x2, L.x, ctx->scal);
     ctx->stats.kernel_launches++;
     prof_mark(ctx, l == 0 ? "L0 prolong" : l == 1 ? "L1 prolong" : "L>1 prolong");
-    if (L.dist && (rc = halo_xchg(ctx, *L.plan, L.x, true))) return rc;
-    if (L.dist) prof_mark(ctx, l == 0 ? "L0 halo(x) 2" : "L>0 halo(x) 2");
     if (l == 0 && dot_rz) launch_amg_spmv<2, true>(ctx, L, L.x, L.b, om, L.x2);
     else launch_amg_spmv<2, false>(ctx, L, L.x, L.b, om, L.x2);
     prof_mark(ctx, l == 0 ? "L0 smoothing spmv" : l == 1 ? "L1 smoothing spmv" : "L>1 smoothing spmv");

@@ -919,7 +919,9 @@ int amg_dist_coarsen(Context* ctx, Amg* A, int l, const AmgParams& prm, long lon
   // ---- 8. the ghost aggregates this rank needs: every non-owned coarse id in its coarse rows, in the A*P rows and in the
   //         prolongator rows of its owned fine nodes; sorted by global id = grouped by owner ----
   const int nAP_own = F.ap_ghost_base;
-  const long long ncand = nk + nAP_own + nP_own;
+  // (the prolongator rows of the GHOST fine nodes count too: the cycle prolongs onto them redundantly, which saves the halo
+  //  exchange of x after the prolongation)
+  const long long ncand = nk + nAP_own + nP;
   if (ncand >= (1LL << 31) - 1) { ctx->fail(DDPS_ERR_ARG, "distributed multigrid: too many structural products on one rank"); return DDPS_ERR_ARG; }
   int *d_cand, *d_cand2, *d_ng;
   DDPS_CUDA(tmp.alloc(&d_cand, (size_t)std::max<long long>(ncand, 1)));
@@ -927,7 +929,7 @@ int amg_dist_coarsen(Context* ctx, Amg* A, int l, const AmgParams& prm, long lon
   DDPS_CUDA(tmp.alloc(&d_ng, 4));
   if (nk) k_cand_keys<<<nblk(nk, T), T, 0, st>>>(nk, d_k0, off, nc, d_cand);
   if (nAP_own) k_cand_int<<<nblk(nAP_own, T), T, 0, st>>>(nAP_own, F.APcol, off, nc, d_cand + nk);
-  if (nP_own) k_cand_int2<<<nblk(nP_own, T), T, 0, st>>>(nP_own, F.Pent, off, nc, d_cand + nk + nAP_own);
+  if (nP) k_cand_int2<<<nblk(nP, T), T, 0, st>>>(nP, F.Pent, off, nc, d_cand + nk + nAP_own);
   int ngh = 0;
   std::vector<int> gl;
   if (ncand > 0) {

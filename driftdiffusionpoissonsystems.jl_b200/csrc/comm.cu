@@ -276,41 +276,52 @@ __device__ __forceinline__ bool xspin(const volatile unsigned long long* flag, u
 }
 
 struct XchgArgs {
-  int nneigh, n_own;
+  int nneigh, n_own, nslice;
   int send_off[kMaxRanks + 1], recv_off[kMaxRanks + 1];
   double* rstage[kMaxRanks];                     // the peer's staging buffer (this tag's half) at my block's offset
   unsigned long long* rflag[kMaxRanks];          // &peer window->xflag[me]
   const unsigned long long* lflag[kMaxRanks];    // &my window->xflag[peer]
   const double* lstage;                          // my staging buffer (this tag's half)
+  unsigned* ticket;                              // [kMaxRanks] my window's slice tickets
   unsigned long long tag;
   int* err;
 };
 
-// Block j serves neighbour j: stores my boundary values into ITS staging buffer over NVLink, raises its flag, waits for its
-// block to land in MY staging buffer and copies it into the ghost part of `vec`.  When the kernel has finished the ghosts are
-// final, so every consumer reads them through the normal (read-only) path.  Staging is double-buffered by tag parity: a peer
-// can be at most one exchange ahead of me (its exchange k+1 completes only after my push k+1, which follows my copy-out k).
-__global__ void __launch_bounds__(256) k_halo_xchg(const XchgArgs A, const int* __restrict__ send_idx, double* vec, PcgScalars* scal,
+// nslice blocks serve neighbour j (blockIdx.x = j * nslice + s): each stores its slice of my boundary values into the
+// neighbour's staging buffer over NVLink; the block that finishes last raises the neighbour's flag; then every block waits
+// for the neighbour's block to land in MY staging buffer and copies its slice into the ghost part of `vec`.  (One block of
+// 256 threads per neighbour made the two gather loops -- 8193 entries per neighbour at 268M triangles on 8 GPUs -- a chain
+// of 32 dependent-latency steps each: ~20 us per exchange; sliced, an exchange is two short steps around the NVLink round
+// trip.)  When the kernel has finished the ghosts are final, so every consumer reads them through the normal (read-only)
+// path.  Staging is double-buffered by tag parity: a peer can be at most one exchange ahead of me (its exchange k+1 completes
+// only after my push k+1, which follows my copy-out k).
+__global__ void __launch_bounds__(512) k_halo_xchg(const XchgArgs A, const int* __restrict__ send_idx, double* vec, PcgScalars* scal,
                                                   int check_done) {
   if (check_done && scal->done) return;
-  const int j = blockIdx.x;
+  __shared__ bool s_last;
+  const int j = blockIdx.x / A.nslice, sl = blockIdx.x - j * A.nslice;
   const int s0 = A.send_off[j], ns = A.send_off[j + 1] - s0;
   double* dst = A.rstage[j];
-  for (int i = threadIdx.x; i < ns; i += blockDim.x) dst[i] = vec[send_idx[s0 + i]];
+  for (int i = sl * blockDim.x + threadIdx.x; i < ns; i += A.nslice * blockDim.x) dst[i] = vec[send_idx[s0 + i]];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    *(volatile unsigned long long*)A.rflag[j] = A.tag;
+    s_last = atomicInc(&A.ticket[j], A.nslice - 1) == (unsigned)(A.nslice - 1);
+    if (s_last) {
+      __threadfence_system();
+      *(volatile unsigned long long*)A.rflag[j] = A.tag;
+    }
     if (!xspin(A.lflag[j], A.tag, A.err)) {
-      printf("[ddps] staged halo exchange timed out: tag %llu, block %d of %d, flag seen %llu, n_own %d\n", A.tag, j, A.nneigh,
-             *(volatile const unsigned long long*)A.lflag[j], A.n_own);
+      if (sl == 0)
+        printf("[ddps] staged halo exchange timed out: tag %llu, neighbour %d of %d, flag seen %llu, n_own %d\n", A.tag, j, A.nneigh,
+               *(volatile const unsigned long long*)A.lflag[j], A.n_own);
       scal->breakdown = 2; scal->done = 1;
     }
     __threadfence_system();
   }
   __syncthreads();
   const int r0 = A.recv_off[j], nr = A.recv_off[j + 1] - r0;
-  for (int i = threadIdx.x; i < nr; i += blockDim.x) vec[A.n_own + r0 + i] = __ldcg(A.lstage + r0 + i);
+  for (int i = sl * blockDim.x + threadIdx.x; i < nr; i += A.nslice * blockDim.x) vec[A.n_own + r0 + i] = __ldcg(A.lstage + r0 + i);
 }
 
 struct RedArgs {
@@ -359,11 +370,15 @@ __global__ void k_p2p_allreduce(const RedArgs A, double* vals, PcgScalars* scal,
 int halo_xchg(Context* ctx, HaloPlan& H, double* vec, bool check_done) {
   if (ctx->nranks == 1) return 0;
   if (H.p2p && ctx->p2p.xenabled) {
-    // In-process group: the ranks share one device, and with it the copy engines -- a rank whose host runs ahead can park a
-    // device-to-host copy behind a kernel that spins on a peer whose host is itself waiting for a copy queued behind that
-    // one.  A host barrier in front of every spinning kernel keeps the partner's launch unblocked (test transport only).
+    // In-process group: the ranks share one device AND one driver context.  A rank whose host runs ahead can enter a driver
+    // call that blocks on its own stream (a copy to pageable memory, cudaFree) while holding the context lock -- behind a kernel
+    // that spins on a peer whose host then cannot even launch the kernel it waits for.  Host barriers around the launch of
+    // every spinning kernel make sure both kernels sit in their streams before anybody proceeds (test transport only).
     if (ctx->lgroup && !ctx->lgroup->barrier()) return local_fail(ctx);
-    if (H.nneigh == 0) return 0;
+    if (H.nneigh == 0) {
+      if (ctx->lgroup && !ctx->lgroup->barrier()) return local_fail(ctx);
+      return 0;
+    }
     P2PHost& P = ctx->p2p;
     XchgArgs A;
     memset(&A, 0, sizeof(A));
@@ -380,9 +395,14 @@ int halo_xchg(Context* ctx, HaloPlan& H, double* vec, bool check_done) {
     }
     A.lstage = P.stage_local + half;
     A.err = &P.win_local->error;
-    k_halo_xchg<<<H.nneigh, 256, 0, ctx->stream>>>(A, H.send_idx, vec, ctx->scal, check_done ? 1 : 0);
+    A.ticket = P.win_local->xticket;
+    int widest = 1;
+    for (int j = 0; j < H.nneigh; ++j) widest = std::max(widest, std::max(H.send_off[j + 1] - H.send_off[j], H.recv_off[j + 1] - H.recv_off[j]));
+    A.nslice = std::max(1, std::min(16, (widest + 511) / 512));
+    k_halo_xchg<<<H.nneigh * A.nslice, 512, 0, ctx->stream>>>(A, H.send_idx, vec, ctx->scal, check_done ? 1 : 0);
     ctx->stats.kernel_launches++;
     DDPS_CUDA(cudaGetLastError());
+    if (ctx->lgroup && !ctx->lgroup->barrier()) return local_fail(ctx);
     return 0;
   }
   // every rank takes part in the backend exchange, also one without neighbours (the in-process backend is collective)
@@ -411,6 +431,7 @@ int scalar_allreduce(Context* ctx, double* dev_vals, int nsum, int nmax, bool ch
     k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(A, dev_vals, ctx->scal, check_done ? 1 : 0);
     ctx->stats.kernel_launches++;
     DDPS_CUDA(cudaGetLastError());
+    if (ctx->lgroup && !ctx->lgroup->barrier()) return local_fail(ctx);
     return 0;
   }
   int rc;

@@ -124,6 +124,7 @@ struct P2PWin {                                  // one per rank, written by the
   unsigned long long xflag[kMaxRanks];           // [src] tag of the last staged halo block src wrote into my staging buffer
   unsigned long long rflag[2][kMaxRanks];        // generic scalar allreduce, double-buffered by tag parity
   double rval[2][kMaxRanks][4];
+  unsigned xticket[kMaxRanks];                   // slice tickets of the staged exchange (local use)
   int error;
   int pad;
 };
