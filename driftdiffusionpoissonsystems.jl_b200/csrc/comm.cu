@@ -180,6 +180,13 @@ int comm_init(Context* ctx, const char* id128, int rank, int nranks) {
   ctx->nranks = nranks;
   if (nranks == 1) return 0;
   if (strncmp(id128, "LOCAL:", 6) == 0) {
+    const char* ml = getenv("CUDA_MODULE_LOADING");
+    if (!ml || strcmp(ml, "EAGER") != 0) {
+      static bool warned = false;
+      if (!warned) fprintf(stderr, "[ddps] in-process communicator: set CUDA_MODULE_LOADING=EAGER before the first CUDA call -- with lazy module "
+                                   "loading the first launch of a kernel can block behind a kernel that waits for it (ranks share one context)\n");
+      warned = true;
+    }
     const std::string key(id128, strnlen(id128, 128));
     std::lock_guard<std::mutex> lk(g_groups_mu);
     std::shared_ptr<LocalGroup> g = g_groups[key].lock();
@@ -494,8 +501,12 @@ int p2p_setup(Context* ctx) {
   H.xenabled = false;
   if (ctx->nranks == 1) return 0;
   const char* env = getenv("DDPS_P2P");
-  const bool off = env && env[0] == '0';
   const bool local = (bool)ctx->lgroup;
+  // In-process group: NO peer-memory kernels.  They wait for a kernel of another stream; with the ranks sharing one device
+  // and one driver context that concurrency is not guaranteed (observed: deterministic deadlocks on some boxes, none on
+  // others), so the exchanges of that test transport all go through the host-ordered backend.  The peer-memory kernels are
+  // exercised where they are used: one process per GPU (tests/test_multigpu.py, bench.py).
+  const bool off = (env && env[0] == '0') || local;
   const int me = ctx->rank, nr = ctx->nranks;
   int rc;
   struct Xchg { cudaIpcMemHandle_t hp, hw, hs; void *pp, *pw, *ps; int off[kMaxRanks]; int device; int ok; long long cap; };
