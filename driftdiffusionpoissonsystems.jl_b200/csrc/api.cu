@@ -595,6 +595,7 @@ int ddps_ctx_create(ddps_ctx** out, int device) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
   ctx->num_sms = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   {   // setup temporaries live in the stream-ordered pool: keep freed blocks cached for the next setup
     cudaMemPool_t pool;

@@ -502,11 +502,9 @@ int p2p_setup(Context* ctx) {
   if (ctx->nranks == 1) return 0;
   const char* env = getenv("DDPS_P2P");
   const bool local = (bool)ctx->lgroup;
-  // In-process group: NO peer-memory kernels.  They wait for a kernel of another stream; with the ranks sharing one device
-  // and one driver context that concurrency is not guaranteed (observed: deterministic deadlocks on some boxes, none on
-  // others), so the exchanges of that test transport all go through the host-ordered backend.  The peer-memory kernels are
-  // exercised where they are used: one process per GPU (tests/test_multigpu.py, bench.py).
-  const bool off = (env && env[0] == '0') || local;
+  // (in-process group: the staged peer-memory kernels run too, with plain pointers instead of IPC mappings and host
+  //  barriers around their launches, see halo_xchg; DDPS_P2P=0 selects the host-ordered backend exchange for everything)
+  const bool off = env && env[0] == '0';
   const int me = ctx->rank, nr = ctx->nranks;
   int rc;
   struct Xchg { cudaIpcMemHandle_t hp, hw, hs; void *pp, *pw, *ps; int off[kMaxRanks]; int device; int ok; long long cap; };

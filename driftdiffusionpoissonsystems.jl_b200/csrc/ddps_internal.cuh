@@ -184,6 +184,7 @@ struct Context {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
   int num_sms = 148;
+  int max_smem_optin = 227 * 1024;
   std::string err;
   int err_code = 0;
   ddps_solver_opts opts;

@@ -376,7 +376,11 @@ static int launch_asm(Context* ctx, const AsmArgs& a) {
   size_t smem = (size_t)P.max_row_len * kAsmBlock * sizeof(double) + (size_t)P.max_bn * (nf * sizeof(double) + sizeof(int) + 1);
   smem = (smem + 15) & ~(size_t)15;
   auto kern = k_assemble<STIFF, MASS, RHS, RESID>;
-  if (smem > 48 * 1024) DDPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the opt-in limit is a property of the FUNCTION in the context, shared by every host thread: always raise it to the
+  // device maximum (idempotent) -- setting the exact size per launch lets another context's thread (in-process ranks with
+  // different meshes) lower it between this call and the launch
+  if (smem > 48 * 1024) DDPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+  if (smem > (size_t)ctx->max_smem_optin) { ctx->fail(DDPS_ERR_ARG, "assembly block needs more shared memory than the device offers (node of very high degree?)"); return DDPS_ERR_ARG; }
   kern<<<P.nblocks, kAsmBlock, smem, ctx->stream>>>(a);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());

@@ -1,6 +1,6 @@
 """Node-partitioned solves with the ranks running as threads on ONE GPU (in-process communicator): N-rank results against the
-single-rank result and the golden fixtures, both preconditioners.  The in-process transport orders every exchange on the host
-(no kernel waits for another rank's kernel); the peer-memory kernels and NCCL run with one process per GPU in
+single-rank result and the golden fixtures, both preconditioners, both transports of the hot exchanges (staged peer-memory
+kernels with plain pointers / host-ordered backend exchange).  CUDA IPC and NCCL run with one process per GPU in
 tests/test_multigpu.py, which repeats these checks."""
 import numpy as np
 import pytest
@@ -23,8 +23,10 @@ def _solve_ddpe(D, mesh, pr, comm=None, **opts):
     return V, u, v, st
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("nranks", [2, 3])
-def test_jacobi_path_local_ranks(D, nranks):
+def test_jacobi_path_local_ranks(D, nranks, p2p, monkeypatch):
+    monkeypatch.setenv("DDPS_P2P", p2p)
     mesh = D.structured_mesh(96, 48, 0.0, 2.0, 0.0, 1.0)
     pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0)
     ref = _solve_ddpe(D, mesh, pr)
@@ -59,11 +61,13 @@ def test_semlin_and_golden_local_ranks(D):
         assert st["outer_iters"] == len(z["control"])
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("nranks,tail,cells", [(2, 1100, (96, 48)), (3, 1100, (128, 64)), (2, 200000, (96, 48)), (4, 1100, (192, 96))])
-def test_distributed_multigrid_local_ranks(D, nranks, tail, cells, monkeypatch):
+def test_distributed_multigrid_local_ranks(D, nranks, tail, cells, p2p, monkeypatch):
     """The distributed multigrid hierarchy (rank-local aggregates, ghost prolongator / A*P rows, halo exchanges of the cycle
     vectors, replicated tail below DDPS_AMG_TAIL rows) against the single-GPU hierarchy on the same problem: fields <= 1e-10,
     the same Gummel and Newton counts, and at most 3 more CG iterations in any linear solve."""
+    monkeypatch.setenv("DDPS_P2P", p2p)
     monkeypatch.setenv("DDPS_AMG_TAIL", str(tail))
     mesh = D.structured_mesh(cells[0], cells[1], 0.0, 2.0, 0.0, 1.0)
     pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0)
