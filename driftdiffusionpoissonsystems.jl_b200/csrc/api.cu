@@ -412,7 +412,8 @@ int assemble_uv(Context* ctx, int which, int rec_mode, double tau_p, double tau_
 double energy_tol(const Context* ctx, double outer_tol) {
   if (ctx->opts.lin_etol < 0.0) return 0.0;   // A/B: residual rules only
   const double cap = ctx->opts.lin_etol > 0.0 ? ctx->opts.lin_etol : 1e-10;
-  return std::max(1e-13, std::min(cap, 0.01 * outer_tol));
+  static const double factor = getenv("DDPS_ETOL_FACTOR") ? atof(getenv("DDPS_ETOL_FACTOR")) : 0.01;   // (experiments)
+  return std::max(1e-13, std::min(cap, factor * outer_tol));
 }
 
 struct EventTimer {

@@ -17,7 +17,8 @@ module DriftDiffusionPoissonSystems
 using DelimitedFiles
 
 export Mesh, read_mesh, construct_mesh, construct_mesh4, construct_mesh8, solve_ddpe, solve_semlin_poisson,
-       aquire_boundary, SinhRHS, PolyRHS, derivative, calculate_current, aquire_boundary_separate_edges, get_gradients
+       aquire_boundary, SinhRHS, PolyRHS, derivative, calculate_current, aquire_boundary_separate_edges, get_gradients,
+       ConstFn, AffineFn, StepX, StepY, comm_unique_id, Comm
 
 const LIB = get(ENV, "DDPS_B200_LIB", joinpath(@__DIR__, "..", "..", "driftdiffusionpoissonsystems.jl_b200", "libddps_b200.so"))
 
@@ -46,20 +47,54 @@ end
 derivative(f::SinhRHS) = (x, y, u) -> f.alpha * f.beta * cosh(f.beta * u)
 derivative(f::PolyRHS) = (x, y, u) -> sum((k - 1) * c(x, y) * u^(k - 2) for (k, c) in enumerate(f.coeffs) if k > 1; init = 0.0)
 
-# ---------------------------------------------------------------- C ABI plumbing
+# ---------------------------------------------------------------- registered SPATIAL functors (include/ddps.h: ddps_spatial_kind)
+# Coefficient closures the library samples on the DEVICE (ddps_coeff_functor) -- no host sampling, no upload.  Each is also
+# an ordinary callable (x,y)->value, so user code can evaluate it like the closure it replaces; any other closure is sampled
+# on the host (broadcast) and uploaded with ddps_coeff_set.
+abstract type SpatialFn <: Function end
+struct ConstFn <: SpatialFn; c::Float64; end
+struct AffineFn <: SpatialFn; a::Float64; bx::Float64; by::Float64; end
+struct StepX <: SpatialFn; x0::Float64; left::Float64; right::Float64; end
+struct StepY <: SpatialFn; y0::Float64; below::Float64; above::Float64; end
+(f::ConstFn)(x, y) = f.c
+(f::AffineFn)(x, y) = (f.a + f.bx * x) + f.by * y
+(f::StepX)(x, y) = x > f.x0 ? f.right : f.left
+(f::StepY)(x, y) = y > f.y0 ? f.above : f.below
+spatial_kind(::ConstFn) = 1; spatial_kind(::AffineFn) = 2; spatial_kind(::StepX) = 3; spatial_kind(::StepY) = 4
+spatial_params(f::ConstFn) = [f.c]; spatial_params(f::AffineFn) = [f.a, f.bx, f.by]
+spatial_params(f::StepX) = [f.x0, f.left, f.right]; spatial_params(f::StepY) = [f.y0, f.below, f.above]
+
+# ---------------------------------------------------------------- C ABI plumbing (field order = include/ddps.h)
 struct SolverOpts
     lin_rtol::Cdouble; newton_eta::Cdouble; lin_max_it::Int64
     max_newton::Int32; max_gummel::Int32; check_every::Int32; warm_start::Int32; verbose::Int32; lin_cap_ok::Int32
     no_alt_traversal::Int32; warm_start_v::Int32; no_sym_scaling::Int32; renumber::Int32
     precond::Int32        # 0 = Jacobi-PCG (default), 1 = CG preconditioned with the smoothed-aggregation multigrid V-cycle
     amg_no_lag::Int32     # 1: recompute the multigrid coarse operators for every assembled operator (default 0: lagged)
+    newton_damping::Int32 # k > 0: opt-in backtracking, the Newton step is halved up to k times until ||M*V-b||_inf decreases
+    reserved0::Int32
+    lin_etol::Cdouble     # error-based (energy-norm) stop tolerance of the linear solves (default 1e-10; < 0: residual rules only)
 end
 
 struct Stats
     outer_iters::Int32; newton_total::Int32; pcg_total::Int64; spmv_total::Int64; kernel_launches::Int64
     control::Cdouble; t_setup_ms::Cdouble; t_solve_ms::Cdouble; t_asm_ms::Cdouble; t_pcg_ms::Cdouble; t_wall_ms::Cdouble
     status::Int32; n_negative_area::Int32
-    amg_levels::Int32; amg_reuses::Int32; t_amg_setup_ms::Cdouble; reserved::NTuple{4,Int32}
+    amg_levels::Int32; amg_reuses::Int32; t_amg_setup_ms::Cdouble; newton_halvings::Int32; reserved::NTuple{3,Int32}
+end
+
+# Multi-GPU: one Julia process per GPU.  `id` = comm_unique_id() on rank 0, broadcast by the application's own plumbing
+# (MPI.jl, Distributed, a file); pass `comm = Comm(id, rank, nranks)` to the solvers.  Every rank passes the same mesh and
+# gets the full solution back (the library partitions the nodes by coordinate bisection, include/ddps.h).
+struct Comm
+    id::Vector{UInt8}     # 128 bytes (ncclUniqueId)
+    rank::Int
+    nranks::Int
+end
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    ccall((:ddps_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("ddps: ddps_comm_unique_id failed")
+    id
 end
 
 lasterr(h) = unsafe_string(ccall((:ddps_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
@@ -68,8 +103,11 @@ chk(h, rc) = rc == 0 ? nothing : error("ddps: " * lasterr(h))
 # Preconditioner used by every solve of this module (include/ddps.h: DDPS_PRECOND_JACOBI = 0, DDPS_PRECOND_AMG = 1);
 # switch with `DriftDiffusionPoissonSystems.PRECOND[] = 1`.
 const PRECOND = Ref{Int32}(0)
+# Any other field of ddps_solver_opts, by name: `DriftDiffusionPoissonSystems.OPTS[:newton_damping] = 8`, `OPTS[:renumber] = 1`,
+# `OPTS[:warm_start_v] = 1`, `OPTS[:lin_etol] = 1e-11`, ... (defaults: ddps_default_opts)
+const OPTS = Dict{Symbol,Any}()
 
-function with_ctx(f; device = 0, verbose = true)
+function with_ctx(f; device = 0, verbose = true, comm::Union{Nothing,Comm} = nothing)
     ref = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:ddps_ctx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), ref, device)
     rc == 0 || error("ddps: " * lasterr(C_NULL))
@@ -78,10 +116,11 @@ function with_ctx(f; device = 0, verbose = true)
         o = Ref{SolverOpts}()
         ccall((:ddps_default_opts, LIB), Cvoid, (Ref{SolverOpts},), o)
         v = o[]
-        o[] = SolverOpts(v.lin_rtol, v.newton_eta, v.lin_max_it, v.max_newton, v.max_gummel, v.check_every, v.warm_start,
-                         Int32(verbose), v.lin_cap_ok, v.no_alt_traversal, v.warm_start_v, v.no_sym_scaling, v.renumber, PRECOND[],
-                         v.amg_no_lag)
+        val(name) = name == :verbose ? Int32(verbose) : name == :precond ? PRECOND[] : get(OPTS, name, getfield(v, name))
+        o[] = SolverOpts((convert(fieldtype(SolverOpts, n), val(n)) for n in fieldnames(SolverOpts))...)
         chk(h, ccall((:ddps_set_opts, LIB), Cint, (Ptr{Cvoid}, Ref{SolverOpts}), h, o))
+        # the communicator must exist before the mesh is set (the mesh is partitioned across the ranks there)
+        comm === nothing || chk(h, ccall((:ddps_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), h, comm.id, comm.rank, comm.nranks))
         return f(h)
     finally
         ccall((:ddps_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), h)
@@ -94,6 +133,11 @@ set_dirichlet(h, field, n, gD) = chk(h, ccall((:ddps_dirichlet_set, LIB), Cint, 
                                              h, field, Vector{Int64}(n), Vector{Float64}(gD), length(n)))
 set_coeff(h, slot, a) = (v = vec(Array{Float64}(a)); chk(h, ccall((:ddps_coeff_set, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Int64), h, slot, v, length(v))))
 set_functor(h, kind, p) = chk(h, ccall((:ddps_functor_set, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint), h, kind, Vector{Float64}(p), length(p)))
+# coefficient slot from a closure: registered spatial functors are sampled by the library on the device, anything else is
+# broadcast here over the sampling points (xs, ys) like the reference does (src:254,467,341-343) and uploaded
+set_coeff_fn(h, slot, fn::SpatialFn, xs, ys; square = false) =
+    (p = spatial_params(fn); chk(h, ccall((:ddps_coeff_functor, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint), h, slot, spatial_kind(fn), p, length(p))))
+set_coeff_fn(h, slot, fn, xs, ys; square = false) = set_coeff(h, slot, square ? fn.(xs, ys) .^ 2 : fn.(xs, ys))
 
 # ---------------------------------------------------------------- host-side preprocessing
 function split_bddata(bddata)
@@ -150,7 +194,7 @@ end
 # ---------------------------------------------------------------- public solvers
 function solve_ddpe(mesh::Mesh, rec_mode::Symbol, Vbddata::Array, ubddata::Array, vbddata::Array, lambda::Function,
                     delta::Float64, tau_p::Float64, tau_n::Float64, mu_p::Function, mu_n::Function, C::Function,
-                    tol = 10.0^(-9); device = 0, verbose = true)
+                    tol = 10.0^(-9); device = 0, verbose = true, comm = nothing)
     rec_mode in (:shockley, :zero) || error("rec_mode must be :shockley or :zero")
     n, gD = dirichlet_nodes(mesh, Vbddata)
     _, gDu = dirichlet_nodes(mesh, ubddata)
@@ -159,12 +203,12 @@ function solve_ddpe(mesh::Mesh, rec_mode::Symbol, Vbddata::Array, ubddata::Array
     c = centroids(mesh); mx, my = midpoints(mesh)
     nq = size(mesh.nodes, 2)
     V = zeros(nq); u = zeros(nq); v = zeros(nq)
-    with_ctx(; device = device, verbose = verbose) do h
+    with_ctx(; device = device, verbose = verbose, comm = comm) do h
         set_mesh(h, mesh)
         set_dirichlet(h, 0, n, gD); set_dirichlet(h, 1, n, gDu); set_dirichlet(h, 2, n, gDv)
-        set_coeff(h, 0, lambda.(c[1, :], c[2, :]) .^ 2)
-        set_coeff(h, 1, mu_p.(c[1, :], c[2, :])); set_coeff(h, 2, mu_n.(c[1, :], c[2, :]))
-        set_coeff(h, 3, C.(mx, my))
+        set_coeff_fn(h, 0, lambda, c[1, :], c[2, :]; square = true)      # the library squares a device-sampled lambda itself
+        set_coeff_fn(h, 1, mu_p, c[1, :], c[2, :]); set_coeff_fn(h, 2, mu_n, c[1, :], c[2, :])
+        set_coeff_fn(h, 3, C, mx, my)
         st = Ref{Stats}()
         chk(h, ccall((:ddps_solve_ddpe, LIB), Cint,
                      (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Stats}),
@@ -173,7 +217,7 @@ function solve_ddpe(mesh::Mesh, rec_mode::Symbol, Vbddata::Array, ubddata::Array
     V, u, v
 end
 
-function solve_semlin_poisson(mesh, A::Array, bddata::Array, f, g, tol = 10.0^(-14); device = 0, verbose = true)
+function solve_semlin_poisson(mesh, A::Array, bddata::Array, f, g, tol = 10.0^(-14); device = 0, verbose = true, comm = nothing)
     f isa Union{SinhRHS,PolyRHS} || error("f must be a registered functor (SinhRHS / PolyRHS): arbitrary closures cannot run on the device and there is no CPU fallback")
     n, gD = dirichlet_nodes(mesh, bddata)
     n1, n2, load = neumann_edges(mesh, bddata)
@@ -183,7 +227,7 @@ function solve_semlin_poisson(mesh, A::Array, bddata::Array, f, g, tol = 10.0^(-
     mx, my = midpoints(mesh)
     tag = float.(mesh.elements[5, :])
     V = zeros(nq)
-    with_ctx(; device = device, verbose = verbose) do h
+    with_ctx(; device = device, verbose = verbose, comm = comm) do h
         set_mesh(h, mesh)
         set_coeff(h, 4, Float64[A[1](t) for t in tag]); set_coeff(h, 5, Float64[A[4](t) for t in tag])
         set_dirichlet(h, 3, n, gD)
