@@ -43,7 +43,8 @@ void free_mesh(Context* ctx) {
   dev_free(ctx->val_base); dev_free(ctx->val_op); dev_free(ctx->lift); dev_free(ctx->val_s); dev_free(ctx->sc); dev_free(ctx->bs);
   ctx->last_val = nullptr; ctx->last_dinv = nullptr;
   dev_free(ctx->V); dev_free(ctx->U); dev_free(ctx->W); dev_free(ctx->V0); dev_free(ctx->U0); dev_free(ctx->W0);
-  dev_free(ctx->Unew); dev_free(ctx->EH); dev_free(ctx->EHi); dev_free(ctx->E3); dev_free(ctx->gw);
+  dev_free(ctx->Unew); dev_free(ctx->rec); dev_free(ctx->cinc);
+  for (int k = 0; k < kMaxPoly; ++k) dev_free(ctx->cinc_poly[k]);
   dev_free(ctx->b); dev_free(ctx->resid); dev_free(ctx->dinv); dev_free(ctx->x); dev_free(ctx->r); dev_free(ctx->q);
   dev_free(ctx->p); dev_free(ctx->partials);
   plan_free(ctx->halo);
@@ -300,10 +301,11 @@ AsmArgs base_args(Context* ctx) {
   AsmArgs a;
   memset(&a, 0, sizeof(a));
   const Pattern& P = ctx->pat;
-  a.nrows = P.nrows; a.nslices = P.nslices; a.slice_ptr = P.slice_ptr; a.col = P.col;
-  a.inc_slice_ptr = P.inc_slice_ptr; a.inc = P.inc; a.xy = ctx->xy; a.elem = ctx->elem; a.isD = ctx->isD;
-  a.diag_slot = P.diag_slot; a.bn_ptr = P.bn_ptr; a.bn_nodes = P.bn_nodes; a.lmax = P.max_bn; a.wmax = P.max_row_len;
-  a.partial_max = ctx->partials; a.scal = ctx->scal;
+  a.nrows = P.nrows; a.nslices = P.nslices; a.wmax = P.max_row_len; a.snmax = P.max_sn;
+  static const int pf_env = getenv("DDPS_ASM_PF") ? atoi(getenv("DDPS_ASM_PF")) : -1;   // (experiments) prefetch distance in slices
+  a.pf_dist = pf_env > 0 ? pf_env : (1 << 30);   // default: off (measured: no gain once the records come by bulk copies)
+  a.sdesc = P.sdesc; a.sn_nodes = P.sn_nodes; a.inc_tri = P.inc_tri; a.inc_pack = P.inc_pack; a.arinc = P.arinc;
+  a.runs = P.runs; a.rowinfo = P.rowinfo; a.isD = ctx->isD; a.xy = ctx->xy; a.rec = ctx->rec;
   return a;
 }
 
@@ -329,7 +331,22 @@ int assemble_base(Context* ctx, bool semlin) {
   a.gD = ctx->gD[field];
   a.out_val = ctx->val_base;
   a.lift_out = ctx->lift;
+  if ((rc = launch_prep_base(ctx))) return rc;
   if ((rc = launch_assemble_base(ctx, a))) return rc;
+  // once per solve: the midpoint samples of the Newton systems' load in incidence order (what k_asm_newton streams)
+  auto permute = [&](int slot, double** out) -> int {
+    if (!ctx->coeff[slot]) return 0;
+    if (!*out) { int r = dev_alloc(ctx, out, (size_t)ctx->pat.inc_entries); if (r) return r; }
+    return launch_permute_mid(ctx, ctx->coeff[slot], *out);
+  };
+  if (!semlin) {
+    if ((rc = permute(DDPS_COEFF_C_MID, &ctx->cinc))) return rc;
+  } else if (ctx->functor_kind == DDPS_FUNCTOR_SINH) {
+    if ((rc = permute(DDPS_COEFF_H_MID, &ctx->cinc))) return rc;
+  } else if (ctx->functor_kind == DDPS_FUNCTOR_POLY) {
+    for (int k = 0; k < kMaxPoly; ++k)
+      if ((rc = permute(DDPS_COEFF_POLY_MID0 + k, &ctx->cinc_poly[k]))) return rc;
+  }
   ctx->base_ready = true;
   ctx->base_is_semlin = semlin;
   return 0;
@@ -351,23 +368,23 @@ int maybe_amg_setup(Context* ctx) {
 int assemble_newton(Context* ctx, bool semlin, double delta, const double* Vit, const double* u, const double* v) {
   int rc;
   AsmArgs a = base_args(ctx);
-  a.base_val = ctx->val_base; a.lift_in = ctx->lift; a.gw = ctx->gw; a.xvec = Vit;
+  a.base_val = ctx->val_base; a.lift_in = ctx->lift;
   a.out_val = ctx->val_op; a.dinv = ctx->dinv; a.b = ctx->b; a.resid = ctx->resid;
   if (!semlin) {
     if ((rc = need_coeff(ctx, DDPS_COEFF_C_MID, "C_MID"))) return rc;
+    if (!ctx->cinc) { ctx->fail(DDPS_ERR_STATE, "C_MID was set after the base assembly of this solve"); return DDPS_ERR_STATE; }
     if ((rc = launch_prep_poisson(ctx, Vit, u, v, delta * delta))) return rc;
     a.gD = ctx->gD[DDPS_FIELD_V];
-    a.fu = u; a.fv = v; a.EH = ctx->EH; a.EHi = ctx->EHi; a.mid = ctx->coeff[DDPS_COEFF_C_MID];
+    a.cinc = ctx->cinc;
     a.par0 = delta * delta;
     return launch_assemble_newton(ctx, a, RHS_DDP);
   }
   if ((rc = launch_prep_semlin(ctx, Vit))) return rc;
   a.gD = ctx->gD[DDPS_FIELD_SCALAR];
-  a.EH = Vit;
   a.nodal_const = ctx->coeff[DDPS_COEFF_NEUMANN];
   if (ctx->functor_kind == DDPS_FUNCTOR_SINH) {
     if ((rc = need_coeff(ctx, DDPS_COEFF_H_MID, "H_MID"))) return rc;
-    a.mid = ctx->coeff[DDPS_COEFF_H_MID];
+    a.cinc = ctx->cinc;
     a.par0 = ctx->functor_par[0]; a.par1 = ctx->functor_par[1];
     return launch_assemble_newton(ctx, a, RHS_SINH);
   } else if (ctx->functor_kind == DDPS_FUNCTOR_POLY) {
@@ -375,7 +392,7 @@ int assemble_newton(Context* ctx, bool semlin, double delta, const double* Vit, 
     for (int k = 0; k <= deg; ++k) {
       if ((rc = need_coeff(ctx, DDPS_COEFF_POLY_MID0 + k, "POLY_MID")) || (rc = need_coeff(ctx, DDPS_COEFF_POLY_NODE0 + k, "POLY_NODE")))
         return rc;
-      a.mid_poly[k] = ctx->coeff[DDPS_COEFF_POLY_MID0 + k];
+      a.cinc_poly[k] = ctx->cinc_poly[k];
     }
     a.par0 = (double)deg;
     return launch_assemble_newton(ctx, a, RHS_POLY);
@@ -393,12 +410,10 @@ int assemble_uv(Context* ctx, int which, int rec_mode, double tau_p, double tau_
   int mu_slot = isU ? DDPS_COEFF_MU_P : DDPS_COEFF_MU_N;
   if ((rc = need_coeff(ctx, mu_slot, isU ? "MU_P" : "MU_N"))) return rc;
   if (!ctx->have_D[which]) { ctx->fail(DDPS_ERR_STATE, "Dirichlet data for u/v not set"); return DDPS_ERR_STATE; }
-  if ((rc = launch_prep_uv(ctx, isU ? 1.0 : -1.0, V, nullptr, u0, v0, tau_p, tau_n, rec_mode))) return rc;
+  if ((rc = launch_prep_uv(ctx, isU ? 1.0 : -1.0, V, u0, v0, tau_p, tau_n, rec_mode))) return rc;
   AsmArgs a = base_args(ctx);
   a.gD = ctx->gD[which];
-  a.phx = ctx->coeff[mu_slot]; a.E3 = ctx->E3; a.gw = ctx->gw;
-  a.fu = isU ? u0 : v0; a.fv = isU ? v0 : u0;   // callee's (u0, v0)
-  a.EH = ctx->EH; a.EHi = ctx->EHi;
+  a.phx = ctx->coeff[mu_slot];
   a.par0 = isU ? tau_p : tau_n; a.par1 = isU ? tau_n : tau_p;   // callee's (tau_p, tau_n)
   a.out_val = ctx->val_op; a.dinv = ctx->dinv; a.b = ctx->b;
   if (rec_mode == DDPS_REC_SHOCKLEY) return launch_assemble_uv(ctx, a, RHS_SRH, true);
@@ -698,8 +713,9 @@ static int finish_mesh(ddps_ctx* ctx, double t0) {
     if ((rc = dev_alloc(ctx, &ctx->gD[f], nl))) return rc;
     DDPS_CUDA(cudaMemsetAsync(ctx->gD[f], 0, nl * sizeof(double), ctx->stream));
   }
-  double** nodal[] = {&ctx->V, &ctx->U, &ctx->W, &ctx->V0, &ctx->U0, &ctx->W0, &ctx->Unew, &ctx->EH, &ctx->EHi, &ctx->E3,
-                      &ctx->gw, &ctx->p};
+  if ((rc = dev_alloc(ctx, &ctx->rec, nl * kRecD))) return rc;
+  DDPS_CUDA(cudaMemsetAsync(ctx->rec, 0, nl * kRecD * sizeof(double), ctx->stream));
+  double** nodal[] = {&ctx->V, &ctx->U, &ctx->W, &ctx->V0, &ctx->U0, &ctx->W0, &ctx->Unew, &ctx->p};
   for (double** pp : nodal) {
     if ((rc = dev_alloc(ctx, pp, nl))) return rc;
     DDPS_CUDA(cudaMemsetAsync(*pp, 0, nl * sizeof(double), ctx->stream));
@@ -1534,6 +1550,8 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
       case 7: return amg_numeric(ctx, ctx->val_op, ctx->dinv, -1);
       case 8: return amg_vcycle(ctx, ctx->r, ctx->q, false);
       case 9: case 10: case 11: case 12: case 13: return amg_time_launch(ctx, kernel, it, nullptr);
+      case 14: return launch_prep_poisson(ctx, ctx->V, ctx->U0, ctx->W0, ctx->delta * ctx->delta);   // the nodal passes alone
+      case 15: return launch_prep_uv(ctx, 1.0, ctx->V, ctx->U0, ctx->W0, ctx->tau_p, ctx->tau_n, ctx->rec_mode);
     }
     ctx->fail(DDPS_ERR_ARG, "unknown kernel id");
     return DDPS_ERR_ARG;
@@ -1547,6 +1565,7 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
     case 3: bytes = 12.0 * nme + 16.0 * nq + 3 * 8.0 * nq + 24.0 * nme + 12.0 * nnz + 8.0 * nnz + 16.0 * nq; break;  // 134 B/triangle
     case 4: bytes = 12.0 * nme + 16.0 * nq + 8.0 * nme + 8.0 * nnz + 8.0 * nq; break;
     case 5: bytes = 12.0 * nnz + 4.0 * (nq + 1) + 16.0 * nq; break;
+    case 14: case 15: bytes = (3 * 8.0 + 8.0 * kRecD) * (double)ctx->n_loc; break;
   }
   if (kernel >= 6 && kernel <= 13) {
     if (!amg_ready(ctx)) { ctx->fail(DDPS_ERR_STATE, "no multigrid hierarchy (opts.precond = DDPS_PRECOND_AMG and a base assembly first)"); return DDPS_ERR_STATE; }

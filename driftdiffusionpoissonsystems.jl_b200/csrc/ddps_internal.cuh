@@ -9,12 +9,12 @@
 //    column-major inside the slice, so lane l of a warp reads entry k of row 32*s+l at
 //    slice_ptr[s] + 32*k + l  -> perfectly coalesced value/column streams for both the row-major
 //    assembly (writes) and the SpMV (reads).  Padding entries carry value 0 and column = own row.
-//  * row -> incident triangle lists ("incidence"), also slice-interleaved; each 8-byte record packs
-//    the triangle id, the row's local corner (0..2), the pre-computed slots of that triangle's
-//    off-diagonal row entries and the positions of its two other corners in the row block's
-//    node list, so the scatter needs no search and no atomics.
-//  * per block of 128 rows: the sorted list of distinct nodes its rows touch, staged once per
-//    block in shared memory by the assembly kernel.
+//  * row -> incident triangle lists ("incidence"), also slice-interleaved, as three parallel streams: the
+//    triangle id + the row's local corner (0..2); the pre-computed slots of that triangle's off-diagonal
+//    row entries + the positions of its two other corners in the SLICE's node list (4 bytes); the signed
+//    area in the row's own frame.  The scatter needs no search and no atomics.
+//  * per slice of 32 rows: the sorted list of distinct nodes its rows touch, staged once per slice in
+//    shared memory by the warp that assembles the slice (cp.async gathers of 48-byte nodal records).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -36,8 +36,7 @@
 namespace ddps {
 
 constexpr int kSlice = 32;        // rows per slice = warp size
-constexpr int kAsmBlock = 128;    // threads per block of the row-major assembly kernels
-constexpr int kAsmRows = 128;     // rows per assembly block (= kAsmBlock: one thread per row)
+constexpr int kAsmBlock = 128;    // threads per block of the assembly kernels: 4 independent warps, one slice each
 constexpr int kMaxRowLen = 40;    // shared-memory accumulator columns available per row
 constexpr int kVecBlock = 256;    // threads per block of SpMV / vector kernels
 constexpr int kMaxPoly = 5;       // polynomial functor: degree 0..4
@@ -63,15 +62,20 @@ struct Pattern {
   int* col = nullptr;        // [nentries] slice-interleaved
   int* rowptr = nullptr;     // [nrows+1] plain CSR (export + slot search)
   int* csrcol = nullptr;     // [nnz]
-  // incidence lists
+  // incidence streams (setup.cu: k_fill_incidence)
   int64_t inc_entries = 0;
   int* inc_slice_ptr = nullptr;  // [nslices+1]
-  int2* inc = nullptr;           // [inc_entries] {tri*4+corner | -1, slot_next | slot_prev<<5 | l_next<<10 | l_prev<<21}
-  unsigned char* diag_slot = nullptr;  // [nrows] slot of the diagonal entry
-  // row blocks of kAsmRows rows: sorted distinct nodes the block touches (staged in shared memory by k_assemble)
-  int nblocks = 0, max_bn = 0, bn_total = 0;
-  int* bn_ptr = nullptr;         // [nblocks+1]
-  int* bn_nodes = nullptr;       // [bn_total]
+  int* inc_tri = nullptr;        // [inc_entries] tri*4+corner | -1
+  unsigned* inc_pack = nullptr;  // [inc_entries] slot_next | slot_prev<<5 | l_next<<10 | l_prev<<20 | again<<30,31 | 0xffffffff
+  double* arinc = nullptr;       // [inc_entries] signed area in the row's own frame
+  unsigned short* rowinfo = nullptr;   // [nrows] slot of the diagonal entry | row length << 5
+  // per slice: sorted distinct nodes the slice's rows touch + the packed descriptor the assembling warp starts from
+  int max_sn = 0, sn_total = 0;
+  int* sn_ptr = nullptr;         // [nslices+1]
+  int* sn_nodes = nullptr;       // [sn_total]
+  int64_t nruns = 0;
+  int2* runs = nullptr;          // runs of consecutive node ids of every slice list: {first node, position | length<<16}
+  int4* sdesc = nullptr;         // [nslices][3] {base, ibase, nbase, w | iw<<6 | nn<<12 | l_first<<22}, {run base, #runs, run0}, {run1, run2}
 };
 
 // device-side scalar block of one PCG solve (all control flow stays on the device)
@@ -239,7 +243,9 @@ struct Context {
   double *V = nullptr, *U = nullptr, *W = nullptr;          // fields
   double *V0 = nullptr, *U0 = nullptr, *W0 = nullptr;       // previous Gummel iterate
   double *Unew = nullptr;                                   // scratch field
-  double *EH = nullptr, *EHi = nullptr, *E3 = nullptr, *gw = nullptr;
+  double* rec = nullptr;                                    // [n_loc][kRecD] nodal records of the running assembly (prep kernels)
+  double* cinc = nullptr;                                   // [inc_entries] C_MID / H_MID in incidence order
+  double* cinc_poly[kMaxPoly] = {nullptr};
   // solver vectors
   double *b = nullptr, *resid = nullptr, *dinv = nullptr;   // [n_own]
   double *x = nullptr, *r = nullptr, *q = nullptr;          // [n_own]
@@ -274,44 +280,35 @@ void free_pattern(Context* ctx);
 void partition_nodes_rcb(const double* nodes, int64_t nq, int nparts, int32_t* owner);
 
 // ---- kernels.cu ----
+constexpr int kRecD = 6;          // doubles per nodal record: {gw, s1 | u, v | eh, ehi}
 struct AsmArgs {
-  int nrows, nslices, wmax;
-  const int* slice_ptr;
-  const int* col;
-  const int* inc_slice_ptr;
-  const int2* inc;
-  const unsigned char* diag_slot;
-  const int* bn_ptr;
-  const int* bn_nodes;
-  int lmax;
-  const double2* xy;
-  const int4* elem;
+  int nrows, nslices, wmax, snmax;
+  int pf_dist;            // L2 prefetch distance in slices (about one wave of resident warps)
+  const int4* sdesc;
+  const int* sn_nodes;
+  const int* inc_tri;
+  const unsigned* inc_pack;
+  const double* arinc;
+  const int2* runs;
+  const unsigned short* rowinfo;
   const unsigned char* isD;
+  const double2* xy;
+  const double* rec;      // [n_loc][kRecD] nodal records written by the prep kernels
   const double* gD;
   const double* phx;      // per-element coefficient (x pairing) or mu
   const double* phy;      // per-element coefficient (y pairing)
-  const double* E3;       // nodal exp(+-V/3)
-  const double* base_val; // base matrix values (STIFF==0)
-  const double* gw;       // nodal mass weight g_k
-  // rhs inputs
-  const double* fu;       // nodal u (or u0)
-  const double* fv;       // nodal v (or v0)
-  const double* EH;       // nodal exp(+V/2)   (semlin: the iterate itself)
-  const double* EHi;      // nodal exp(-V/2)
-  const double* mid;      // [nme*3] midpoint samples (C or H)
-  const double* mid_poly[kMaxPoly];
+  const double* base_val; // base matrix values (Newton systems)
+  const double* cinc;     // midpoint samples (C or H) in incidence order
+  const double* cinc_poly[kMaxPoly];
   const double* nodal_const;  // neumann loads (may be null)
-  const double* lift_in;      // precomputed lifting of the base stiffness (STIFF==0)
-  double par0, par1, par2;    // delta^2 | tau_p,tau_n | alpha,beta | degree
-  const double* xvec;         // iterate for the residual
+  const double* lift_in;      // precomputed lifting of the base stiffness (Newton systems)
+  double par0, par1;          // delta^2 | tau_p,tau_n | alpha,beta | degree
   // outputs
   double* out_val;
   double* dinv;
   double* b;
   double* lift_out;
   double* resid;
-  double* partial_max;
-  PcgScalars* scal;
 };
 
 enum { STIFF_BASE = 0, STIFF_COEF = 1, STIFF_EXPV = 2 };
@@ -321,10 +318,13 @@ int launch_assemble_base(Context* ctx, const AsmArgs& a);
 int launch_assemble_uv(Context* ctx, const AsmArgs& a, int rhs_kind, bool mass);
 int launch_assemble_newton(Context* ctx, const AsmArgs& a, int rhs_kind);
 
+int launch_prep_base(Context* ctx);
 int launch_prep_poisson(Context* ctx, const double* V, const double* u, const double* v, double delta2);
-int launch_prep_uv(Context* ctx, double sign, const double* V, const double* other, const double* u0, const double* v0,
-                   double tau_p, double tau_n, int rec_mode);
+int launch_prep_uv(Context* ctx, double sign, const double* V, const double* u0, const double* v0, double tau_p,
+                   double tau_n, int rec_mode);
 int launch_prep_semlin(Context* ctx, const double* V);
+// element-midpoint samples [3*nme] -> incidence order [inc_entries] (what the Newton-system kernels stream)
+int launch_permute_mid(Context* ctx, const double* mid, double* out);
 
 int launch_spmv(Context* ctx, const double* val, const double* x, double* y);
 int launch_spmv_dot(Context* ctx, const double* val, const double* x, double* y);  // the PCG variant (fused p.Ap)

@@ -1,18 +1,9 @@
 // Hand-written sm_100a FP64 kernels of the hot path (compiled with -fmad=false so the element
 // formulas round exactly like the reference's IEEE expressions).
 //
-//   k_assemble<STIFF,MASS,RHS,RESID>  row-major fused assembly (K1-K7 of SURVEY section 2.1):
-//       one thread per matrix row walks the row's incident triangles in increasing triangle order
-//       (= the duplicate-summation order of the reference's sparse()), recomputes the triangle
-//       geometry from coalesced 16-byte loads, and accumulates its row of every local 3x3 matrix
-//       into private shared-memory slots that were resolved at setup time: no atomics, no staging
-//       buffer, bitwise reproducible run to run.  Dirichlet elimination (src:271-284), boundary
-//       lifting (src:362), the lumped edge-midpoint load vector (src:345-350) and -- for the
-//       Newton systems -- the residual M*V-b (src:368) are fused into the same pass.
+//   (the fused assembly kernels and the nodal prep kernels live in assemble.cu)
 //   k_spmv_dot                        SELL-32 SpMV fused with the p.Ap partial dot (K8/K9)
 //   k_pcg_update / k_pcg_direction    fused vector updates + dots of Jacobi-PCG (K9)
-//   nodal prep kernels                exp(+-V/2), exp(+-V/3) and the nodal mass weights g_k, so
-//                                     the element loops contain no transcendental at all.
 #include <cuda_pipeline.h>
 
 #include "ddps_internal.cuh"
@@ -112,386 +103,6 @@ __global__ void __launch_bounds__(1024) k_halo_push(const PushArgs A, const int*
   if (threadIdx.x == 0) *(volatile unsigned long long*)A.flag[j] = A.tag;
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// Row-major fused assembly with block-cooperative staging.
-//
-// One CTA per block of 128 consecutive rows, one thread per row.
-//   level 1 (coalesced):  the block's sorted node list (built at setup) and each row's packed 8-byte
-//                         incidence records;
-//   level 2 (gathers):    the nodal fields of every DISTINCT node the block touches are gathered ONCE
-//                         into shared memory (a 128-row block of a P1 mesh touches ~3x128 nodes but its
-//                         rows reference them ~13x128 times), plus the per-triangle coefficients;
-//   compute:              each thread walks its row's incident triangles in increasing triangle order,
-//                         reads the two other corners from shared memory through the block-local
-//                         indices packed in the record, and accumulates its row of every local 3x3
-//                         matrix into its PRIVATE shared-memory column (slots resolved at setup).
-// No atomics, no staging buffer in HBM, bitwise reproducible, same summation order as the reference's
-// sparse() (increasing triangle id per entry).  Dirichlet elimination (src:271-284), lifting
-// (src:362), the lumped edge-midpoint load (src:345-350) and, for the Newton systems, the residual
-// M*V-b (src:368) are fused into the same pass; all transcendentals live in the nodal prep kernels.
-// ------------------------------------------------------------------------------------------------
-constexpr int kMaxIncReg = 8;   // incidence records held in registers; longer rows take the tail loop
-#ifndef DDPS_ASM_MINBLOCKS
-#define DDPS_ASM_MINBLOCKS 1
-#endif
-
-template <int STIFF, bool MASS, int RHS, bool RESID>
-__global__ void __launch_bounds__(kAsmBlock, DDPS_ASM_MINBLOCKS) k_assemble(const AsmArgs P) {
-  extern __shared__ double sm[];
-  constexpr bool NEED_UV = (RHS == RHS_DDP || RHS == RHS_SRH);
-  constexpr bool NEED_EH = NEED_UV || RHS == RHS_SINH || RHS == RHS_POLY;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int lmax = P.lmax;
-  // shared memory: acc[wmax][128] | X | Y | E3 | GW | FU | FV | EH | EHI  (each [lmax]) | node ids | isD
-  double* acc = sm;
-  double* sX = acc + (size_t)P.wmax * kAsmBlock;
-  double* sY = sX + lmax;
-  double* sE3 = sY + lmax;
-  double* sGW = sE3 + (STIFF == STIFF_EXPV ? lmax : 0);
-  double* sFU = sGW + (MASS ? lmax : 0);
-  double* sFV = sFU + (NEED_UV ? lmax : 0);
-  double* sEH = sFV + (NEED_UV ? lmax : 0);
-  double* sEHI = sEH + (NEED_EH ? lmax : 0);
-  int* sNode = reinterpret_cast<int*>(sEHI + (NEED_UV ? lmax : 0));
-  unsigned char* sD = reinterpret_cast<unsigned char*>(sNode + lmax);
-
-  const int blk = blockIdx.x;
-  const int row = blk * kAsmRows + tid;
-  const bool live = row < P.nrows;
-  const int rr = live ? row : 0;
-  const int slice = row >> 5;
-  const bool in_pat = slice < P.nslices;
-  int base = 0, w = 0, ibase = 0, iw = 0;
-  if (in_pat) {
-    base = P.slice_ptr[slice]; w = (P.slice_ptr[slice + 1] - base) >> 5;
-    ibase = P.inc_slice_ptr[slice]; iw = (P.inc_slice_ptr[slice + 1] - ibase) >> 5;
-  }
-  // ---- level 1: incidence records (coalesced) ----
-  int2 rec[kMaxIncReg];
-#pragma unroll
-  for (int k = 0; k < kMaxIncReg; ++k) {
-    rec[k] = make_int2(-1, 0);
-    if (k < iw && live) rec[k] = P.inc[ibase + k * 32 + lane];
-  }
-  // ---- stage the block's distinct nodes (level 1: ids, level 2: fields) ----
-  const int nb0 = P.bn_ptr[blk], nn = P.bn_ptr[blk + 1] - nb0;
-  for (int i0 = tid; i0 < nn; i0 += 4 * kAsmBlock) {   // 4 list entries per thread per pass: ids first, then all gathers
-    int g[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const int i = i0 + j * kAsmBlock; g[j] = (i < nn) ? P.bn_nodes[nb0 + i] : -1; }
-    double2 q[4];
-    double f_e3[4], f_gw[4], f_u[4], f_v[4], f_eh[4], f_ehi[4];
-    unsigned char f_d[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (g[j] < 0) continue;
-      q[j] = P.xy[g[j]];
-      if (STIFF == STIFF_EXPV) f_e3[j] = P.E3[g[j]];
-      if (STIFF != STIFF_BASE) f_d[j] = P.isD[g[j]];
-      if (MASS) f_gw[j] = P.gw[g[j]];
-      if (NEED_UV) { f_u[j] = P.fu[g[j]]; f_v[j] = P.fv[g[j]]; f_ehi[j] = P.EHi[g[j]]; }
-      if (NEED_EH) f_eh[j] = P.EH[g[j]];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (g[j] < 0) continue;
-      const int i = i0 + j * kAsmBlock;
-      sX[i] = q[j].x; sY[i] = q[j].y;
-      sNode[i] = g[j];
-      if (STIFF == STIFF_EXPV) sE3[i] = f_e3[j];
-      if (STIFF != STIFF_BASE) sD[i] = f_d[j];
-      if (MASS) sGW[i] = f_gw[j];
-      if (NEED_UV) { sFU[i] = f_u[j]; sFV[i] = f_v[j]; sEHI[i] = f_ehi[j]; }
-      if (NEED_EH) sEH[i] = f_eh[j];
-    }
-  }
-  // ---- own-node data (coalesced) and per-triangle coefficients (level 2) ----
-  const double2 q_own = P.xy[rr];
-  const bool rowD = live && P.isD[rr] != 0;
-  double own_g = 0.0, own_e3 = 0.0, own_u = 0.0, own_v = 0.0, own_eh = 0.0, own_ehi = 0.0;
-  if (MASS) own_g = P.gw[rr];
-  if (STIFF == STIFF_EXPV) own_e3 = P.E3[rr];
-  if (NEED_UV) { own_u = P.fu[rr]; own_v = P.fv[rr]; own_ehi = P.EHi[rr]; }
-  if (NEED_EH) own_eh = P.EH[rr];
-  double cphx[kMaxIncReg], cphy[kMaxIncReg], cmid[kMaxIncReg];
-#pragma unroll
-  for (int k = 0; k < kMaxIncReg; ++k) {
-    cphx[k] = 0.0; cphy[k] = 0.0; cmid[k] = 0.0;
-    if (rec[k].x >= 0) {
-      const int e = rec[k].x >> 2, a = rec[k].x & 3;
-      if (STIFF != STIFF_BASE) cphx[k] = P.phx[e];
-      if (STIFF == STIFF_COEF) cphy[k] = P.phy[e];
-      if (RHS == RHS_DDP || RHS == RHS_SINH) cmid[k] = P.mid[3 * e + a];
-    }
-  }
-  for (int k = 0; k < w; ++k) acc[k * kAsmBlock + tid] = 0.0;
-  const int sdiag = live ? P.diag_slot[row] : 0;
-  // Newton systems: base*x for the residual -- all values + columns of the row first, then all x gathers
-  double mv = 0.0;
-  if (STIFF == STIFF_BASE && RESID && in_pat) {
-    for (int k0 = 0; k0 < w; k0 += 8) {
-      double m[8];
-      int c[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        m[j] = 0.0; c[j] = rr;
-        if (k0 + j < w) { m[j] = ld_stream(P.base_val + base + (k0 + j) * 32 + lane); c[j] = ld_stream(P.col + base + (k0 + j) * 32 + lane); }
-      }
-      double xv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] = (k0 + j < w) ? P.xvec[c[j]] : 0.0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (k0 + j < w) mv += m[j] * xv[j];
-    }
-  }
-  __syncthreads();
-
-  double bsum = 0.0, lift = 0.0;
-  auto one = [&](const int2 r, const double phx_in, const double phy_in, const double mid_in) {
-    const int e = r.x >> 2, a = r.x & 3;
-    const unsigned y = (unsigned)r.y;
-    const int s_next = y & 31, s_prev = (y >> 5) & 31, lb = (y >> 10) & 2047, lc = y >> 21;
-    // Own frame of the row: A = this row's corner, B = next, C = previous corner (cyclic).  Edge vectors opposite
-    // each corner (src:243-245 up to the cyclic relabelling) and the signed area (src:246); every product is
-    // written so that entry (i,j) computed for row i and entry (j,i) computed for row j use the same operands
-    // in a commutative order (no 3-way selects on the corner index).
-    const double bx = sX[lb], by = sY[lb], cx = sX[lc], cy = sY[lc];
-    const double eax = bx - cx, eay = by - cy;            // e_A = q_B - q_C
-    const double ebx = cx - q_own.x, eby = cy - q_own.y;  // e_B = q_C - q_A
-    const double ecx = q_own.x - bx, ecy = q_own.y - by;  // e_C = q_A - q_B
-    const double ar = (eax * eby - eay * ebx) * 0.5;
-    double c_self = 0.0, c_next = 0.0, c_prev = 0.0;
-    if (STIFF != STIFF_BASE) {
-      double phx = phx_in, phy = phy_in;
-      if (STIFF == STIFF_EXPV) { phx = phx_in * (own_e3 * sE3[lb] * sE3[lc]); phy = phx; }   // src:469
-      const double inv4 = 1.0 / fabs(ar * 4.0);  // src:257 (one division per triangle; <= 1 ulp vs x/ar4)
-      // K(i,j) = (e_i.x*phx*e_j.x + e_i.y*phy*e_j.y)/|4ar| (src:260-266)
-      const double k_self = (phx * (eax * eax) + phy * (eay * eay)) * inv4;
-      const double k_next = (phx * (eax * ebx) + phy * (eay * eby)) * inv4;
-      const double k_prev = (phx * (eax * ecx) + phy * (eay * ecy)) * inv4;
-      const bool bD = sD[lb] != 0, cD = sD[lc] != 0;
-      // Dirichlet elimination src:271-278: rows and columns of D are zeroed (kept in the pattern)
-      c_self = rowD ? 0.0 : k_self;
-      c_next = (rowD || bD) ? 0.0 : k_next;
-      c_prev = (rowD || cD) ? 0.0 : k_prev;
-      // boundary lifting b -= K[:,D]*gD on rows outside D, src:362 (rare: rows next to a contact)
-      if (!rowD) {
-        if (bD) lift += k_next * P.gD[sNode[lb]];
-        if (cD) lift += k_prev * P.gD[sNode[lc]];
-      }
-    }
-    if (MASS) {
-      // weighted mass with nodal weights W_k = g_k*ar/30, SIGNED ar (src:375-386, Q2); J0 is never eliminated (Q3).
-      // diag = 3Wa+Wb+Wc, (a,b) = Wa+Wb+Wc/2: the pair sum first, so that (a,b) and (b,a) round identically
-      const double ar30 = ar * (1.0 / 30.0);
-      const double Wa = own_g * ar30, Wb = sGW[lb] * ar30, Wc = sGW[lc] * ar30;
-      c_self -= 3.0 * Wa + (Wb + Wc);
-      c_next -= (Wa + Wb) + Wc * 0.5;
-      c_prev -= (Wa + Wc) + Wb * 0.5;
-    }
-    if (STIFF != STIFF_BASE || MASS) {
-      acc[sdiag * kAsmBlock + tid] += c_self;
-      acc[s_next * kAsmBlock + tid] += c_next;
-      acc[s_prev * kAsmBlock + tid] += c_prev;
-    }
-    // lumped edge-midpoint load: corner a takes the midpoint between a and next (src:345-350, Q1)
-    if (RHS != RHS_NONE && RHS != RHS_ZERO) {
-      double f;
-      if (RHS == RHS_DDP) {   // src:341-343
-        const double ua = (own_u + sFU[lb]) * 0.5, va = (own_v + sFV[lb]) * 0.5;
-        const double eS = own_eh * sEH[lb], eSi = own_ehi * sEHI[lb];
-        f = P.par0 * (eSi * va - eS * ua) + mid_in;
-      } else if (RHS == RHS_SRH) {  // src:517-519
-        const double ua = (own_u + sFU[lb]) * 0.5, va = (own_v + sFV[lb]) * 0.5;
-        const double eS = own_eh * sEH[lb], eSi = own_ehi * sEHI[lb];
-        f = 1.0 / (P.par0 * (eS * ua + 1.0) + P.par1 * (eSi * va + 1.0));
-      } else if (RHS == RHS_SINH) {  // registered functor, test:95
-        const double S = (own_eh + sEH[lb]) * 0.5;
-        f = mid_in + P.par0 * sinh(P.par1 * S);
-      } else {  // RHS_POLY, README:107-108
-        const double S = (own_eh + sEH[lb]) * 0.5;
-        const int deg = (int)P.par0;
-        f = P.mid_poly[deg][3 * e + a];
-        for (int dd = deg - 1; dd >= 0; --dd) f = f * S + P.mid_poly[dd][3 * e + a];
-      }
-      bsum += f * (fabs(ar) * (1.0 / 3.0));  // src:349
-    }
-  };
-#pragma unroll
-  for (int k = 0; k < kMaxIncReg; ++k)
-    if (rec[k].x >= 0) one(rec[k], cphx[k], cphy[k], cmid[k]);
-  for (int k = kMaxIncReg; k < iw; ++k) {   // rows with more than kMaxIncReg triangles (rare)
-    if (!live) break;
-    const int2 r = P.inc[ibase + k * 32 + lane];
-    if (r.x < 0) continue;
-    const int e = r.x >> 2, a = r.x & 3;
-    one(r, STIFF != STIFF_BASE ? P.phx[e] : 0.0, STIFF == STIFF_COEF ? P.phy[e] : 0.0,
-        (RHS == RHS_DDP || RHS == RHS_SINH) ? P.mid[3 * e + a] : 0.0);
-  }
-
-  // ---- write the rows (coalesced per slice) ----
-  if (!in_pat) return;
-  if (STIFF != STIFF_BASE && rowD) acc[sdiag * kAsmBlock + tid] += 1.0;  // src:279-281
-  double diag = 0.0;
-  for (int k0 = 0; k0 < w; k0 += 8) {
-    double m[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {   // base values again (L2-resident from the pass above), all loads in flight together
-      m[j] = 0.0;
-      if (STIFF == STIFF_BASE && k0 + j < w) m[j] = P.base_val[base + (k0 + j) * 32 + lane];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = k0 + j;
-      if (k < w) {
-        const double a_k = acc[k * kAsmBlock + tid] + m[j];
-        if (k == sdiag) diag = a_k;
-        P.out_val[base + k * 32 + lane] = live ? a_k : 0.0;
-      }
-    }
-  }
-  if (live) {
-    if (P.dinv) P.dinv[row] = 1.0 / diag;
-    if (STIFF != STIFF_BASE && P.lift_out) P.lift_out[row] = lift;
-    if (RHS != RHS_NONE) {
-      if (STIFF == STIFF_BASE) lift = P.lift_in[row];
-      double bi = bsum;
-      if (P.nodal_const) bi += P.nodal_const[row];   // Neumann loads, src:994-996
-      bi -= lift;                                    // src:362
-      if (rowD) bi = P.gD[row];                      // src:363
-      P.b[row] = bi;
-      if (RESID) P.resid[row] = mv - bi;             // src:368
-    }
-  }
-}
-
-template <int STIFF, bool MASS, int RHS, bool RESID>
-static int launch_asm(Context* ctx, const AsmArgs& a) {
-  const Pattern& P = ctx->pat;
-  if (P.nblocks == 0) return 0;
-  constexpr bool NEED_UV = (RHS == RHS_DDP || RHS == RHS_SRH);
-  constexpr bool NEED_EH = NEED_UV || RHS == RHS_SINH || RHS == RHS_POLY;
-  const int nf = 2 + (STIFF == STIFF_EXPV ? 1 : 0) + (MASS ? 1 : 0) + (NEED_UV ? 3 : 0) + (NEED_EH ? 1 : 0);
-  size_t smem = (size_t)P.max_row_len * kAsmBlock * sizeof(double) + (size_t)P.max_bn * (nf * sizeof(double) + sizeof(int) + 1);
-  smem = (smem + 15) & ~(size_t)15;
-  auto kern = k_assemble<STIFF, MASS, RHS, RESID>;
-  // the opt-in limit is a property of the FUNCTION in the context, shared by every host thread: always raise it to the
-  // device maximum (idempotent) -- setting the exact size per launch lets another context's thread (in-process ranks with
-  // different meshes) lower it between this call and the launch
-  if (smem > 48 * 1024) DDPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-  if (smem > (size_t)ctx->max_smem_optin) { ctx->fail(DDPS_ERR_ARG, "assembly block needs more shared memory than the device offers (node of very high degree?)"); return DDPS_ERR_ARG; }
-  kern<<<P.nblocks, kAsmBlock, smem, ctx->stream>>>(a);
-  ctx->stats.kernel_launches++;
-  DDPS_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int launch_assemble_base(Context* ctx, const AsmArgs& a) { return launch_asm<STIFF_COEF, false, RHS_NONE, false>(ctx, a); }
-
-int launch_assemble_uv(Context* ctx, const AsmArgs& a, int rhs_kind, bool mass) {
-  if (rhs_kind == RHS_SRH && mass) return launch_asm<STIFF_EXPV, true, RHS_SRH, false>(ctx, a);
-  if (rhs_kind == RHS_ZERO && !mass) return launch_asm<STIFF_EXPV, false, RHS_ZERO, false>(ctx, a);
-  ctx->fail(DDPS_ERR_ARG, "unsupported uv assembly mode");
-  return DDPS_ERR_ARG;
-}
-
-int launch_assemble_newton(Context* ctx, const AsmArgs& a, int rhs_kind) {
-  switch (rhs_kind) {
-    case RHS_DDP: return launch_asm<STIFF_BASE, true, RHS_DDP, true>(ctx, a);
-    case RHS_SINH: return launch_asm<STIFF_BASE, true, RHS_SINH, true>(ctx, a);
-    case RHS_POLY: return launch_asm<STIFF_BASE, true, RHS_POLY, true>(ctx, a);
-  }
-  ctx->fail(DDPS_ERR_ARG, "unsupported Newton rhs functor");
-  return DDPS_ERR_ARG;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Nodal prep kernels (all transcendental work of an assembly, one pass over the nodes)
-// ------------------------------------------------------------------------------------------------
-__global__ void k_prep_poisson(int n, const double* __restrict__ V, const double* __restrict__ u,
-                               const double* __restrict__ v, double delta2, double* __restrict__ EH,
-                               double* __restrict__ EHi, double* __restrict__ gw) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double Vi = V[i];
-  EH[i] = exp(Vi / 2.0);
-  EHi[i] = exp(-Vi / 2.0);
-  gw[i] = -delta2 * (u[i] * exp(Vi) + v[i] * exp(-Vi));  // src:375-377
-}
-
-// sign = +1: u-solve with (V, tau_p, tau_n, u0, v0); sign = -1: v-solve, the reference passes
-// (-V, tau_n, tau_p, v0, u0) (src:598-599).  V here is always the true potential.
-__global__ void k_prep_uv(int n, double sign, const double* __restrict__ V, const double* __restrict__ u0,
-                          const double* __restrict__ v0, double tau_p, double tau_n, int shockley,
-                          double* __restrict__ EH, double* __restrict__ EHi, double* __restrict__ E3,
-                          double* __restrict__ gw) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double Vs = sign * V[i];   // the "V" the reference's uvsolve sees
-  EH[i] = exp(Vs / 2.0);
-  EHi[i] = exp(-Vs / 2.0);
-  E3[i] = exp(Vs / 3.0);           // exp((V1+V2+V3)/3) = product of the three nodal factors, src:469
-  if (shockley) {
-    // src:568: g_k = -v0_k / (tau_p(e^{V}u0+1) + tau_n(e^{-V}v0+1)) in the callee's own naming
-    const double a = (sign > 0) ? u0[i] : v0[i];   // callee's u0
-    const double b = (sign > 0) ? v0[i] : u0[i];   // callee's v0
-    const double tp = (sign > 0) ? tau_p : tau_n, tn = (sign > 0) ? tau_n : tau_p;
-    gw[i] = -b / (tp * (exp(Vs) * a + 1.0) + tn * (exp(-Vs) * b + 1.0));
-  } else {
-    gw[i] = 0.0;
-  }
-}
-
-struct PolyNodal { const double* c[kMaxPoly]; };
-
-__global__ void k_prep_semlin(int n, const double* __restrict__ V, int kind, double p0, double p1, PolyNodal pn,
-                              double* __restrict__ gw) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double u = V[i];
-  double g;
-  if (kind == DDPS_FUNCTOR_SINH) {
-    g = p0 * p1 * cosh(p1 * u);   // g = df/du, test:96
-  } else {
-    const int deg = (int)p0;
-    g = 0.0;
-    for (int d = deg; d >= 1; --d) g = g * u + d * pn.c[d][i];
-  }
-  gw[i] = g;   // src:1046-1048
-}
-
-int launch_prep_poisson(Context* ctx, const double* V, const double* u, const double* v, double delta2) {
-  int n = ctx->n_loc;
-  if (!n) return 0;
-  k_prep_poisson<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, V, u, v, delta2, ctx->EH, ctx->EHi, ctx->gw);
-  ctx->stats.kernel_launches++;
-  DDPS_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int launch_prep_uv(Context* ctx, double sign, const double* V, const double* /*unused*/, const double* u0,
-                   const double* v0, double tau_p, double tau_n, int rec_mode) {
-  int n = ctx->n_loc;
-  if (!n) return 0;
-  k_prep_uv<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, sign, V, u0, v0, tau_p, tau_n, rec_mode == DDPS_REC_SHOCKLEY,
-                                                    ctx->EH, ctx->EHi, ctx->E3, ctx->gw);
-  ctx->stats.kernel_launches++;
-  DDPS_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int launch_prep_semlin(Context* ctx, const double* V) {
-  int n = ctx->n_loc;
-  if (!n) return 0;
-  PolyNodal pn;
-  for (int k = 0; k < kMaxPoly; ++k) pn.c[k] = ctx->coeff[DDPS_COEFF_POLY_NODE0 + k];
-  k_prep_semlin<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, V, ctx->functor_kind, ctx->functor_par[0],
-                                                        ctx->functor_par[1], pn, ctx->gw);
-  ctx->stats.kernel_launches++;
-  DDPS_CUDA(cudaGetLastError());
-  return 0;
-}
 
 // ------------------------------------------------------------------------------------------------
 // SpMV (SELL-32) with fused dot, persistent grid-stride over slices

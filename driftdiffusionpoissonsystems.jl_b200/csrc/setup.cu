@@ -100,13 +100,13 @@ __device__ __forceinline__ int find_slot(const int* __restrict__ cols, int len, 
   return lo;
 }
 
-// keys (row block << 32 | column) of every stored entry: sorted + uniqued they give, per block of
-// kAsmRows consecutive rows, the sorted list of distinct nodes the block's rows touch
+// keys (slice << 32 | column) of every stored entry: sorted + uniqued they give, per slice of 32
+// consecutive rows (= the warp that assembles them), the sorted list of distinct nodes its rows touch
 __global__ void k_make_block_keys(const int* __restrict__ rowptr, const int* __restrict__ csrcol, int nrows,
                                   unsigned long long* __restrict__ keys) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows) return;
-  const unsigned long long hi = (unsigned long long)(row / kAsmRows) << 32;
+  const unsigned long long hi = (unsigned long long)(row / kSlice) << 32;
   for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) keys[k] = hi | (unsigned)csrcol[k];
 }
 
@@ -115,41 +115,99 @@ __global__ void k_block_maxlen(const int* __restrict__ bn_ptr, int nblk, int* __
   if (b < nblk) atomicMax(out_max, bn_ptr[b + 1] - bn_ptr[b]);
 }
 
-// Incidence record (8 bytes): x = triangle*4 + corner (or -1), y = slot_next | slot_prev<<5 | l_next<<10 | l_prev<<21
-// where l_* are the positions of the two other corners in the row block's node list.
+// Incidence streams, slice-interleaved like the matrix (entry k of row r at inc_slice_ptr[r/32] + 32k + r%32):
+//   inc_tri  = triangle*4 + corner (or -1 for padding)
+//   inc_pack = slot_next | slot_prev<<5 | l_next<<10 | l_prev<<20 | again_next<<30 | again_prev<<31 (0xffffffff for
+//              padding), slot_* = positions of the triangle's two off-diagonal entries in the row, l_* = positions of the
+//              two other corners in the SLICE's node list (what the assembling warp stages in shared memory), again_* =
+//              an earlier triangle of this row already contributed to that slot (so the first contribution is a plain
+//              store and only the second one -- an edge has at most two triangles -- reads the accumulator back)
+//   arinc    = signed area of the triangle in the row's own frame (A = the row's corner, B = next, C = previous corner,
+//              src:243-246 up to the cyclic relabelling): the Newton-system kernels need nothing else of the geometry
 __global__ void k_fill_incidence(const int* __restrict__ inc_ptr, const int* __restrict__ inc_vals,
-                                 const int4* __restrict__ elem, const int* __restrict__ rowptr,
-                                 const int* __restrict__ csrcol, int nrows, int nslices,
-                                 const int* __restrict__ inc_slice_ptr, const int* __restrict__ bn_ptr,
-                                 const int* __restrict__ bn_nodes, int2* __restrict__ inc,
-                                 unsigned char* __restrict__ diag_slot) {
+                                 const int4* __restrict__ elem, const double2* __restrict__ xy,
+                                 const int* __restrict__ rowptr, const int* __restrict__ csrcol, int nrows, int nslices,
+                                 const int* __restrict__ inc_slice_ptr, const int* __restrict__ sn_ptr,
+                                 const int* __restrict__ sn_nodes, int* __restrict__ inc_tri,
+                                 unsigned* __restrict__ inc_pack, double* __restrict__ arinc,
+                                 unsigned short* __restrict__ rowinfo) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   int slice = row >> 5, lane = row & 31;
   if (slice >= nslices) return;
   int base = inc_slice_ptr[slice];
   int w = (inc_slice_ptr[slice + 1] - base) >> 5;
-  int beg = 0, len = 0, rbeg = 0, rlen = 0, lb = 0, ll = 0;
+  int beg = 0, len = 0, rbeg = 0, rlen = 0;
+  const int lb = sn_ptr[slice], ll = sn_ptr[slice + 1] - lb;
   if (row < nrows) {
     beg = inc_ptr[row]; len = inc_ptr[row + 1] - beg;
     rbeg = rowptr[row]; rlen = rowptr[row + 1] - rbeg;
-    const int blk = row / kAsmRows;
-    lb = bn_ptr[blk]; ll = bn_ptr[blk + 1] - lb;
-    diag_slot[row] = (unsigned char)find_slot(csrcol + rbeg, rlen, row);
+    rowinfo[row] = (unsigned short)(find_slot(csrcol + rbeg, rlen, row) | (rlen << 5));   // diagonal slot | row length
   }
+  unsigned seen = 0;
   for (int k = 0; k < w; ++k) {
-    int2 rec = make_int2(-1, 0);
+    int tri = -1;
+    unsigned pack = 0xffffffffu;
+    double ar = 0.0;
     if (k < len) {
-      int packed = inc_vals[beg + k];
-      int e = packed >> 2, a = packed & 3;
+      tri = inc_vals[beg + k];
+      int e = tri >> 2, a = tri & 3;
       int4 el = elem[e];
       int nb = (a == 0) ? el.y : (a == 1) ? el.z : el.x;   // next corner
       int nc = (a == 0) ? el.z : (a == 1) ? el.x : el.y;   // previous corner
       unsigned sb = find_slot(csrcol + rbeg, rlen, nb), sc = find_slot(csrcol + rbeg, rlen, nc);
-      unsigned l1 = find_slot(bn_nodes + lb, ll, nb), l2 = find_slot(bn_nodes + lb, ll, nc);
-      rec = make_int2(packed, (int)(sb | (sc << 5) | (l1 << 10) | (l2 << 21)));
+      unsigned l1 = find_slot(sn_nodes + lb, ll, nb), l2 = find_slot(sn_nodes + lb, ll, nc);
+      pack = sb | (sc << 5) | (l1 << 10) | (l2 << 20) | (((seen >> sb) & 1u) << 30) | (((seen >> sc) & 1u) << 31);
+      seen |= (1u << sb) | (1u << sc);
+      const double2 qa = xy[row], qb = xy[nb], qc = xy[nc];
+      const double eax = qb.x - qc.x, eay = qb.y - qc.y;   // e_A = q_B - q_C
+      const double ebx = qc.x - qa.x, eby = qc.y - qa.y;   // e_B = q_C - q_A
+      ar = (eax * eby - eay * ebx) * 0.5;
     }
-    inc[base + k * 32 + lane] = rec;
+    inc_tri[base + k * 32 + lane] = tri;
+    inc_pack[base + k * 32 + lane] = pack;
+    arinc[base + k * 32 + lane] = ar;
   }
+}
+
+// Runs of consecutive node ids in every slice's node list: the assembling warp copies a run with ONE bulk copy (its
+// records are contiguous in memory).  Pass 1 (runs == nullptr) counts, pass 2 writes {first node, position in the list |
+// length << 16} at run_ptr[slice].
+__global__ void k_slice_runs(int nslices, const int* __restrict__ sn_ptr, const int* __restrict__ sn_nodes,
+                             const int* __restrict__ run_ptr, int* __restrict__ counts, int2* __restrict__ runs) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslices) return;
+  const int b = sn_ptr[s], e = sn_ptr[s + 1];
+  int n = 0, start = b;
+  int2* out = runs ? runs + run_ptr[s] : nullptr;
+  for (int i = b + 1; i <= e; ++i) {
+    if (i == e || sn_nodes[i] != sn_nodes[i - 1] + 1) {
+      if (out) out[n] = make_int2(sn_nodes[start], (start - b) | ((i - start) << 16));
+      ++n;
+      start = i;
+    }
+  }
+  if (counts) counts[s] = n;
+}
+
+// per-slice descriptor, 48 bytes = three 16-byte loads, everything the assembling warp needs to start its copies:
+//   {matrix base, incidence base, node-list base, w | iw<<6 | nn<<12 | l_first<<22}   (l_first = position of the slice's
+//   first row in its node list; the slice's own rows are consecutive there because the list is sorted)
+//   {run base, number of runs, run 0}, {run 1, run 2}   (the first three runs inline: a regular numbering has exactly three)
+__global__ void k_fill_sdesc(int nslices, const int* __restrict__ slice_ptr, const int* __restrict__ inc_slice_ptr,
+                             const int* __restrict__ sn_ptr, const int* __restrict__ sn_nodes,
+                             const int* __restrict__ run_ptr, const int2* __restrict__ runs, int4* __restrict__ sdesc) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslices) return;
+  const int base = slice_ptr[s], ibase = inc_slice_ptr[s], nbase = sn_ptr[s];
+  const unsigned w = (unsigned)(slice_ptr[s + 1] - base) >> 5, iw = (unsigned)(inc_slice_ptr[s + 1] - ibase) >> 5;
+  const unsigned nn = (unsigned)(sn_ptr[s + 1] - nbase);
+  const unsigned lf = (unsigned)find_slot(sn_nodes + nbase, (int)nn, s * kSlice);
+  const int rb = run_ptr[s], nr = run_ptr[s + 1] - rb;
+  int2 r[3] = {make_int2(0, 0), make_int2(0, 0), make_int2(0, 0)};
+  for (int j = 0; j < 3 && j < nr; ++j) r[j] = runs[rb + j];
+  sdesc[3 * (size_t)s + 0] = make_int4(base, ibase, nbase, (int)(w | (iw << 6) | (nn << 12) | (lf << 22)));
+  sdesc[3 * (size_t)s + 1] = make_int4(rb, nr, r[0].x, r[0].y);
+  sdesc[3 * (size_t)s + 2] = make_int4(r[1].x, r[1].y, r[2].x, r[2].y);
 }
 
 __global__ void k_min_deg(const int* __restrict__ ptr, int nrows, int* __restrict__ out_min) {
@@ -179,7 +237,8 @@ inline int bits_for(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) +
 void free_pattern(Context* ctx) {
   Pattern& P = ctx->pat;
   cudaFree(P.slice_ptr); cudaFree(P.col); cudaFree(P.rowptr); cudaFree(P.csrcol);
-  cudaFree(P.inc_slice_ptr); cudaFree(P.inc); cudaFree(P.bn_ptr); cudaFree(P.bn_nodes); cudaFree(P.diag_slot);
+  cudaFree(P.inc_slice_ptr); cudaFree(P.inc_tri); cudaFree(P.inc_pack); cudaFree(P.arinc); cudaFree(P.sdesc);
+  cudaFree(P.sn_ptr); cudaFree(P.sn_nodes); cudaFree(P.runs); cudaFree(P.rowinfo);
   P = Pattern();
 }
 
@@ -291,15 +350,13 @@ int build_pattern(Context* ctx) {
       return DDPS_ERR_ARG;
     }
   }
-  // ---- 5. per row block (kAsmRows rows): sorted list of the distinct nodes its rows touch ----------
-  const int nblk = (n_own + kAsmRows - 1) / kAsmRows;
-  P.nblocks = nblk;
+  // ---- 5. per slice (32 rows = one assembling warp): sorted list of the distinct nodes its rows touch ----------
   {
     unsigned long long *bk_in, *bk_out;
     DDPS_CUDA(tmp.alloc(&bk_in, (size_t)nnz)); DDPS_CUDA(tmp.alloc(&bk_out, (size_t)nnz));
     k_make_block_keys<<<(n_own + T - 1) / T, T, 0, st>>>(P.rowptr, P.csrcol, n_own, bk_in);
     size_t bytes = 0;
-    const int endbit = 32 + bits_for((uint64_t)nblk + 1);
+    const int endbit = 32 + bits_for((uint64_t)nsl + 1);
     cub::DeviceRadixSort::SortKeys(nullptr, bytes, bk_in, bk_out, nnz, 0, endbit, st);
     void* ws; DDPS_CUDA(tmp.alloc((char**)&ws, bytes));
     DDPS_CUDA(cub::DeviceRadixSort::SortKeys(ws, bytes, bk_in, bk_out, nnz, 0, endbit, st));
@@ -310,25 +367,48 @@ int build_pattern(Context* ctx) {
     int nlist = 0;
     DDPS_CUDA(cudaMemcpyAsync(&nlist, d_num, sizeof(int), cudaMemcpyDeviceToHost, st));
     DDPS_CUDA(cudaStreamSynchronize(st));
-    DDPS_CUDA(cudaMalloc(&P.bn_ptr, ((size_t)nblk + 1) * sizeof(int)));
-    DDPS_CUDA(cudaMalloc(&P.bn_nodes, std::max<size_t>(nlist, 1) * sizeof(int)));
-    k_lower_bound<unsigned long long><<<(nblk + 1 + T - 1) / T, T, 0, st>>>(bk_in, nlist, nblk + 1, 32, P.bn_ptr);
-    k_low32<<<(unsigned)((nlist + T - 1) / T), T, 0, st>>>(bk_in, nlist, P.bn_nodes);
+    DDPS_CUDA(cudaMalloc(&P.sn_ptr, ((size_t)nsl + 1) * sizeof(int)));
+    DDPS_CUDA(cudaMalloc(&P.sn_nodes, std::max<size_t>(nlist, 1) * sizeof(int)));
+    k_lower_bound<unsigned long long><<<(nsl + 1 + T - 1) / T, T, 0, st>>>(bk_in, nlist, nsl + 1, 32, P.sn_ptr);
+    k_low32<<<(unsigned)((nlist + T - 1) / T), T, 0, st>>>(bk_in, nlist, P.sn_nodes);
     DDPS_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
-    k_block_maxlen<<<(nblk + T - 1) / T, T, 0, st>>>(P.bn_ptr, nblk, d_max);
-    DDPS_CUDA(cudaMemcpyAsync(&P.max_bn, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    k_block_maxlen<<<(nsl + T - 1) / T, T, 0, st>>>(P.sn_ptr, nsl, d_max);
+    DDPS_CUDA(cudaMemcpyAsync(&P.max_sn, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
     DDPS_CUDA(cudaStreamSynchronize(st));
-    P.bn_total = nlist;
-    if (P.max_bn > 2047 || P.max_row_len > 32) {
+    P.sn_total = nlist;
+    if (P.max_sn > 1023 || P.max_row_len > 32 || P.max_inc > 63) {
       ctx->fail(DDPS_ERR_ARG, "mesh connectivity too dense for the packed incidence records (a node with > 31 neighbours "
-                              "or a 128-row block touching > 2047 nodes)");
+                              "or > 63 triangles, or a 32-row slice touching > 1023 nodes)");
       return DDPS_ERR_ARG;
     }
   }
-  DDPS_CUDA(cudaMalloc(&P.inc, std::max<size_t>(P.inc_entries, 1) * sizeof(int2)));
-  DDPS_CUDA(cudaMalloc(&P.diag_slot, std::max<size_t>(n_own, 1)));
-  k_fill_incidence<<<(nsl * 32 + T - 1) / T, T, 0, st>>>(inc_ptr, iv_out, ctx->elem, P.rowptr, P.csrcol, n_own, nsl,
-                                                        P.inc_slice_ptr, P.bn_ptr, P.bn_nodes, P.inc, P.diag_slot);
+  DDPS_CUDA(cudaMalloc(&P.inc_tri, std::max<size_t>(P.inc_entries, 1) * sizeof(int)));
+  DDPS_CUDA(cudaMalloc(&P.inc_pack, std::max<size_t>(P.inc_entries, 1) * sizeof(unsigned)));
+  DDPS_CUDA(cudaMalloc(&P.arinc, std::max<size_t>(P.inc_entries, 1) * sizeof(double)));
+  DDPS_CUDA(cudaMalloc(&P.sdesc, std::max<size_t>(nsl, 1) * 3 * sizeof(int4)));
+  DDPS_CUDA(cudaMalloc(&P.rowinfo, std::max<size_t>(n_own, 1) * sizeof(unsigned short)));
+  k_fill_incidence<<<(nsl * 32 + T - 1) / T, T, 0, st>>>(inc_ptr, iv_out, ctx->elem, ctx->xy, P.rowptr, P.csrcol, n_own, nsl,
+                                                        P.inc_slice_ptr, P.sn_ptr, P.sn_nodes, P.inc_tri, P.inc_pack,
+                                                        P.arinc, P.rowinfo);
+  // runs of consecutive nodes in the slice lists (count, scan, write), then the descriptors
+  {
+    int *cnt, *run_ptr;
+    DDPS_CUDA(tmp.alloc(&cnt, (size_t)nsl + 1)); DDPS_CUDA(tmp.alloc(&run_ptr, (size_t)nsl + 1));
+    DDPS_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)nsl + 1) * sizeof(int), st));
+    k_slice_runs<<<(nsl + T - 1) / T, T, 0, st>>>(nsl, P.sn_ptr, P.sn_nodes, nullptr, cnt, nullptr);
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, run_ptr, nsl + 1, st);
+    void* ws; DDPS_CUDA(tmp.alloc((char**)&ws, bytes));
+    DDPS_CUDA(cub::DeviceScan::ExclusiveSum(ws, bytes, cnt, run_ptr, nsl + 1, st));
+    int nruns = 0;
+    DDPS_CUDA(cudaMemcpyAsync(&nruns, run_ptr + nsl, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DDPS_CUDA(cudaStreamSynchronize(st));
+    P.nruns = nruns;
+    DDPS_CUDA(cudaMalloc(&P.runs, std::max<size_t>(nruns, 1) * sizeof(int2)));
+    k_slice_runs<<<(nsl + T - 1) / T, T, 0, st>>>(nsl, P.sn_ptr, P.sn_nodes, run_ptr, nullptr, P.runs);
+    k_fill_sdesc<<<(nsl + T - 1) / T, T, 0, st>>>(nsl, P.slice_ptr, P.inc_slice_ptr, P.sn_ptr, P.sn_nodes, run_ptr, P.runs,
+                                                 P.sdesc);
+  }
   DDPS_CUDA(cudaStreamSynchronize(st));
   DDPS_CUDA(cudaGetLastError());
   return 0;
