@@ -303,6 +303,8 @@ AsmArgs base_args(Context* ctx) {
   const Pattern& P = ctx->pat;
   a.nrows = P.nrows; a.nslices = P.nslices; a.wmax = P.max_row_len; a.snmax = P.max_sn;
   static const int pf_env = getenv("DDPS_ASM_PF") ? atoi(getenv("DDPS_ASM_PF")) : -1;   // (experiments) prefetch distance in slices
+  static const int pfd_env = getenv("DDPS_ASM_PFD") ? atoi(getenv("DDPS_ASM_PFD")) : -1;
+  a.pf_desc = pfd_env >= 0 ? (pfd_env ? pfd_env : (1 << 30)) : ctx->num_sms * 24;
   a.pf_dist = pf_env > 0 ? pf_env : (1 << 30);   // default: off (measured: no gain once the records come by bulk copies)
   a.sdesc = P.sdesc; a.sn_nodes = P.sn_nodes; a.inc_tri = P.inc_tri; a.inc_pack = P.inc_pack; a.arinc = P.arinc;
   a.runs = P.runs; a.rowinfo = P.rowinfo; a.isD = ctx->isD; a.xy = ctx->xy; a.rec = ctx->rec;

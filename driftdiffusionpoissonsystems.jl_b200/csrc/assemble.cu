@@ -36,6 +36,11 @@ namespace ddps {
 namespace {
 
 constexpr int kWarps = kAsmBlock / 32;
+#define DDPS_PRAGMA_(x) _Pragma(#x)
+#define DDPS_PRAGMA(x) DDPS_PRAGMA_(x)
+#ifndef DDPS_STIFF_UNROLL
+#define DDPS_STIFF_UNROLL 1
+#endif
 #ifndef DDPS_STIFF_MINB
 #define DDPS_STIFF_MINB 6   // resident CTAs per SM the stiffness kernels are compiled for (register cap 80)
 #endif
@@ -133,6 +138,11 @@ __global__ void __launch_bounds__(kAsmBlock) k_asm_newton(const AsmArgs P) {
   __syncwarp();
   stage_runs<false>(P, d1, d2, D.nn, lane, smem_u32(nodes), 0u, bar, (unsigned)D.w * 256);
   if (lane == 31) bulk_g2s(smem_u32(bv - lane), P.base_val + D.base, (unsigned)D.w * 256, bar);   // the slice's block of the base matrix
+  // the slice's own streams towards L2 in one request each: the loop below then reads them with L2 latency
+  if (lane == 30) prefetch_l2(P.arinc + D.ibase, (unsigned)D.iw * 256);
+  if (lane == 29 && (RHS == RHS_DDP || RHS == RHS_SINH)) prefetch_l2(P.cinc + D.ibase, (unsigned)D.iw * 256);
+  if (lane == 28) prefetch_l2(P.inc_pack + D.ibase, (unsigned)D.iw * 128);
+  if (lane == 27 && slice + P.pf_desc < P.nslices) prefetch_l2(P.sdesc + 3 * (size_t)(slice + P.pf_desc), 48);
 
   const int row = slice * 32 + lane;
   const bool live = row < P.nrows;
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(kAsmBlock, DDPS_STIFF_MINB) k_asm_stiff(const 
       bsum += f * (fabs(ar) * (1.0 / 3.0));  // src:349
     }
   };
-#pragma unroll 3
+  DDPS_PRAGMA(unroll DDPS_STIFF_UNROLL)
   for (int k = 0; k < D.iw; ++k) {
     const Inc q = q0;
     const Coef c = c0;

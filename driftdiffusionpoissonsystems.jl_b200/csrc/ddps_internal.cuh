@@ -284,6 +284,7 @@ constexpr int kRecD = 6;          // doubles per nodal record: {gw, s1 | u, v | 
 struct AsmArgs {
   int nrows, nslices, wmax, snmax;
   int pf_dist;            // L2 prefetch distance in slices (about one wave of resident warps)
+  int pf_desc;            // descriptor prefetch distance in slices
   const int4* sdesc;
   const int* sn_nodes;
   const int* inc_tri;
