@@ -399,8 +399,8 @@ def main():
                     "traffic": traffic.get(tkey) if tkey else None}
 
         kern = {"spmv_dot": entry(5, "k_spmv<true,false> (SELL-32 SpMV + fused p.Ap, fp64 values)", its_step, tkey="k_spmv_dot"),
-                "assembly_uv": entry(1, "k_prep_uv + k_assemble<EXPV,MASS,SRH> (continuity system, 72 B/triangle)", 2, tkey="k_assemble_uv"),
-                "assembly_newton": entry(3, "k_prep_poisson + k_assemble<BASE,MASS,DDP,RESID> (Newton system, 134 B/triangle)", solves_step - 2 + 1,
+                "assembly_uv": entry(1, "k_prep_uv + k_asm_stiff<EXPV,MASS,SRH> (continuity system, 72 B/triangle)", 2, tkey="k_assemble_uv"),
+                "assembly_newton": entry(3, "k_prep_poisson + k_asm_newton<DDP> (Newton system: A = MV - J0, b, F = MV*V - b; 134 B/triangle)", solves_step - 2 + 1,
                                          tkey="k_assemble_newton")}
         if precond == "amg":
             kern.update({

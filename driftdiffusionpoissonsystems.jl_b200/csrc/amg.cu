@@ -540,6 +540,162 @@ __global__ void __launch_bounds__(1024) k_amg_dense_apply(int n, const double* _
   }
 }
 
+constexpr int kAmgSmallLevel = 32768;   // rows; below this the warp-per-row kernels run (and the fused tail of the cycle starts)
+
+// ------------------------------------------------------------------------------------------------------------
+// The bottom of the V-cycle in ONE launch.  Below kAmgSmallLevel rows every cycle kernel is a dependent chain of a few
+// memory round trips on a handful of CTAs: 5-11 us per launch, 17 launches for four levels (latency, not work).  This
+// kernel walks those levels down and up itself on one CTA per SM (co-resident: cooperative launch), phases separated by a
+// grid barrier (one atomic per CTA on a counter the last CTA to leave resets): residual / restriction + first sweep per level
+// on the way down, the dense coarsest solve, prolongation / smoothing sweep on the way up.  Vectors written inside the kernel
+// are read back through L2 (ld.global.cg): another CTA produced them since this SM's L1 saw the line.  Same arithmetic as the
+// per-level kernels; levels between kAmgTailWpr and kAmgSmallLevel rows sum their rows lane-per-row (sequential walk) instead
+// of warp-per-row (shuffle tree) -- a fixed order either way, so the cycle stays a fixed linear operator, reproducible run to
+// run (DDPS_AMG_NO_TAIL=1 keeps the per-level launches).
+// ------------------------------------------------------------------------------------------------------------
+struct TailLevel {
+  int n, nc, nslices, wpr;   // wpr: warp-per-row kernels (n <= kAmgTailWpr), else lane-per-row
+  const int *slice_ptr, *col, *rowptr;
+  const double *val, *dinv;
+  const int *Pptr, *Rptr;
+  const int2 *Pent, *Rent;
+  double *b, *x, *x2, *t;
+};
+constexpr int kAmgTailMax = 8;
+constexpr int kAmgTailWpr = 4096;
+struct TailArgs {
+  int nl;                       // levels in the tail; the last one is the coarsest (dense)
+  TailLevel lv[kAmgTailMax];
+  const double* dense;
+  double om;
+  unsigned* bar;                // {phase counter, exit counter}
+  const PcgScalars* scal;
+};
+
+__device__ __forceinline__ void tail_sync(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*(volatile unsigned*)bar < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// y = b - A x (MODE 1) or y = x + om dinv (b - A x) (MODE 2) on one tail level
+template <int MODE>
+__device__ __forceinline__ void tail_spmv(const TailLevel& L, double om, const double* x, double* y, int gw, int nw, int lane) {
+  if (L.wpr) {
+    for (int row = gw; row < L.n; row += nw) {
+      const int len = __ldg(L.rowptr + row + 1) - __ldg(L.rowptr + row);
+      const int base = __ldg(L.slice_ptr + (row >> 5)) + (row & 31);
+      double sum = 0.0;
+      for (int k = lane; k < len; k += 32) sum += __ldg(L.val + base + 32 * k) * __ldcg(x + __ldg(L.col + base + 32 * k));
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        double out;
+        if (MODE == 1) out = __ldcg(L.b + row) - sum;
+        else out = __ldcg(x + row) + om * (__ldg(L.dinv + row) * (__ldcg(L.b + row) - sum));
+        y[row] = out;
+      }
+    }
+  } else {
+    for (int slice = gw; slice < L.nslices; slice += nw) {
+      const int base = __ldg(L.slice_ptr + slice);
+      const int w = (__ldg(L.slice_ptr + slice + 1) - base) >> 5;
+      int idx = base + lane;
+      double sum = 0.0;
+      int k = 0;
+      for (; k + 4 <= w; k += 4) {
+        const int c0 = __ldg(L.col + idx), c1 = __ldg(L.col + idx + 32), c2 = __ldg(L.col + idx + 64), c3 = __ldg(L.col + idx + 96);
+        const double v0 = __ldg(L.val + idx), v1 = __ldg(L.val + idx + 32), v2 = __ldg(L.val + idx + 64), v3 = __ldg(L.val + idx + 96);
+        const double x0 = __ldcg(x + c0), x1 = __ldcg(x + c1), x2 = __ldcg(x + c2), x3 = __ldcg(x + c3);
+        sum += v0 * x0; sum += v1 * x1; sum += v2 * x2; sum += v3 * x3;
+        idx += 128;
+      }
+      for (; k < w; ++k) {
+        sum += __ldg(L.val + idx) * __ldcg(x + __ldg(L.col + idx));
+        idx += 32;
+      }
+      const int row = slice * 32 + lane;
+      if (row < L.n) {
+        double out;
+        if (MODE == 1) out = __ldcg(L.b + row) - sum;
+        else out = __ldcg(x + row) + om * (__ldg(L.dinv + row) * (__ldcg(L.b + row) - sum));
+        y[row] = out;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_amg_tail(const __grid_constant__ TailArgs A) {
+  if (A.scal->done) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  unsigned phase = 0;
+  const unsigned G = gridDim.x;
+  // ---- down: residual, restriction (+ first damped-Jacobi sweep of the coarse level from the zero guess) ----
+  for (int l = 0; l + 1 < A.nl; ++l) {
+    const TailLevel& L = A.lv[l];
+    const TailLevel& C = A.lv[l + 1];
+    tail_spmv<1>(L, A.om, L.x, L.t, gw, nw, lane);
+    tail_sync(A.bar, ++phase * G);
+    const bool sweep = (l + 2 < A.nl);
+    {   // warp per coarse row (as k_amg_restrict_wpr)
+      for (int I = gw; I < L.nc; I += nw) {
+        const int q0 = __ldg(L.Rptr + I), q1 = __ldg(L.Rptr + I + 1);
+        double s = 0.0;
+        for (int q = q0 + lane; q < q1; q += 32) {
+          const int2 en = __ldg(L.Rent + q);
+          s += (double)__int_as_float(en.y) * __ldcg(L.t + en.x);
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+          C.b[I] = s;
+          if (sweep) C.x[I] = A.om * (__ldg(C.dinv + I) * s);
+        }
+      }
+    }
+    tail_sync(A.bar, ++phase * G);
+  }
+  // ---- coarsest level: x2 = Ainv b, one warp per row ----
+  {
+    const TailLevel& L = A.lv[A.nl - 1];
+    for (int i = gw; i < L.n; i += nw) {
+      double s = 0.0;
+      for (int j = lane; j < L.n; j += 32) s += __ldg(A.dense + (size_t)i * L.n + j) * __ldcg(L.b + j);
+      s = warp_sum(s);
+      if (lane == 0) L.x2[i] = s;
+    }
+    tail_sync(A.bar, ++phase * G);
+  }
+  // ---- up: prolongation, smoothing sweep ----
+  for (int l = A.nl - 2; l >= 0; --l) {
+    const TailLevel& L = A.lv[l];
+    const TailLevel& C = A.lv[l + 1];
+    for (int i = gt; i < L.n; i += nt) {
+      double s = 0.0;
+      const int e = __ldg(L.Pptr + i + 1);
+#pragma unroll 1
+      for (int m = __ldg(L.Pptr + i); m < e; ++m) {
+        const int2 en = __ldg(L.Pent + m);
+        if (en.x >= 0) s += (double)__int_as_float(en.y) * __ldcg(C.x2 + en.x);
+      }
+      L.x[i] = __ldcg(L.x + i) + s;
+    }
+    tail_sync(A.bar, ++phase * G);
+    tail_spmv<2>(L, A.om, L.x, L.x2, gw, nw, lane);
+    if (l > 0) tail_sync(A.bar, ++phase * G);
+  }
+  // ---- the last CTA to leave resets the counters for the next launch ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(A.bar + 1, 1u) == G - 1) { A.bar[0] = 0u; A.bar[1] = 0u; __threadfence(); }
+  }
+}
+
 // ---- CG with a general preconditioner: control kernels -------------------------------------------------------
 // r = rhs - q (q = A x0) or r = rhs; sums {r.r, rhs.rhs, x0.rhs}, max|r|
 template <bool HAVE_Q>
@@ -685,6 +841,7 @@ void amg_free(Context* ctx) {
   }
   amg_release(A->dense);
   amg_release(A->z);
+  amg_release(A->tail_bar);
   for (int k = 0; k < kAmgKinds; ++k) {
     AmgOpSet& S = A->sets[k];
     auto rel = [&](auto*& p) { if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; } };
@@ -922,6 +1079,21 @@ static int amg_finish_setup(Context* ctx, Amg* A, int nlev, double t0) {
   DDPS_CUDA(cudaFuncSetAttribute(k_amg_dense_inverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kAmgDenseShared * kAmgDenseShared * (int)sizeof(double)));
   if ((rc = amg_alloc(ctx, &A->z, (size_t)A->lv[0].n))) return rc;
+  // fused tail of the cycle: from the first small, replicated, FP64-only level down (k_amg_tail)
+  A->tail_from = 0;
+  if (!getenv("DDPS_AMG_NO_TAIL")) {
+    int lt = nlev;
+    while (lt > 1 && A->lv[lt - 1].n <= kAmgSmallLevel && A->lv[lt - 1].dist == 0 && !A->lv[lt - 1].val32 && nlev - (lt - 1) <= kAmgTailMax) --lt;
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_amg_tail, 256, 0);
+    if (coop && per_sm >= 1 && nlev - lt >= 2) {   // (a tail of the coarsest level alone is the dense solve: nothing to fuse)
+      A->tail_from = lt;
+      A->tail_grid = ctx->num_sms;
+      if (!A->tail_bar && (rc = amg_alloc(ctx, &A->tail_bar, 2))) return rc;
+      DDPS_CUDA(cudaMemsetAsync(A->tail_bar, 0, 2 * sizeof(unsigned), ctx->stream));
+    }
+  }
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
   A->ready = true;
   A->setup_ms = wall_ms() - t0;
@@ -1187,7 +1359,6 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind) {
   return 0;
 }
 
-constexpr int kAmgSmallLevel = 32768;   // rows; below this the warp-per-row kernels run
 
 template <int MODE, bool DOT>
 static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x, const double* b, double om, double* y) {
@@ -1221,7 +1392,9 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
   int rc;
   A.lv[0].b = const_cast<double*>(r);
   A.lv[0].x2 = z;
-  for (int l = 0; l + 1 < A.nlev; ++l) {
+  const int lt = (A.tail_from > 0 && A.tail_from < A.nlev) ? A.tail_from : A.nlev;   // first level of the fused tail
+  const int ltop = std::min(A.nlev - 1, lt);                                          // per-level launches for l < ltop
+  for (int l = 0; l < ltop; ++l) {
     AmgLevelDev& L = A.lv[l];
     if (l == 0 && !have_first_sweep) {   // (inside the CG the update kernel already produced the first sweep of the finest
       k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);   // level; coarser
@@ -1253,13 +1426,29 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
       prof_mark(ctx, "tail allreduce + sweep");
     }
   }
-  {
+  if (lt < A.nlev) {
+    TailArgs T;
+    T.nl = A.nlev - lt;
+    for (int l = lt; l < A.nlev; ++l) {
+      const AmgLevelDev& L = A.lv[l];
+      TailLevel& t = T.lv[l - lt];
+      t.n = L.n; t.nc = L.nc; t.nslices = L.nslices; t.wpr = L.n <= kAmgTailWpr;
+      t.slice_ptr = L.slice_ptr; t.col = L.col; t.rowptr = L.rowptr; t.val = L.cur_val; t.dinv = L.cur_dinv;
+      t.Pptr = L.Pptr; t.Rptr = L.Rptr; t.Pent = L.Pent; t.Rent = L.Rent;
+      t.b = L.b; t.x = L.x; t.x2 = L.x2; t.t = L.t;
+    }
+    T.dense = A.cur_dense; T.om = om; T.bar = A.tail_bar; T.scal = ctx->scal;
+    void* args[] = {&T};
+    DDPS_CUDA(cudaLaunchCooperativeKernel((const void*)k_amg_tail, dim3(A.tail_grid), dim3(256), args, 0, st));
+    ctx->stats.kernel_launches++;
+    prof_mark(ctx, "fused tail of the cycle");
+  } else {
     AmgLevelDev& L = A.lv[A.nlev - 1];
     k_amg_dense_apply<<<1, 1024, 0, st>>>(L.n, A.cur_dense, L.b, L.x2, ctx->scal);
     ctx->stats.kernel_launches++;
     prof_mark(ctx, "coarsest solve");
   }
-  for (int l = A.nlev - 2; l >= 0; --l) {
+  for (int l = ltop - 1; l >= 0; --l) {
     AmgLevelDev& L = A.lv[l];
     AmgLevelDev& C = A.lv[l + 1];
     if (L.dist == 1 && (rc = halo_xchg(ctx, *C.plan, C.x2, true))) return rc;

@@ -93,6 +93,8 @@ struct Amg {
   double* z = nullptr;       // [n0] preconditioned residual of the CG
   double omega = 2.0 / 3.0;
   double setup_ms = 0.0;
+  int tail_from = 0, tail_grid = 0;   // fused tail of the cycle (k_amg_tail): first level it covers (0: off), CTAs
+  unsigned* tail_bar = nullptr;       // its grid-barrier counters
 };
 
 
