@@ -218,14 +218,21 @@ __global__ void k_amg_jac0(int n, double om, const double* __restrict__ dinv, co
 
 // bc = R t   (R = P^T stored row-wise: a deterministic gather); fused: xc = om * dinv_c * bc, the first damped-Jacobi
 // sweep of the coarse level from the zero initial guess (dinv_c == nullptr on the coarsest level)
-__global__ void k_amg_restrict(int nc, const int* __restrict__ Rptr, const int2* __restrict__ Rent,
+__global__ void __launch_bounds__(256) k_amg_restrict(int nc, const int* __restrict__ Rptr, const int2* __restrict__ Rent,
                                const double* __restrict__ t, double* __restrict__ bc, const double* __restrict__ dinv_c,
                                double om, double* __restrict__ xc, const PcgScalars* scal) {
   if (scal->done) return;
   for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += gridDim.x * blockDim.x) {
     double s = 0.0;
     const int e = Rptr[I + 1];
-    for (int q = Rptr[I]; q < e; ++q) {
+    int q = Rptr[I];
+    for (; q + 4 <= e; q += 4) {   // four entries, then their four gathers, in flight together; summed in entry order
+      const int2 e0 = Rent[q], e1 = Rent[q + 1], e2 = Rent[q + 2], e3 = Rent[q + 3];
+      const double t0 = __ldg(t + e0.x), t1 = __ldg(t + e1.x), t2 = __ldg(t + e2.x), t3 = __ldg(t + e3.x);
+      s += (double)__int_as_float(e0.y) * t0; s += (double)__int_as_float(e1.y) * t1;
+      s += (double)__int_as_float(e2.y) * t2; s += (double)__int_as_float(e3.y) * t3;
+    }
+    for (; q < e; ++q) {
       const int2 en = Rent[q];
       s += (double)__int_as_float(en.y) * __ldg(t + en.x);
     }

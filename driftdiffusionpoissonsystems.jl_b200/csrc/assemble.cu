@@ -456,36 +456,42 @@ int launch_assemble_newton(Context* ctx, const AsmArgs& a, int rhs_kind) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ void put_rec(double* __restrict__ rec, int i, double gw, double s1, double u, double v,
+// The records of a block's 256 consecutive nodes are one contiguous 12 KB piece of memory: they go through shared memory so
+// that the stores are coalesced 16-byte pieces (a thread storing its own three pieces writes 32 scattered sectors per request).
+constexpr int kPrepBlock = 256;
+__device__ __forceinline__ void put_rec(double* __restrict__ rec, int n, double gw, double s1, double u, double v,
                                         double eh, double ehi) {
-  double2* r = reinterpret_cast<double2*>(rec + (size_t)i * kRecD);
-  r[0] = make_double2(gw, s1);
-  r[1] = make_double2(u, v);
-  r[2] = make_double2(eh, ehi);
+  __shared__ double2 sh[kPrepBlock * 3];
+  const int t = threadIdx.x;
+  sh[3 * t] = make_double2(gw, s1);
+  sh[3 * t + 1] = make_double2(u, v);
+  sh[3 * t + 2] = make_double2(eh, ehi);
+  __syncthreads();
+  const size_t first = (size_t)blockIdx.x * kPrepBlock;               // first node of the block
+  const int cnt = (int)min((size_t)kPrepBlock, (size_t)n - first) * 3;   // 16-byte pieces to store
+  double2* out = reinterpret_cast<double2*>(rec + first * kRecD);
+  for (int i = t; i < cnt; i += kPrepBlock) out[i] = sh[i];
 }
 
-__global__ void k_prep_base(int n, const unsigned char* __restrict__ isD, double* __restrict__ rec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  put_rec(rec, i, 0.0, isD[i] ? -1.0 : 1.0, 0.0, 0.0, 0.0, 0.0);
+__global__ void __launch_bounds__(kPrepBlock) k_prep_base(int n, const unsigned char* __restrict__ isD, double* __restrict__ rec) {
+  const int i = min(blockIdx.x * blockDim.x + threadIdx.x, n - 1);   // (the tail threads recompute the last node; not stored)
+  put_rec(rec, n, 0.0, isD[i] ? -1.0 : 1.0, 0.0, 0.0, 0.0, 0.0);
 }
 
-__global__ void k_prep_poisson(int n, const double* __restrict__ V, const double* __restrict__ u,
-                               const double* __restrict__ v, double delta2, double* __restrict__ rec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void __launch_bounds__(kPrepBlock) k_prep_poisson(int n, const double* __restrict__ V, const double* __restrict__ u,
+                                                             const double* __restrict__ v, double delta2, double* __restrict__ rec) {
+  const int i = min(blockIdx.x * blockDim.x + threadIdx.x, n - 1);
   const double Vi = V[i], ui = u[i], vi = v[i];
   const double gw = -delta2 * (ui * exp(Vi) + vi * exp(-Vi));  // src:375-377
-  put_rec(rec, i, gw, Vi, ui, vi, exp(Vi / 2.0), exp(-Vi / 2.0));
+  put_rec(rec, n, gw, Vi, ui, vi, exp(Vi / 2.0), exp(-Vi / 2.0));
 }
 
 // sign = +1: u-solve with (V, tau_p, tau_n, u0, v0); sign = -1: v-solve, the reference passes
 // (-V, tau_n, tau_p, v0, u0) (src:598-599).  V here is always the true potential.
-__global__ void k_prep_uv(int n, double sign, const double* __restrict__ V, const double* __restrict__ u0,
-                          const double* __restrict__ v0, double tau_p, double tau_n, int shockley,
-                          const unsigned char* __restrict__ isD, double* __restrict__ rec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void __launch_bounds__(kPrepBlock) k_prep_uv(int n, double sign, const double* __restrict__ V, const double* __restrict__ u0,
+                                                        const double* __restrict__ v0, double tau_p, double tau_n, int shockley,
+                                                        const unsigned char* __restrict__ isD, double* __restrict__ rec) {
+  const int i = min(blockIdx.x * blockDim.x + threadIdx.x, n - 1);
   const double Vs = sign * V[i];   // the "V" the reference's uvsolve sees
   const double a = (sign > 0) ? u0[i] : v0[i];   // callee's u0
   const double b = (sign > 0) ? v0[i] : u0[i];   // callee's v0
@@ -496,15 +502,14 @@ __global__ void k_prep_uv(int n, double sign, const double* __restrict__ V, cons
     const double tp = (sign > 0) ? tau_p : tau_n, tn = (sign > 0) ? tau_n : tau_p;
     gw = -b / (tp * (exp(Vs) * a + 1.0) + tn * (exp(-Vs) * b + 1.0));
   }
-  put_rec(rec, i, gw, isD[i] ? -e3 : e3, a, b, exp(Vs / 2.0), exp(-Vs / 2.0));
+  put_rec(rec, n, gw, isD[i] ? -e3 : e3, a, b, exp(Vs / 2.0), exp(-Vs / 2.0));
 }
 
 struct PolyNodal { const double* c[kMaxPoly]; };
 
-__global__ void k_prep_semlin(int n, const double* __restrict__ V, int kind, double p0, double p1, PolyNodal pn,
-                              double* __restrict__ rec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void __launch_bounds__(kPrepBlock) k_prep_semlin(int n, const double* __restrict__ V, int kind, double p0, double p1, PolyNodal pn,
+                                                            double* __restrict__ rec) {
+  const int i = min(blockIdx.x * blockDim.x + threadIdx.x, n - 1);
   const double u = V[i];
   double g;
   if (kind == DDPS_FUNCTOR_SINH) {
@@ -514,7 +519,7 @@ __global__ void k_prep_semlin(int n, const double* __restrict__ V, int kind, dou
     g = 0.0;
     for (int d = deg; d >= 1; --d) g = g * u + d * pn.c[d][i];
   }
-  put_rec(rec, i, g, u, 0.0, 0.0, 0.0, 0.0);   // src:1046-1048
+  put_rec(rec, n, g, u, 0.0, 0.0, 0.0, 0.0);   // src:1046-1048
 }
 
 __global__ void k_permute_mid(int64_t n, const int* __restrict__ inc_tri, const double* __restrict__ mid,
@@ -530,7 +535,7 @@ __global__ void k_permute_mid(int64_t n, const int* __restrict__ inc_tri, const 
 int launch_prep_base(Context* ctx) {
   int n = ctx->n_loc;
   if (!n) return 0;
-  k_prep_base<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->isD, ctx->rec);
+  k_prep_base<<<(n + kPrepBlock - 1) / kPrepBlock, kPrepBlock, 0, ctx->stream>>>(n, ctx->isD, ctx->rec);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
   return 0;
@@ -539,7 +544,7 @@ int launch_prep_base(Context* ctx) {
 int launch_prep_poisson(Context* ctx, const double* V, const double* u, const double* v, double delta2) {
   int n = ctx->n_loc;
   if (!n) return 0;
-  k_prep_poisson<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, V, u, v, delta2, ctx->rec);
+  k_prep_poisson<<<(n + kPrepBlock - 1) / kPrepBlock, kPrepBlock, 0, ctx->stream>>>(n, V, u, v, delta2, ctx->rec);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
   return 0;
@@ -549,7 +554,7 @@ int launch_prep_uv(Context* ctx, double sign, const double* V, const double* u0,
                    double tau_n, int rec_mode) {
   int n = ctx->n_loc;
   if (!n) return 0;
-  k_prep_uv<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, sign, V, u0, v0, tau_p, tau_n, rec_mode == DDPS_REC_SHOCKLEY,
+  k_prep_uv<<<(n + kPrepBlock - 1) / kPrepBlock, kPrepBlock, 0, ctx->stream>>>(n, sign, V, u0, v0, tau_p, tau_n, rec_mode == DDPS_REC_SHOCKLEY,
                                                     ctx->isD, ctx->rec);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
@@ -561,7 +566,7 @@ int launch_prep_semlin(Context* ctx, const double* V) {
   if (!n) return 0;
   PolyNodal pn;
   for (int k = 0; k < kMaxPoly; ++k) pn.c[k] = ctx->coeff[DDPS_COEFF_POLY_NODE0 + k];
-  k_prep_semlin<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, V, ctx->functor_kind, ctx->functor_par[0],
+  k_prep_semlin<<<(n + kPrepBlock - 1) / kPrepBlock, kPrepBlock, 0, ctx->stream>>>(n, V, ctx->functor_kind, ctx->functor_par[0],
                                                         ctx->functor_par[1], pn, ctx->rec);
   ctx->stats.kernel_launches++;
   DDPS_CUDA(cudaGetLastError());
