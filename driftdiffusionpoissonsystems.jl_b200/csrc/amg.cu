@@ -247,13 +247,26 @@ __global__ void k_amg_prolong(int n, const int* __restrict__ Pptr, const int2* _
   if (scal->done) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double s = 0.0;
-    const int e = Pptr[i + 1];
-#pragma unroll 1   // rows hold 2-4 entries: a 16x unrolled body would never run
-    for (int m = Pptr[i]; m < e; ++m) {
-      const int2 en = Pent[m];
-      if (en.x >= 0) s += (double)__int_as_float(en.y) * __ldg(xc + en.x);
+    const int m0 = Pptr[i], e = Pptr[i + 1];
+    const double xi = x[i];
+    if (e - m0 <= 4) {   // the usual row (1-4 aggregates): all entries, then all gathers, in flight together; summed in entry order
+      int2 en[4];
+      double xv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) en[k] = (m0 + k < e) ? Pent[m0 + k] : make_int2(-1, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xv[k] = (en[k].x >= 0) ? __ldg(xc + en[k].x) : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (en[k].x >= 0) s += (double)__int_as_float(en[k].y) * xv[k];
+    } else {
+#pragma unroll 1
+      for (int m = m0; m < e; ++m) {
+        const int2 en = Pent[m];
+        if (en.x >= 0) s += (double)__int_as_float(en.y) * __ldg(xc + en.x);
+      }
     }
-    x[i] += s;
+    x[i] = xi + s;
   }
 }
 
