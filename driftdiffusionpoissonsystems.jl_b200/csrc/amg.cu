@@ -226,7 +226,17 @@ __global__ void __launch_bounds__(256) k_amg_restrict(int nc, const int* __restr
     double s = 0.0;
     const int e = Rptr[I + 1];
     int q = Rptr[I];
-    for (; q + 4 <= e; q += 4) {   // four entries, then their four gathers, in flight together; summed in entry order
+    for (; q + 8 <= e; q += 8) {   // eight entries, then their eight gathers, in flight together; summed in entry order
+      int2 en[8];
+      double tv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) en[k] = Rent[q + k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tv[k] = __ldg(t + en[k].x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += (double)__int_as_float(en[k].y) * tv[k];
+    }
+    for (; q + 4 <= e; q += 4) {
       const int2 e0 = Rent[q], e1 = Rent[q + 1], e2 = Rent[q + 2], e3 = Rent[q + 3];
       const double t0 = __ldg(t + e0.x), t1 = __ldg(t + e1.x), t2 = __ldg(t + e2.x), t3 = __ldg(t + e3.x);
       s += (double)__int_as_float(e0.y) * t0; s += (double)__int_as_float(e1.y) * t1;
