@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_amg_spmv(int nrows, int nslice
                                                         const double* __restrict__ x, const double* __restrict__ b,
                                                         const double* __restrict__ dinv, double om,
                                                         double* __restrict__ y, double* partials, PcgScalars* scal) {
+  pdl_enter();
   __shared__ double sh_red[32];
   if (scal->done) return;
   const int lane = threadIdx.x & 31;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256) k_amg_spmv_wpr(int nrows, const int* __re
                                                       const double* __restrict__ x, const double* __restrict__ b,
                                                       const double* __restrict__ dinv, double om, double* __restrict__ y,
                                                       const PcgScalars* scal) {
+  pdl_enter();
   if (scal->done) return;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(256) k_amg_restrict_wpr(int nc, const int* __r
                                                           const double* __restrict__ t, double* __restrict__ bc,
                                                           const double* __restrict__ dinv_c, double om, double* __restrict__ xc,
                                                           const PcgScalars* scal) {
+  pdl_enter();
   if (scal->done) return;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -212,6 +215,7 @@ __global__ void k_amg_to_float(size_t n, const double* __restrict__ in, float* _
 // x = om * dinv * b  (first damped-Jacobi sweep from the zero initial guess)
 __global__ void k_amg_jac0(int n, double om, const double* __restrict__ dinv, const double* __restrict__ b,
                            double* __restrict__ x, const PcgScalars* scal) {
+  pdl_enter();
   if (scal->done) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = om * (dinv[i] * b[i]);
 }
@@ -221,6 +225,7 @@ __global__ void k_amg_jac0(int n, double om, const double* __restrict__ dinv, co
 __global__ void __launch_bounds__(256) k_amg_restrict(int nc, const int* __restrict__ Rptr, const int2* __restrict__ Rent,
                                const double* __restrict__ t, double* __restrict__ bc, const double* __restrict__ dinv_c,
                                double om, double* __restrict__ xc, const PcgScalars* scal) {
+  pdl_enter();
   if (scal->done) return;
   for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += gridDim.x * blockDim.x) {
     double s = 0.0;
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(256) k_amg_restrict(int nc, const int* __restr
 // x += P xc
 __global__ void k_amg_prolong(int n, const int* __restrict__ Pptr, const int2* __restrict__ Pent,
                               const double* __restrict__ xc, double* __restrict__ x, const PcgScalars* scal) {
+  pdl_enter();
   if (scal->done) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double s = 0.0;
@@ -795,6 +801,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, in
                                                            const double* __restrict__ dinv, double om, double* __restrict__ xs,
                                                            double* partials, PcgScalars* scal) {
   __shared__ double sh_red[32];
+  pdl_enter();
   if (scal->done) return;
   const double pq = scal->sums[0];
   const double rz = scal->rz[par];
@@ -831,6 +838,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_update(int n, int par, in
 __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_direction(int n, int par, int first, double rtol,
                                                               const double* __restrict__ z, double* __restrict__ p,
                                                               PcgScalars* scal) {
+  pdl_enter();
   if (scal->done) return;
   const double rz_new = scal->sums[1];
   const double beta = first ? 0.0 : rz_new / scal->rz[par];
@@ -1393,19 +1401,19 @@ int amg_numeric(Context* ctx, const double* val, const double* dinv, int kind) {
 template <int MODE, bool DOT>
 static void launch_amg_spmv(Context* ctx, const AmgLevelDev& L, const double* x, const double* b, double om, double* y) {
   if (!DOT && L.n <= kAmgSmallLevel && !L.cur32) {
-    k_amg_spmv_wpr<MODE><<<amg_grid(ctx, (int64_t)L.n * 32, 256), 256, 0, ctx->stream>>>(L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, x, b,
-                                                                                        L.cur_dinv, om, y, ctx->scal);
+    (void)(launch_pdl(k_amg_spmv_wpr<MODE>, amg_grid(ctx, (int64_t)L.n * 32, 256), 256, 0, ctx->stream, L.n, L.rowptr, L.slice_ptr, L.col, L.cur_val, x, b,
+                                                                                        L.cur_dinv, om, y, ctx->scal));
     ctx->stats.kernel_launches++;
     ctx->stats.spmv_total++;
     return;
   }
   const int grid = amg_grid(ctx, (int64_t)L.nslices * 32, kVecBlock);
   if (L.cur32)
-    k_amg_spmv<MODE, DOT, float><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur32, x, b, L.cur_dinv,
-                                                                     om, y, ctx->partials, ctx->scal);
+    (void)(launch_pdl(k_amg_spmv<MODE, DOT, float>, grid, kVecBlock, 0, ctx->stream, L.n, L.nslices, L.slice_ptr, L.col, L.cur32, x, b, L.cur_dinv,
+                                                                     om, y, ctx->partials, ctx->scal));
   else
-    k_amg_spmv<MODE, DOT, double><<<grid, kVecBlock, 0, ctx->stream>>>(L.n, L.nslices, L.slice_ptr, L.col, L.cur_val, x, b, L.cur_dinv,
-                                                            om, y, ctx->partials, ctx->scal);
+    (void)(launch_pdl(k_amg_spmv<MODE, DOT, double>, grid, kVecBlock, 0, ctx->stream, L.n, L.nslices, L.slice_ptr, L.col, L.cur_val, x, b, L.cur_dinv,
+                                                            om, y, ctx->partials, ctx->scal));
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
 }
@@ -1427,7 +1435,7 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
   for (int l = 0; l < ltop; ++l) {
     AmgLevelDev& L = A.lv[l];
     if (l == 0 && !have_first_sweep) {   // (inside the CG the update kernel already produced the first sweep of the finest
-      k_amg_jac0<<<amg_grid(ctx, L.n, 256), 256, 0, st>>>(L.n, om, L.cur_dinv, L.b, L.x, ctx->scal);   // level; coarser
+      DDPS_CUDA(launch_pdl(k_amg_jac0, amg_grid(ctx, L.n, 256), 256, 0, st, L.n, om, L.cur_dinv, L.b, L.x, ctx->scal));   // level; coarser
       ctx->stats.kernel_launches++;                                                                    // levels: fused in restrict)
     }
     if (L.dist && (rc = halo_xchg(ctx, *L.plan, L.x, true))) return rc;
@@ -1440,17 +1448,17 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
     const bool coarsest = (l + 2 == A.nlev);
     const bool fuse_sweep = !coarsest && L.dist != 2;   // transition: the sweep needs the COMPLETED right-hand side
     if (L.nc <= kAmgSmallLevel)
-      k_amg_restrict_wpr<<<amg_grid(ctx, (int64_t)L.nc * 32, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr,
-                                                                                om, C.x, ctx->scal);
+      DDPS_CUDA(launch_pdl(k_amg_restrict_wpr, amg_grid(ctx, (int64_t)L.nc * 32, 256), 256, 0, st, L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr,
+                                                                                om, C.x, ctx->scal));
     else
-      k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, st>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr, om, C.x,
-                                                              ctx->scal);
+      DDPS_CUDA(launch_pdl(k_amg_restrict, amg_grid(ctx, L.nc, 256), 256, 0, st, L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr, om, C.x,
+                                                              ctx->scal));
     ctx->stats.kernel_launches++;
     prof_mark(ctx, l == 0 ? "L0 restrict" : l == 1 ? "L1 restrict" : "L>1 restrict");
     if (L.dist == 2) {
       if ((rc = comm_allreduce(ctx, C.b, (size_t)C.n, COMM_SUM))) return rc;
       if (!coarsest) {
-        k_amg_jac0<<<amg_grid(ctx, C.n, 256), 256, 0, st>>>(C.n, om, C.cur_dinv, C.b, C.x, ctx->scal);
+        DDPS_CUDA(launch_pdl(k_amg_jac0, amg_grid(ctx, C.n, 256), 256, 0, st, C.n, om, C.cur_dinv, C.b, C.x, ctx->scal));
         ctx->stats.kernel_launches++;
       }
       prof_mark(ctx, "tail allreduce + sweep");
@@ -1487,7 +1495,7 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
     // pre-smoothed x from the exchange on the way down): same numbers in the same order as on the owner, so x needs no
     // exchange before the smoothing sweep
     const int np = L.dist ? L.n_loc : L.n;
-    k_amg_prolong<<<amg_grid(ctx, np, 256), 256, 0, st>>>(np, L.Pptr, L.Pent, C.x2, L.x, ctx->scal);
+    DDPS_CUDA(launch_pdl(k_amg_prolong, amg_grid(ctx, np, 256), 256, 0, st, np, L.Pptr, L.Pent, C.x2, L.x, ctx->scal));
     ctx->stats.kernel_launches++;
     prof_mark(ctx, l == 0 ? "L0 prolong" : l == 1 ? "L1 prolong" : "L>1 prolong");
     if (l == 0 && dot_rz) launch_amg_spmv<2, true>(ctx, L, L.x, L.b, om, L.x2);
@@ -1530,16 +1538,16 @@ int amg_time_launch(Context* ctx, int which, int it, double* bytes) {
       if (bytes) *bytes = (vw + 4.0) * nnz + 4.0 * (n + 1) + 4 * 8.0 * n;
       return 0;
     case 11:
-      k_apcg_update<true><<<amg_grid(ctx, L.n, kVecBlock), kVecBlock, 0, ctx->stream>>>(L.n, it & 1, it, 1 << 30, ctx->p, ctx->q, ctx->x, ctx->r, L.cur_dinv,
-                                                                                A.omega, L.x, ctx->partials, ctx->scal);
+      DDPS_CUDA(launch_pdl(k_apcg_update<true>, amg_grid(ctx, L.n, kVecBlock), kVecBlock, 0, ctx->stream, L.n, it & 1, it, 1 << 30, ctx->p, ctx->q, ctx->x, ctx->r, L.cur_dinv,
+                                                                                A.omega, L.x, ctx->partials, ctx->scal));
       if (bytes) *bytes = 8 * 8.0 * n;
       return 0;
     case 12:
-      k_amg_restrict<<<amg_grid(ctx, L.nc, 256), 256, 0, ctx->stream>>>(L.nc, L.Rptr, L.Rent, L.t, C.b, C.cur_dinv, A.omega, C.x, ctx->scal);
+      DDPS_CUDA(launch_pdl(k_amg_restrict, amg_grid(ctx, L.nc, 256), 256, 0, ctx->stream, L.nc, L.Rptr, L.Rent, L.t, C.b, C.cur_dinv, A.omega, C.x, ctx->scal));
       if (bytes) *bytes = 8.0 * nnzP + 4.0 * (nc + 1) + 8.0 * n + 3 * 8.0 * nc;
       return 0;
     case 13:
-      k_amg_prolong<<<amg_grid(ctx, L.n, 256), 256, 0, ctx->stream>>>(L.n, L.Pptr, L.Pent, C.x2, L.x, ctx->scal);
+      DDPS_CUDA(launch_pdl(k_amg_prolong, amg_grid(ctx, L.n, 256), 256, 0, ctx->stream, L.n, L.Pptr, L.Pent, C.x2, L.x, ctx->scal));
       if (bytes) *bytes = 8.0 * nnzP + 4.0 * (n + 1) + 8.0 * nc + 2 * 8.0 * n;
       return 0;
   }
@@ -1584,20 +1592,20 @@ int amg_pcg_iteration_launch(Context* ctx, double* x, int it, int max_it) {
   if (mr) {
     if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[0], 1, 0, true))) return rc;
     prof_mark(ctx, "allreduce p.Ap");
-    k_apcg_update<false><<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
-                                                            A.lv[0].x, ctx->partials, ctx->scal);
+    DDPS_CUDA(launch_pdl(k_apcg_update<false>, g2, kVecBlock, 0, ctx->stream, n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
+                                                            A.lv[0].x, ctx->partials, ctx->scal));
     if ((rc = scalar_allreduce(ctx, &ctx->scal->sums[2], 1, 1, true))) return rc;   // {r.r, max|r|}
     k_apcg_decide<<<1, 1, 0, ctx->stream>>>(ctx->scal, par, it, max_it);
     ctx->stats.kernel_launches++;
     prof_mark(ctx, "update + allreduce + decide");
   } else {
-    k_apcg_update<true><<<g2, kVecBlock, 0, ctx->stream>>>(n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
-                                                           A.lv[0].x, ctx->partials, ctx->scal);
+    DDPS_CUDA(launch_pdl(k_apcg_update<true>, g2, kVecBlock, 0, ctx->stream, n, par, it, max_it, ctx->p, ctx->q, x, ctx->r, A.lv[0].cur_dinv, A.omega,
+                                                           A.lv[0].x, ctx->partials, ctx->scal));
     prof_mark(ctx, "update");
   }
   if ((rc = amg_vcycle_impl(ctx, ctx->r, A.z, true, true))) return rc;             // z = B r, r.z -> sums[1]
   if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[1], 1, 0, true))) return rc;
-  k_apcg_direction<<<g2, kVecBlock, 0, ctx->stream>>>(n, par, 0, 0.0, A.z, ctx->p, ctx->scal);
+  DDPS_CUDA(launch_pdl(k_apcg_direction, g2, kVecBlock, 0, ctx->stream, n, par, 0, 0.0, A.z, ctx->p, ctx->scal));
   prof_mark(ctx, mr ? "allreduce r.z + direction" : "direction");
   ctx->stats.kernel_launches += 2;
   if (it == 3) prof_end(ctx);
@@ -1629,7 +1637,7 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
   k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf, x0_nonzero ? 1 : 0, ctx->eps_e);
   if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;
   if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[1], 1, 0, true))) return rc;
-  k_apcg_direction<<<g, kVecBlock, 0, st>>>(n, 0, 1, rtol, A.z, ctx->p, ctx->scal);
+  DDPS_CUDA(launch_pdl(k_apcg_direction, g, kVecBlock, 0, st, n, 0, 1, rtol, A.z, ctx->p, ctx->scal));
   ctx->stats.kernel_launches += 3;
   DDPS_CUDA(cudaGetLastError());
 

@@ -6,6 +6,35 @@
 namespace ddps {
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the kernels of the CG iteration are launched with the programmatic-stream-serialization
+// attribute, so the NEXT kernel's CTAs are scheduled while the tail of the current one is still running and find their launch
+// latency hidden; each such kernel starts with pdl_enter(): wait until the preceding kernel has completed and its writes are
+// visible (nothing before this touches memory), then allow its own dependent to be scheduled.  Both instructions are no-ops for
+// a kernel launched the ordinary way.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = getenv("DDPS_NO_PDL") == nullptr;
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_spmv(int nrows, int nslices, c
                                                     const double* __restrict__ x, double* __restrict__ y,
                                                     double* partials, PcgScalars* scal, const P2PDev pd, const int rev) {
   __shared__ double sh_red[32];
+  pdl_enter();
   if (DOT && scal->done) return;
   if (MR) {   // the neighbours' halo pushes for this iteration must have landed
     if (threadIdx.x < pd.nneigh) {
@@ -190,7 +191,8 @@ int launch_spmv(Context* ctx, const double* val, const double* x, double* y) {
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
-  k_spmv<false, false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr, none, 0);
+  DDPS_CUDA(launch_pdl(k_spmv<false, false>, grid, kVecBlock, 0, ctx->stream, P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, nullptr, nullptr,
+                       none, 0));
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
@@ -202,7 +204,8 @@ int launch_spmv_dot(Context* ctx, const double* val, const double* x, double* y)
   if (!P.nslices) return 0;
   int grid = vec_grid(ctx, (int64_t)P.nslices * 32, kVecBlock);
   P2PDev none; memset(&none, 0, sizeof(none)); none.nranks = 1;
-  k_spmv<true, false><<<grid, kVecBlock, 0, ctx->stream>>>(P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials, ctx->scal, none, 0);
+  DDPS_CUDA(launch_pdl(k_spmv<true, false>, grid, kVecBlock, 0, ctx->stream, P.nrows, P.nslices, P.slice_ptr, P.col, val, x, y, ctx->partials,
+                       ctx->scal, none, 0));
   ctx->stats.kernel_launches++;
   ctx->stats.spmv_total++;
   DDPS_CUDA(cudaGetLastError());
