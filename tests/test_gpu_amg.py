@@ -250,3 +250,28 @@ def test_lagged_coarse_operators(D, O):
     assert sl["outer_iters"] == se["outer_iters"]
     assert [int(k) for k in sl["newton_per_vsolve"]] == [int(k) for k in se["newton_per_vsolve"]]
     assert sl["pcg_total"] <= 1.1 * se["pcg_total"] + 4, (sl["pcg_total"], se["pcg_total"])
+
+
+def test_fused_cycle_tail_equals_per_level_launches(D, monkeypatch):
+    """k_amg_tail runs the levels below 32768 rows of the V-cycle in ONE cooperative launch (grid barriers between the phases)
+    instead of one launch per level and phase (DDPS_AMG_NO_TAIL=1).  Same arithmetic on every level of <= 4096 rows, a different
+    but fixed row-summation order between 4096 and 32768 rows: same Gummel / Newton path, CG counts within one iteration per
+    solve, fields equal far below the parity tolerance; and the fused launch is what runs by default (fewer launches)."""
+    mesh = D.structured_mesh(320, 160, 0.0, 2.0, 0.0, 1.0)   # levels 51681 / ~8600 / ~960 / ... rows
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
+    out = {}
+    for name in ("fused", "per_level"):
+        if name == "per_level":
+            monkeypatch.setenv("DDPS_AMG_NO_TAIL", "1")
+        with D.Session(0, precond=1) as s:
+            V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+        out[name] = (V, u, v, st)
+    monkeypatch.delenv("DDPS_AMG_NO_TAIL")
+    sf, sp_ = out["fused"][3], out["per_level"][3]
+    assert sf["amg_levels"] >= 4
+    assert sf["outer_iters"] == sp_["outer_iters"]
+    assert [int(k) for k in sf["newton_per_vsolve"]] == [int(k) for k in sp_["newton_per_vsolve"]]
+    assert np.all(np.abs(np.array(sf["pcg_per_solve"]) - np.array(sp_["pcg_per_solve"])) <= 1)
+    for a, b in zip(out["fused"][:3], out["per_level"][:3]):
+        assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)
+    assert sf["kernel_launches"] < 0.8 * sp_["kernel_launches"], (sf["kernel_launches"], sp_["kernel_launches"])
