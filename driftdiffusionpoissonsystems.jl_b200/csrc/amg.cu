@@ -578,6 +578,23 @@ __global__ void __launch_bounds__(1024) k_amg_dense_apply(int n, const double* _
 
 constexpr int kAmgSmallLevel = 32768;   // rows; below this the warp-per-row kernels run (and the fused tail of the cycle starts)
 
+// b = sum over the ranks of the partial restrictions of the transition level, in rank order (bitwise the same on every rank);
+// fused: the first damped-Jacobi sweep of the (replicated) level from the zero guess
+__global__ void k_amg_tail_sum(int nc, int nr, int me, const double* __restrict__ parts, double* __restrict__ b,
+                               const double* __restrict__ dinv, double om, double* __restrict__ x, const PcgScalars* scal) {
+  pdl_enter();
+  if (scal->done) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < nr; ++q) {
+      const double v = parts[(q == me ? 0 : (size_t)(1 + (q < me ? q : q - 1)) * nc) + i];
+      s = q == 0 ? v : s + v;
+    }
+    b[i] = s;
+    if (dinv) x[i] = om * (dinv[i] * s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // The bottom of the V-cycle in ONE launch.  Below kAmgSmallLevel rows every cycle kernel is a dependent chain of a few
 // memory round trips on a handful of CTAs: 5-11 us per launch, 17 launches for four levels (latency, not work).  This
@@ -880,6 +897,8 @@ void amg_free(Context* ctx) {
   amg_release(A->dense);
   amg_release(A->z);
   amg_release(A->tail_bar);
+  amg_release(A->tail_parts);
+  if (A->tail_plan) { plan_free(*A->tail_plan); delete A->tail_plan; A->tail_plan = nullptr; }
   for (int k = 0; k < kAmgKinds; ++k) {
     AmgOpSet& S = A->sets[k];
     auto rel = [&](auto*& p) { if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; } };
@@ -1117,6 +1136,36 @@ static int amg_finish_setup(Context* ctx, Amg* A, int nlev, double t0) {
   DDPS_CUDA(cudaFuncSetAttribute(k_amg_dense_inverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kAmgDenseShared * kAmgDenseShared * (int)sizeof(double)));
   if ((rc = amg_alloc(ctx, &A->z, (size_t)A->lv[0].n))) return rc;
+  // transition level of a distributed hierarchy: staged all-to-all of the partial right-hand sides (collective: every rank
+  // takes the same decision -- sizes, capacity and the switch are identical everywhere)
+  if (ctx->nranks > 1 && !getenv("DDPS_AMG_TAIL_NCCL")) {
+    for (int l = 0; l + 1 < nlev; ++l) {
+      if (A->lv[l].dist != 2) continue;
+      const int nc = A->lv[l + 1].n, nr = ctx->nranks, me = ctx->rank;
+      if (!ctx->p2p.xenabled || (size_t)(nr - 1) * nc > ctx->p2p.stage_cap) break;
+      HaloPlan* P = new HaloPlan();
+      P->n_own = nc; P->n_ghost = (nr - 1) * nc; P->nneigh = nr - 1;
+      P->send_off.assign(nr, 0); P->recv_off.assign(nr, 0);
+      for (int q = 0, j = 0; q < nr; ++q) {
+        if (q == me) continue;
+        P->peer.push_back(q);
+        ++j;
+        P->send_off[j] = j * nc; P->recv_off[j] = j * nc;
+      }
+      P->nsend = (nr - 1) * nc;
+      std::vector<int> idx((size_t)P->nsend);
+      for (int k = 0; k < P->nsend; ++k) idx[k] = k % nc;
+      DDPS_CUDA(cudaMalloc(&P->send_idx, std::max<size_t>(idx.size(), 1) * sizeof(int)));
+      DDPS_CUDA(cudaMalloc(&P->send_buf, std::max<size_t>(idx.size(), 1) * sizeof(double)));
+      DDPS_CUDA(cudaMemcpyAsync(P->send_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+      A->tail_plan = P;
+      if ((rc = plan_finish(ctx, *P))) return rc;
+      if ((rc = amg_alloc(ctx, &A->tail_parts, (size_t)nr * nc))) return rc;
+      DDPS_CUDA(cudaMemsetAsync(A->tail_parts, 0, (size_t)nr * nc * sizeof(double), ctx->stream));
+      break;
+    }
+  }
   // fused tail of the cycle: from the first small, replicated, FP64-only level down (k_amg_tail)
   A->tail_from = 0;
   if (!getenv("DDPS_AMG_NO_TAIL")) {
@@ -1447,15 +1496,23 @@ static int amg_vcycle_impl(Context* ctx, const double* r, double* z, bool dot_rz
     AmgLevelDev& C = A.lv[l + 1];
     const bool coarsest = (l + 2 == A.nlev);
     const bool fuse_sweep = !coarsest && L.dist != 2;   // transition: the sweep needs the COMPLETED right-hand side
+    const bool staged_sum = L.dist == 2 && A.tail_plan;   // partial sums into my slot of the exchange buffer
+    double* bc = staged_sum ? A.tail_parts : C.b;
     if (L.nc <= kAmgSmallLevel)
-      DDPS_CUDA(launch_pdl(k_amg_restrict_wpr, amg_grid(ctx, (int64_t)L.nc * 32, 256), 256, 0, st, L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr,
+      DDPS_CUDA(launch_pdl(k_amg_restrict_wpr, amg_grid(ctx, (int64_t)L.nc * 32, 256), 256, 0, st, L.nc, L.Rptr, L.Rent, L.t, bc, fuse_sweep ? C.cur_dinv : nullptr,
                                                                                 om, C.x, ctx->scal));
     else
-      DDPS_CUDA(launch_pdl(k_amg_restrict, amg_grid(ctx, L.nc, 256), 256, 0, st, L.nc, L.Rptr, L.Rent, L.t, C.b, fuse_sweep ? C.cur_dinv : nullptr, om, C.x,
+      DDPS_CUDA(launch_pdl(k_amg_restrict, amg_grid(ctx, L.nc, 256), 256, 0, st, L.nc, L.Rptr, L.Rent, L.t, bc, fuse_sweep ? C.cur_dinv : nullptr, om, C.x,
                                                               ctx->scal));
     ctx->stats.kernel_launches++;
     prof_mark(ctx, l == 0 ? "L0 restrict" : l == 1 ? "L1 restrict" : "L>1 restrict");
-    if (L.dist == 2) {
+    if (staged_sum) {
+      if ((rc = halo_xchg(ctx, *A.tail_plan, A.tail_parts, true))) return rc;
+      DDPS_CUDA(launch_pdl(k_amg_tail_sum, amg_grid(ctx, C.n, 256), 256, 0, st, C.n, ctx->nranks, ctx->rank, A.tail_parts, C.b,
+                           coarsest ? nullptr : C.cur_dinv, om, C.x, ctx->scal));
+      ctx->stats.kernel_launches++;
+      prof_mark(ctx, "tail exchange + sum + sweep");
+    } else if (L.dist == 2) {
       if ((rc = comm_allreduce(ctx, C.b, (size_t)C.n, COMM_SUM))) return rc;
       if (!coarsest) {
         DDPS_CUDA(launch_pdl(k_amg_jac0, amg_grid(ctx, C.n, 256), 256, 0, st, C.n, om, C.cur_dinv, C.b, C.x, ctx->scal));

@@ -95,6 +95,10 @@ struct Amg {
   double setup_ms = 0.0;
   int tail_from = 0, tail_grid = 0;   // fused tail of the cycle (k_amg_tail): first level it covers (0: off), CTAs
   unsigned* tail_bar = nullptr;       // its grid-barrier counters
+  // transition level of a distributed hierarchy: the partial right-hand sides of the first replicated level travel by ONE staged
+  // peer-memory exchange (every rank to every rank) and are summed in rank order -- instead of a library allreduce
+  HaloPlan* tail_plan = nullptr;
+  double* tail_parts = nullptr;       // [nranks][n of the first replicated level]: own part first, then the peers' in rank order
 };
 
 

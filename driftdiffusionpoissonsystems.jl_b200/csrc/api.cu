@@ -729,10 +729,8 @@ static int finish_mesh(ddps_ctx* ctx, double t0) {
   }
   if ((rc = dev_alloc(ctx, &ctx->val_base, ne))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->val_op, ne))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->val_s, ne))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->sc, nl))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->bs, no))) return rc;
-  DDPS_CUDA(cudaMemsetAsync(ctx->val_s, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
   DDPS_CUDA(cudaMemsetAsync(ctx->sc, 0, std::max<size_t>(nl, 1) * sizeof(double), ctx->stream));
   DDPS_CUDA(cudaMemsetAsync(ctx->val_base, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
   DDPS_CUDA(cudaMemsetAsync(ctx->val_op, 0, std::max<size_t>(ne, 1) * sizeof(double), ctx->stream));
@@ -1588,7 +1586,7 @@ int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_p
     // fresh PCG state on the last assembled system; rtol 0 keeps the done flag down
     if ((rc = halo_exchange(ctx, ctx->p))) return rc;
     rc = pcg_solve(ctx, ctx->last_val ? ctx->last_val : ctx->val_op, ctx->last_val ? ctx->last_dinv : ctx->dinv,
-                   ctx->last_val == ctx->val_s ? ctx->bs : ctx->b, ctx->x, false, 0.0, -1.0, 1, nullptr, nullptr);
+                   (ctx->val_s && ctx->last_val == ctx->val_s) ? ctx->bs : ctx->b, ctx->x, false, 0.0, -1.0, 1, nullptr, nullptr);
     if (rc != DDPS_ERR_NOCONV && rc != 0) return rc;
     DDPS_CUDA(cudaMemsetAsync(&ctx->scal->done, 0, sizeof(int), ctx->stream));
   }

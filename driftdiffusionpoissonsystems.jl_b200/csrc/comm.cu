@@ -514,7 +514,9 @@ int p2p_setup(Context* ctx) {
   mine.ok = off ? 0 : 1;
   // staging capacity: identical on all ranks (largest ghost block of the finest level, doubled: the coarse levels' ghost
   // sets reach two aggregate rings deep but shrink with the level size)
-  long long cap = 2LL * ctx->halo.n_ghost + 1024;
+  // ... and room for the replicated right-hand side of the multigrid transition level, which every rank receives from every
+  // other rank in one exchange (amg.cu: up to kAmgSmallLevel = 32768 doubles per rank)
+  long long cap = std::max(2LL * ctx->halo.n_ghost + 1024, (long long)(nr - 1) * 32768);
   {
     double c = (double)cap;
     DDPS_CUDA(cudaMemcpyAsync(&ctx->scal->norm_aux2, &c, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
