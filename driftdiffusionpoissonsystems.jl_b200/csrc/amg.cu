@@ -1137,8 +1137,9 @@ static int amg_finish_setup(Context* ctx, Amg* A, int nlev, double t0) {
                                  kAmgDenseShared * kAmgDenseShared * (int)sizeof(double)));
   if ((rc = amg_alloc(ctx, &A->z, (size_t)A->lv[0].n))) return rc;
   // transition level of a distributed hierarchy: staged all-to-all of the partial right-hand sides (collective: every rank
-  // takes the same decision -- sizes, capacity and the switch are identical everywhere)
-  if (ctx->nranks > 1 && !getenv("DDPS_AMG_TAIL_NCCL")) {
+  // takes the same decision -- sizes, capacity and the switch are identical everywhere).  OPT-IN (DDPS_AMG_TAIL_P2P=1): measured
+  // at 16.8M triangles it is no faster than the library allreduce it replaces (8 GPUs: 47.9 vs 42.9 us, 2 GPUs: 25.8 vs 20 us).
+  if (ctx->nranks > 1 && getenv("DDPS_AMG_TAIL_P2P")) {
     for (int l = 0; l + 1 < nlev; ++l) {
       if (A->lv[l].dist != 2) continue;
       const int nc = A->lv[l + 1].n, nr = ctx->nranks, me = ctx->rank;
