@@ -776,6 +776,10 @@ __global__ void k_apcg_init(int n, const double* __restrict__ rhs, const double*
 // the residual of a smooth error (the Gummel update of the previous outer iteration) is far below rtol*||rhs|| long
 // before the error itself is, and a solve that returns its initial guess would end the Gummel loop early.
 __global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int warm, double eps_e) {
+  // a warm start that does not even reduce the residual (||b - A x0|| >= ||b||: the earlier solution this guess comes from has
+  // little to do with the new system) is dropped: k_apcg_cold restarts the solve from x = 0
+  scal->pad0 = (warm && scal->sums[0] >= scal->sums[1]) ? 1 : 0;
+  if (scal->pad0) { warm = 0; scal->sums[0] = scal->sums[1]; scal->sums[2] = 0.0; scal->sums[3] = 1e300; }
   scal->rr = scal->sums[0]; scal->bb = scal->sums[1]; scal->xb = scal->sums[2]; scal->rmax = scal->sums[3];
   scal->thresh2 = rtol * rtol * scal->bb;
   scal->thresh_inf = atol_inf;
@@ -795,6 +799,12 @@ __global__ void k_apcg_start(PcgScalars* scal, double rtol, double atol_inf, int
 // Fused: xs = om * dinv * r, the first damped-Jacobi sweep of the V-cycle on the finest level (saves a pass over r).
 // The convergence decision from the (global) sums {r.r, max|r|}: by the last block of k_apcg_update on one rank, by the
 // one-thread kernel k_apcg_decide after the allreduce in multi-rank contexts (identical on every rank).
+__global__ void k_apcg_cold(int n, const double* __restrict__ rhs, double* __restrict__ x, double* __restrict__ r,
+                            const PcgScalars* scal) {
+  if (!scal->pad0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { x[i] = 0.0; r[i] = rhs[i]; }
+}
+
 __device__ __forceinline__ void apcg_decide(PcgScalars* scal, double rr, double rmax, double rz, int it, int max_it) {
   scal->rr = rr;
   scal->rmax = rmax;
@@ -862,11 +872,13 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_apcg_direction(int n, int par,
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     scal->rz[first ? 0 : (par ^ 1)] = rz_new;
     if (first) {
-      // r0.Br0 ~ the energy of what this solve adds to x0; E_ref carries the largest one across the corrections of a Newton loop
-      const double eref = fmax(scal->e_ref, rz_new);
+      // r0.Br0 ~ the energy of what this solve adds to x0, x0.b ~ the energy of x0 itself (warm start): E_ref carries the largest
+      // SOLUTION energy across the corrections of a Newton loop (a warm-started correction counts with its full size, not with
+      // the little that was left to add)
+      const double eref = fmax(scal->e_ref, fmax(rz_new, fabs(scal->xb)));
       scal->e_ref = eref;
       const double e2 = scal->eps_e2 > 0.0 ? scal->eps_e2 : rtol * rtol;
-      scal->thresh_e = e2 * fmax(fabs(scal->xb), eref);
+      scal->thresh_e = e2 * eref;
     }
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1693,6 +1705,7 @@ int amg_pcg_solve(Context* ctx, const double* val, const double* dinv, const dou
   }
   if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[0], 3, 1, false))) return rc;   // {r.r, b.b, x0.b, max|r|}
   k_apcg_start<<<1, 1, 0, st>>>(ctx->scal, rtol, atol_inf, x0_nonzero ? 1 : 0, ctx->eps_e);
+  if (x0_nonzero) { k_apcg_cold<<<g, kVecBlock, 0, st>>>(n, rhs, x, ctx->r, ctx->scal); ctx->stats.kernel_launches++; }
   if ((rc = amg_vcycle(ctx, ctx->r, A.z, true))) return rc;
   if (mr && (rc = scalar_allreduce(ctx, &ctx->scal->sums[1], 1, 0, true))) return rc;
   DDPS_CUDA(launch_pdl(k_apcg_direction, g, kVecBlock, 0, st, n, 0, 1, rtol, A.z, ctx->p, ctx->scal));

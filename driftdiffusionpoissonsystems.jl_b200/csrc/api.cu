@@ -47,6 +47,7 @@ void free_mesh(Context* ctx) {
   for (int k = 0; k < kMaxPoly; ++k) dev_free(ctx->cinc_poly[k]);
   dev_free(ctx->b); dev_free(ctx->resid); dev_free(ctx->dinv); dev_free(ctx->x); dev_free(ctx->r); dev_free(ctx->q);
   dev_free(ctx->p); dev_free(ctx->partials);
+  for (int k = 0; k < Context::kNewtonWarm; ++k) { dev_free(ctx->newton_x[k]); ctx->newton_x_valid[k] = false; }
   plan_free(ctx->halo);
   ctx->loc2glob.clear(); ctx->elem_glob.clear(); ctx->Dset.clear();
   ctx->have_mesh = false; ctx->base_ready = false; ctx->ddpe_active = false; ctx->local_ingest = false;
@@ -483,13 +484,24 @@ int newton_loop(Context* ctx, bool semlin, double delta, double tol, const doubl
     // reference's direct solve, a linear problem converges in one step); newton_eta is a relative floor.
     ctx->amg_kind = count == 0 ? 0 : 3;
     ctx->eps_e = eps_e;
-    rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, false, ctx->opts.newton_eta, 0.1 * tol,
+    // Gummel loop: the k-th correction of this Vsolve starts from the k-th correction of the previous one (they converge with
+    // the outer iteration; the stop rules -- absolute residual, error energy relative to the correction's -- are unchanged, so
+    // the Newton iterates and counts are the reference's; only the CG iteration counts shrink).  Not for solve_semlin: one loop.
+    const bool warm_slot = !semlin && ctx->ddpe_active && ctx->opts.warm_start && count < Context::kNewtonWarm;
+    const bool warm = warm_slot && ctx->newton_x_valid[count];
+    if (warm) DDPS_CUDA(cudaMemcpyAsync(ctx->x, ctx->newton_x[count], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = solve_system(ctx, ctx->val_op, ctx->dinv, ctx->resid, ctx->x, warm, ctx->opts.newton_eta, 0.1 * tol,
                       ctx->opts.lin_max_it, nullptr, nullptr);                               // src:394, 1063
     ctx->amg_kind = -1;
     ctx->eps_e = 0.0;
     tp.stop();
     ctx->stats.t_pcg_ms += tp.ms();
     if (rc) return rc;
+    if (warm_slot) {
+      if (!ctx->newton_x[count]) DDPS_CUDA(cudaMalloc(&ctx->newton_x[count], std::max<size_t>(n, 1) * sizeof(double)));
+      DDPS_CUDA(cudaMemcpyAsync(ctx->newton_x[count], ctx->x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      ctx->newton_x_valid[count] = true;
+    }
     if (damp) DDPS_CUDA(cudaMemcpyAsync(ctx->Unew, ctx->V, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     if ((rc = launch_axpy(ctx, -1.0, ctx->x, ctx->V, n))) return rc;                         // src:395, 1064
     if ((rc = halo_exchange(ctx, ctx->V))) return rc;
@@ -1209,6 +1221,7 @@ int ddps_ddpe_begin(ddps_ctx* ctx, int rec_mode, double delta, double tau_p, dou
   DDPS_CUDA(cudaMemsetAsync(ctx->W, 0, bytes, ctx->stream));
   DDPS_CUDA(cudaMemsetAsync(ctx->V, 0, bytes, ctx->stream));
   DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < Context::kNewtonWarm; ++k) ctx->newton_x_valid[k] = false;   // a new solve: no earlier corrections
   ctx->ddpe_active = true;
   return DDPS_OK;
 }

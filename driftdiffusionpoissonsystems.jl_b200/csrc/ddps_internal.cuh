@@ -255,6 +255,12 @@ struct Context {
   PcgScalars* scal = nullptr;                               // device
   PcgScalars* scal_host = nullptr;                          // pinned
 
+  // Newton corrections of the previous Vsolve, by Newton step: initial guesses of the same step's linear solve in the next Gummel
+  // iteration (opts.warm_start; the Newton iterates themselves still restart from V = 0, src:311)
+  static constexpr int kNewtonWarm = 8;
+  double* newton_x[kNewtonWarm] = {nullptr};
+  bool newton_x_valid[kNewtonWarm] = {false};
+
   // ddpe state
   bool ddpe_active = false;
   int rec_mode = 0;

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kVecBlock, 8) k_pcg_direction(int n, int par, 
     if (scal->eps_e2 > 0.0) {
       scal->hs_ring[it % scal->hs_d] = hs_term;
       scal->hs_total = hs_tot;
-      if (stop) scal->e_ref = fmax(scal->e_ref, hs_tot);   // later corrections of the same Newton loop refer to the largest one
+      if (stop) scal->e_ref = fmax(scal->e_ref, fmax(hs_tot, fabs(scal->xb)));   // later corrections of the same Newton loop refer to the largest one (a warm-started one counts with its full size)
     }
     if (conv) scal->conv = 1;
     if (stop) scal->done = 1;

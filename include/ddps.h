@@ -99,7 +99,9 @@ typedef struct ddps_solver_opts {
   int32_t max_newton;   /* Newton cap per solve, 0 = 1000 (the reference has none, src:368,1040) */
   int32_t max_gummel;   /* Gummel cap, 0 = 1000 (the reference has none, src:649) */
   int32_t check_every;  /* PCG iterations between host polls of the device-side done flag (default 32) */
-  int32_t warm_start;   /* 1: continuity solves start PCG from the previous iterate (same solution) (default 1) */
+  int32_t warm_start;   /* 1: linear solves start PCG from what the previous Gummel iteration found -- the continuity solves from
+                           the previous iterate, the k-th Newton correction of a Vsolve from the k-th correction of the previous
+                           Vsolve (same solutions, same Newton iterates and counts: only fewer CG iterations) (default 1) */
   int32_t verbose;      /* 1: print "iteration k, tolerance: c" lines like src:655,1093 */
   int32_t lin_cap_ok;   /* 1: PCG / Newton solves that hit their caps are accepted instead of failing (profiling runs only) */
   int32_t no_alt_traversal; /* 1: disable the alternating traversal direction of the PCG kernels (A/B timing) */
