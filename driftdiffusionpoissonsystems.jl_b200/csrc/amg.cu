@@ -980,6 +980,53 @@ int amg_install_transfers(Context* ctx, AmgLevelDev& L, const AmgHostLevel& HL) 
 // coarsened on the device (amg_setup.cu: only the strong-neighbour lists travel to the host for the greedy
 // aggregation); the small rest of the hierarchy is built by the host reference implementation (amg_host.cu) and
 // uploaded.  DDPS_AMG_HOST_SETUP=1 forces the host path for every level (A/B and fallback).
+// Damping of the cycle's Jacobi sweeps.  omega * rho(D^-1 A) < 2 keeps the sweep convergent and the V-cycle symmetric positive
+// definite; the Gershgorin bound rho_G = max_i sum_j |a_ij| / a_ii of the BASE operator (2 for the stiffness matrix of an acute mesh:
+// an M-matrix with zero row sums) is computed once per hierarchy, and omega = min(0.8, 1.6 / rho_G): 0.8 is the optimal point-Jacobi
+// damping of the 5-point / P1 stencil (smoothing factor 0.6 instead of 0.78 at 2/3), meshes with obtuse triangles (positive
+// off-diagonals, rho_G > 2) get less.  Measured at 16.8M triangles: 501 -> 459 CG iterations per solve.  The prolongator smoothing
+// keeps prm.omega = 2/3.
+__global__ void k_amg_gershgorin(int nrows, const int* __restrict__ slice_ptr, const double* __restrict__ val,
+                                 const unsigned short* __restrict__ rowinfo, double* partials, PcgScalars* scal) {
+  __shared__ double sh_red[32];
+  double m = 0.0;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x) {
+    const int base = slice_ptr[row >> 5] + (row & 31);
+    const int len = rowinfo[row] >> 5, sd = rowinfo[row] & 31;
+    double sum = 0.0, d = 0.0;
+    for (int k = 0; k < len; ++k) {
+      const double v = val[base + 32 * k];
+      sum += fabs(v);
+      if (k == sd) d = v;
+    }
+    if (d > 0.0) m = fmax(m, sum / d);
+  }
+  double v[1] = {m}, tot[1];
+  if (grid_reduce<1, true>(v, partials, &scal->cnt[3], sh_red, tot)) {
+    if (threadIdx.x == 0) scal->sums[0] = tot[0];
+  }
+}
+
+static int amg_cycle_omega(Context* ctx, Amg* A, double fallback) {
+  if (const char* e = getenv("DDPS_AMG_OMEGA_CYCLE")) { A->omega = atof(e); return 0; }   // (experiments)
+  A->omega = fallback;
+  const Pattern& P = ctx->pat;
+  if (!P.rowinfo || !ctx->val_base) return 0;
+  int rc;
+  if (P.nrows > 0)
+    k_amg_gershgorin<<<amg_grid(ctx, P.nrows, 256), 256, 0, ctx->stream>>>(P.nrows, P.slice_ptr, ctx->val_base, P.rowinfo, ctx->partials, ctx->scal);
+  else
+    DDPS_CUDA(cudaMemsetAsync(&ctx->scal->sums[0], 0, sizeof(double), ctx->stream));
+  ctx->stats.kernel_launches++;
+  if ((rc = comm_allreduce(ctx, &ctx->scal->sums[0], 1, COMM_MAX))) return rc;   // (collective; no-op on one rank)
+  double rho = 0.0;
+  DDPS_CUDA(cudaMemcpyAsync(&rho, &ctx->scal->sums[0], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DDPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (rho > 0.0 && rho == rho) A->omega = std::min(0.8, 1.6 / rho);
+  if (getenv("DDPS_AMG_TIMING") && ctx->rank == 0) fprintf(stderr, "[ddps amg] Gershgorin bound of D^-1 A (base operator) %.4f -> cycle damping %.4f\n", rho, A->omega);
+  return 0;
+}
+
 static int amg_finish_setup(Context* ctx, Amg* A, int nlev, double t0);
 
 // Multi-rank contexts: distributed coarsening (amg_setup.cu: amg_dist_coarsen) while the level has more than DDPS_AMG_TAIL
@@ -994,9 +1041,9 @@ static int amg_setup_dist(Context* ctx) {
   const bool timing = getenv("DDPS_AMG_TIMING") != nullptr;
   Amg* A = new Amg();
   ctx->amg = A;
-  A->omega = prm.omega;
   A->prof.on = getenv("DDPS_PROFILE_ITER") != nullptr;
   int rc;
+  if ((rc = amg_cycle_omega(ctx, A, prm.omega))) return rc;
   {
     AmgLevelDev& L = A->lv[0];
     L.n = P.nrows; L.n_loc = ctx->n_loc; L.nnz = P.nnz; L.nslices = P.nslices; L.nentries = P.nentries; L.wmax = P.max_row_len;
@@ -1054,9 +1101,9 @@ int amg_setup(Context* ctx) {
 
   Amg* A = new Amg();
   ctx->amg = A;
-  A->omega = prm.omega;
   A->prof.on = getenv("DDPS_PROFILE_ITER") != nullptr;
   int rc;
+  if ((rc = amg_cycle_omega(ctx, A, prm.omega))) return rc;
   {
     AmgLevelDev& L = A->lv[0];
     L.n = n; L.nnz = P.nnz; L.nslices = P.nslices; L.nentries = P.nentries; L.wmax = P.max_row_len;

@@ -62,3 +62,15 @@ def pcg(A, b, M, rtol=1e-13, maxit=2000):
         p = z + (rz_new / rz) * p
         rz = rz_new
     return x, maxit
+
+
+def cycle_omega(base):
+    """Damping of the cycle's Jacobi sweeps as the library chooses it (csrc/amg.cu amg_cycle_omega): min(0.8, 1.6 / rho_G) with the
+    Gershgorin bound rho_G = max_i sum_j |a_ij| / a_ii of the BASE operator (2 for the stiffness matrix of an acute mesh)."""
+    import numpy as np
+    A = base.tocsr()
+    d = A.diagonal()
+    rs = np.asarray(abs(A).sum(axis=1)).ravel()
+    ok = d > 0
+    return min(0.8, 1.6 / float(np.max(rs[ok] / d[ok])))
+

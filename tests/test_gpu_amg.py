@@ -102,7 +102,7 @@ def test_device_hierarchy_matches_restatement(D, which, setup, monkeypatch):
         rng = np.random.default_rng(1)
         r = rng.standard_normal(mesh.nq)
         z = s.amg_apply(r)
-        zr = amg_ref.vcycle(ops, Ps, r)
+        zr = amg_ref.vcycle(ops, Ps, r, omega=amg_ref.cycle_omega(MV))
         assert rel_max(z, zr) <= 1e-10
         # run to run bitwise identical
         s.amg_numeric()
@@ -118,6 +118,7 @@ def test_fp32_cycle_matrices(D, monkeypatch):
     V, u, v = smooth_fields(mesh, 9)
     with _session(D, mesh, pr) as s:
         s.debug_assemble_base(False)
+        om = amg_ref.cycle_omega(s.get_csr(0))
         levels = s.amg_hierarchy()
         assert levels[0]["n"] > 1000 and levels[1]["n"] > 1000
         s.debug_assemble_uv(1, "shockley", 1.0, 1.0, V, u, v)
@@ -127,8 +128,8 @@ def test_fp32_cycle_matrices(D, monkeypatch):
         ops, Ps = amg_ref.operator_levels(A, levels)
         r = np.random.default_rng(2).standard_normal(mesh.nq)
         z = s.amg_apply(r)
-        assert rel_max(z, amg_ref.vcycle(ops, Ps, r, fp32_min=1000)) <= 1e-10
-        assert rel_max(z, amg_ref.vcycle(ops, Ps, r)) > 1e-12          # it really is the fp32 copy that ran
+        assert rel_max(z, amg_ref.vcycle(ops, Ps, r, omega=om, fp32_min=1000)) <= 1e-10
+        assert rel_max(z, amg_ref.vcycle(ops, Ps, r, omega=om)) > 1e-12          # it really is the fp32 copy that ran
         x, it, _ = s.debug_pcg(b, rtol=1e-13)
         assert rel_l2(x, spla.spsolve(A.tocsc(), b)) <= 1e-10 and it <= 40
 
