@@ -276,3 +276,28 @@ def test_fused_cycle_tail_equals_per_level_launches(D, monkeypatch):
     for a, b in zip(out["fused"][:3], out["per_level"][:3]):
         assert rel_l2(a, b) <= 1e-10, rel_l2(a, b)
     assert sf["kernel_launches"] < 0.8 * sp_["kernel_launches"], (sf["kernel_launches"], sp_["kernel_launches"])
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_warm_started_newton_corrections(D, O, precond):
+    """opts.warm_start = 1 (default): the k-th Newton correction of a Vsolve starts its CG from the k-th correction of the previous
+    Gummel iteration (the Newton iterates still restart from V = 0, src:311), the continuity solves from the previous iterate.
+    Only the CG iteration counts change: same fields (north-star tolerance against the oracle, far closer to each other), same
+    Gummel / Newton counts and control history."""
+    mesh = D.structured_mesh(160, 80, 0.0, 2.0, 0.0, 1.0)
+    pr = D.problems.pn_junction([2, 4], [1, 2, 3, 4], x_junction=1.0, C0=1.0, U=0.3)
+    ref = O.solve_ddpe(oracle_mesh(mesh), *[pr[k] for k in KEYS])
+    out = {}
+    for warm in (1, 0):
+        with D.Session(0, precond=precond, warm_start=warm) as s:
+            V, u, v, st = D.solve_ddpe(mesh, *[pr[k] for k in KEYS], session=s, return_stats=True, verbose=False)
+        out[warm] = (V, u, v, st)
+        for a, b in zip((V, u, v), ref):
+            assert rel_l2(a, b) <= FIELD_TOL
+    sw, sc = out[1][3], out[0][3]
+    assert sw["outer_iters"] == sc["outer_iters"]
+    assert [int(k) for k in sw["newton_per_vsolve"]] == [int(k) for k in sc["newton_per_vsolve"]]
+    assert np.allclose(sw["control_history"], sc["control_history"], rtol=1e-6, atol=1e-10)   # (update norms down to tol = 1e-9; the fields agree to a few 1e-10)
+    for a, b in zip(out[1][:3], out[0][:3]):
+        assert rel_l2(a, b) <= 5e-9, rel_l2(a, b)
+    assert sw["pcg_total"] < 0.85 * sc["pcg_total"], (sw["pcg_total"], sc["pcg_total"])
