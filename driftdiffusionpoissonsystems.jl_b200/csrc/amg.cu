@@ -1236,7 +1236,10 @@ static int amg_finish_setup(Context* ctx, Amg* A, int nlev, double t0) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_amg_tail, 256, 0);
     if (coop && per_sm >= 1 && nlev - lt >= 2) {   // (a tail of the coarsest level alone is the dense solve: nothing to fuse)
       A->tail_from = lt;
-      A->tail_grid = ctx->num_sms;
+      // two CTAs per SM (measured at S16: 0.819 ms per CG iteration; one per SM 0.825, four 0.830, 64 CTAs in all 0.844): the phases are
+      // latency-bound, more warps hide more of it until the barrier's cost takes over.  In-process ranks share one device: one per SM.
+      A->tail_grid = (per_sm >= 2 && !ctx->lgroup) ? 2 * ctx->num_sms : ctx->num_sms;
+      if (const char* e = getenv("DDPS_AMG_TAIL_GRID")) A->tail_grid = std::max(1, std::min(ctx->num_sms * per_sm, atoi(e)));   // (experiments)
       if (!A->tail_bar && (rc = amg_alloc(ctx, &A->tail_bar, 2))) return rc;
       DDPS_CUDA(cudaMemsetAsync(A->tail_bar, 0, 2 * sizeof(unsigned), ctx->stream));
     }
