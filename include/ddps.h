@@ -274,7 +274,8 @@ int ddps_debug_pcg(ddps_ctx* ctx, const double* rhs, double* x, double rtol, int
  * (opts.precond = DDPS_PRECOND_AMG); 7: the per-operator multigrid numeric phase (Galerkin products on all levels +
  * coarsest inverse); 8: one V-cycle alone; single kernels of the multigrid iteration on the finest level: 9 residual SpMV
  * t = b - A x, 10 smoothing-sweep SpMV fused with r.z, 11 the CG update kernel (x, r, first sweep), 12 restriction to level 1,
- * 13 prolongation from level 1 (kernel 6 reports the summed algorithmic bytes of the whole iteration).
+ * 13 prolongation from level 1 (kernel 6 reports the summed algorithmic bytes of the whole iteration); 14 / 15 the nodal prep pass
+ * of the Newton-system / continuity-system assembly alone (kernels 1 and 3 time the prep pass and the assembly kernel together).
  * Runs `reps` launches after `warm` untimed ones and returns the mean milliseconds per launch and
  * the algorithmic bytes of one launch (definition in DESIGN.md). */
 int ddps_time_kernel(ddps_ctx* ctx, int kernel, int warm, int reps, double* ms_per_launch, double* algo_bytes);
